@@ -1,0 +1,307 @@
+"""Benchmark of the plane-sweep depth-inference hot path (BASELINE.json metric: fusionnet depth frames/sec at
+256x256 with 64 planes; warp+correlate HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one fusionnet keyframe (config c2: 256x256, D=64, 2 measurement frames, recurrent state carried, hidden-
+state warp on) for each of the B independent clips a rank holds (B=1 = BASELINE.json configs[1]); clips are sharded
+across ranks with no data-path collective (weak scaling: per-GPU work fixed).  One JSON line is printed by rank 0:
+  value      frames/s, all ranks, inputs resident in HBM, timed with CUDA events (L2 flushed between steps)
+  e2e        same metric through the reference-facing modules with HOST (pinned) inputs and a host read of the depth
+  roofline   the fused plane-sweep kernel timed alone against the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle (CPU restatement of the reference) on the box's host cores, bounded sample
+`--impl reference` times that CPU path alone (the reference is pure PyTorch-CPU; there is nothing to pip-install).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for _p in (REPO, os.path.join(REPO, "deep-video-mvs_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H, W, D, M = 256, 256, 64, 2
+WORKLOAD = "fusionnet inference 256x256, 64 planes, 2 measurement frames, batch=%d clip(s)/GPU (BASELINE.json configs[1])"
+SWEEP_BYTES_PER_CLIP = ((1 + M) * 32 + D) * (H // 2) * (W // 2) * 4        # 10,485,760 B at c2
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------- workload
+def make_inputs(n_clips, n_frames, rank):
+    import synth_data as synth
+    clips = [synth.make_clip(1000 * rank + c, n_frames, H, W, M) for c in range(n_clips)]
+    return clips
+
+
+def stack_frame(clips, t):
+    """Batched tensors (numpy) for keyframe t of every clip of this rank."""
+    ref = np.stack([c["images"][c["frames"][t][0]] for c in clips])
+    rpose = np.stack([c["poses"][c["frames"][t][0]] for c in clips])
+    meas = [np.stack([c["images"][c["frames"][t][1][m]] for c in clips]) for m in range(M)]
+    mpose = [np.stack([c["poses"][c["frames"][t][1][m]] for c in clips]) for m in range(M)]
+    K = np.stack([c["K"] for c in clips])
+    return ref, rpose, meas, mpose, K
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import synth_data as synth
+    from dvmvs import _native
+    from dvmvs.fusionnet.model import CostVolumeDecoder, CostVolumeEncoder, FeatureExtractor, FeatureShrinker, LSTMFusion
+    from dvmvs.utils import cost_volume_fusion
+    from dvmvs import pipeline
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B = args.clips
+    n_frames = args.warmup + args.steps
+    clips = make_inputs(B, n_frames, rank)
+
+    # random-init weights of the reference architecture (no checkpoints offline): seeded, He-scaled (synth_data.py)
+    mods = {"fe": FeatureExtractor(), "fpn": FeatureShrinker(), "cve": CostVolumeEncoder(), "lstm": LSTMFusion(), "cvd": CostVolumeDecoder()}
+    for tag, m in mods.items():
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes, seed=7).items()}, strict=True)
+        m.to(dev).eval()
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---------------- device-resident arm
+    frames_dev = []
+    for t in range(n_frames):
+        ref, rpose, meas, mpose, K = stack_frame(clips, t)
+        frames_dev.append((torch.from_numpy(ref).to(dev), torch.from_numpy(rpose).to(dev), [torch.from_numpy(x).to(dev) for x in meas],
+                           [torch.from_numpy(p).to(dev) for p in mpose], torch.from_numpy(K).to(dev)))
+    state = pipeline.KeyframeState()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    with torch.no_grad():
+        for t in range(args.warmup):
+            _, state = pipeline.keyframe(mods, state, *frames_dev[t], n_depth_levels=D)
+        torch.cuda.synchronize()
+        barrier()
+        sampler.start()
+        launches0 = _native.launch_count()
+        wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()
+            ev[i][0].record()
+            pred, state = pipeline.keyframe(mods, state, *frames_dev[args.warmup + i], n_depth_levels=D)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        wall1 = time.perf_counter()
+        barrier()
+    launches = _native.launch_count() - launches0
+    clocks = sampler.summary()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    assert bool(torch.isfinite(pred).all()), "non-finite depth"
+
+    # ---------------- end-to-end arm: pinned host inputs -> modules -> host depth, copies inside the timed region
+    frames_host = []
+    for t in range(n_frames):
+        ref, rpose, meas, mpose, K = stack_frame(clips, t)
+        frames_host.append(tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (ref, rpose, *meas, *mpose, K)))
+    h2d_bytes = sum(a.numel() * 4 for a in frames_host[0])
+    out_host = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    d2h_bytes = out_host.numel() * 4
+    state = pipeline.KeyframeState()
+
+    def e2e_step(t, state):
+        hs = [a.to(dev, non_blocking=True) for a in frames_host[t]]
+        ref, rpose, meas, mpose, K = hs[0], hs[1], hs[2:2 + M], hs[2 + M:2 + 2 * M], hs[2 + 2 * M]
+        pred, state = pipeline.keyframe(mods, state, ref, rpose, meas, mpose, K, n_depth_levels=D)
+        out_host.copy_(pred, non_blocking=True)
+        return state
+
+    with torch.no_grad():
+        for t in range(args.warmup):
+            state = e2e_step(t, state)
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            state = e2e_step(args.warmup + i, state)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # ---------------- roofline of the dominant geometric kernel: fused plane sweep, timed alone
+    from dvmvs import _ops as ops
+    f1 = torch.randn(B, H // 2, W // 2, 32, device=dev) * 4
+    f2 = [torch.randn(B, H // 2, W // 2, 32, device=dev) * 4 for _ in range(M)]
+    ref, rpose, meas, mpose, K = frames_dev[0]
+    half_K = K.clone()
+    half_K[:, 0:2, :] /= 2.0
+    sw_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+    for i in range(3):
+        ops.plane_sweep(f1, f2, rpose, mpose, half_K, 0.25, 20.0, D, True)
+    for a, b in sw_ev:
+        flush.zero_()
+        a.record()
+        ops.plane_sweep(f1, f2, rpose, mpose, half_K, 0.25, 20.0, D, True)
+        b.record()
+    torch.cuda.synchronize()
+    sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in sw_ev]))
+
+    # ---------------- max over ranks
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_frames = B * args.steps * world
+    peaks, peak_src = measured_peaks()
+    achieved = SWEEP_BYTES_PER_CLIP * B / (sweep_ms * 1e-3) / 1e9
+    result = {
+        "metric": "fusionnet depth frames/sec @256x256x64planes", "value": total_frames / (dev_ms * 1e-3), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD % B, "clips_per_gpu": B, "height": H, "width": W, "planes": D, "measurement_frames": M,
+                   "weights": "random-init (seeded) reference architecture", "l2": "flushed (256 MiB write) between timed steps",
+                   "parallelism": "clip-sharded x%d, no data-path collective" % world, "host_loop_wall_ms_per_step": (wall1 - wall0) * 1e3 / args.steps},
+        "clocks": clocks,
+        "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+        "gpu_launches": int(lt[0]),
+        "roofline": {"kernel": "plane_sweep_c32_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src, "ms_per_launch": sweep_ms,
+                     "algorithmic_bytes_per_launch": SWEEP_BYTES_PER_CLIP * B,
+                     "note": "52 FLOP/B of fp32 FMA work per algorithmic byte: CUDA-core/L1-gather bound before HBM (DESIGN.md)"},
+    }
+    return result
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arms
+def cpu_baseline(n_frames, threads):
+    """The oracle (restatement of the reference's PyTorch-CPU path) on the host cores: a bounded sample of the same
+    workload (n_frames recurrent keyframes of ONE c2 clip, after one warm-up frame)."""
+    import synth_data as synth
+    from oracle import dvmvs_oracle as oracle
+    torch.set_num_threads(threads)
+    shapes = oracle.state_dict_shapes(D)
+    w = {tag: {k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes[tag], seed=7).items()} for tag in shapes}
+    clip = synth.make_clip(0, n_frames + 1, H, W, M)
+    K = torch.from_numpy(clip["K"])[None]
+    st = oracle.FusionnetState()
+    times = []
+    with torch.no_grad():
+        for ref_i, meas_i in clip["frames"]:
+            t0 = time.perf_counter()
+            _, st = oracle.fusionnet_step(w, st, torch.from_numpy(clip["images"][ref_i])[None], torch.from_numpy(clip["poses"][ref_i])[None],
+                                          [torch.from_numpy(clip["images"][j])[None] for j in meas_i],
+                                          [torch.from_numpy(clip["poses"][j])[None] for j in meas_i], K, n_depth_levels=D)
+            times.append(time.perf_counter() - t0)
+    times = times[1:]
+    return {"value": len(times) / sum(times), "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": "%d recurrent keyframes of one c2 clip (256x256, D=64, M=2) after 1 warm-up, torch %s CPU, %d threads"
+                      % (len(times), torch.__version__, threads)}
+
+
+def run_reference(args):
+    threads = os.cpu_count() or 1
+    per_step = 2
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    base = cpu_baseline(max(2, min(args.steps, 8) * per_step // 2), threads)
+    wall = time.perf_counter() - t0
+    fps = base["value"]
+    base["value"] = fps
+    return {"impl": "reference", "metric": "fusionnet depth frames/sec @256x256x64planes", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / fps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD % 1, "height": H, "width": W, "planes": D, "measurement_frames": M,
+                       "note": "reference's own PyTorch-CPU path (oracle port; the reference has no compiled code), wall %.1f s" % wall},
+            "cpu_baseline": base, "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--clips", type=int, default=1, help="independent clips per GPU (batched through the modules)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=6, help="frames of the bounded CPU-baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference(args)))
+        return 0
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    result = run_ours(args, rank, world, local_rank)
+    if rank == 0:
+        result["cpu_baseline"] = cpu_baseline(args.cpu_frames, os.cpu_count() or 1)
+        print(json.dumps(result))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,533 @@
+// Convolution-stack kernels, fp32 CUDA-core path (exact fp32 arithmetic; also the on-device cross-check of
+// the tcgen05 implicit-GEMM path).  Channel-last activations.  sm_100a.
+//
+// Replaces (reference root relative): dvmvs/layers.py:39-65 conv_layer / depth_layer_3x3,
+// dvmvs/fusionnet/model.py:15-119 building blocks (torch.cat / F.interpolate fused into the input loader),
+// torchvision MnasNet _InvertedResidual depthwise convs and FeaturePyramidNetwork's top-down add.
+#include "common.cuh"
+
+namespace dvmvs {
+
+// =====================================================================================================
+// Generic direct convolution
+// =====================================================================================================
+constexpr int TH = 8, TW = 16;    // output-pixel tile
+constexpr int TN = 32;            // output-channel tile
+constexpr int CK = 8;             // input-channel chunk
+constexpr int kConvThreads = 128; // 8 channel groups (x4) x 16 pixel groups (x8 pixels along x)
+
+struct ConvParams {
+  dvmvs_conv_desc d;
+  int Hout, Wout, Cin, tiles_x, tiles_y, ksplit, chunks_total;
+  int src_cin_offset[3];
+};
+
+__host__ __device__ constexpr int patch_h(int ks, int s) { return (TH - 1) * s + ks; }
+__host__ __device__ constexpr int patch_w(int ks, int s) { return (TW - 1) * s + ks; }
+__host__ __device__ constexpr int plane_stride(int ks, int s) {
+  // >= PH*PW and == 4 (mod 32): the transposing smem fill (lane -> (ck, pixel)) is then bank-conflict free
+  return ((patch_h(ks, s) * patch_w(ks, s) - 4 + 31) / 32) * 32 + 4;
+}
+
+// value of source `s` at input-resolution pixel (iy, ix), channel c (fuses F.interpolate x2 bilinear,
+// align_corners=True: ATen upsample_bilinear2d arithmetic)
+__device__ __forceinline__ float fetch_src(const dvmvs_conv_desc& d, int s, int b, int iy, int ix, int c) {
+  const int Cs = d.src_channels[s];
+  const float* src = d.src[s];
+  if (d.src_mode[s] == DVMVS_SRC_DIRECT) return __ldg(src + (((size_t)b * d.Hin + iy) * d.Win + ix) * Cs + c);
+  const int Hs = d.Hin >> 1, Ws = d.Win >> 1;
+  const float sh = (d.Hin > 1) ? (float)(Hs - 1) / (float)(d.Hin - 1) : 0.f;
+  const float sw = (d.Win > 1) ? (float)(Ws - 1) / (float)(d.Win - 1) : 0.f;
+  const float fy = sh * iy, fx = sw * ix;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < Hs - 1), x1 = x0 + (x0 < Ws - 1);
+  const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float* base = src + (size_t)b * Hs * Ws * Cs + c;
+  const float v00 = __ldg(base + ((size_t)y0 * Ws + x0) * Cs), v01 = __ldg(base + ((size_t)y0 * Ws + x1) * Cs);
+  const float v10 = __ldg(base + ((size_t)y1 * Ws + x0) * Cs), v11 = __ldg(base + ((size_t)y1 * Ws + x1) * Cs);
+  return ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == DVMVS_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == DVMVS_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+__device__ __forceinline__ float residual_at(const dvmvs_conv_desc& d, int Hout, int Wout, int b, int oy, int ox, int c) {
+  if (d.residual_mode == DVMVS_RES_SAME) return __ldg(d.residual + (((size_t)b * Hout + oy) * Wout + ox) * d.Cout + c);
+  const int ry = (int)(((long long)oy * d.Hr) / Hout), rx = (int)(((long long)ox * d.Wr) / Wout);   // nearest (FPN top-down)
+  return __ldg(d.residual + (((size_t)b * d.Hr + ry) * d.Wr + rx) * d.Cout + c);
+}
+
+template <int KS, int STRIDE>
+__global__ void __launch_bounds__(kConvThreads) conv2d_direct_kernel(ConvParams p) {
+  constexpr int PH = patch_h(KS, STRIDE), PW = patch_w(KS, STRIDE), PLANE = plane_stride(KS, STRIDE);
+  constexpr int PAD = (KS - 1) / 2;
+  constexpr int NIV = 7 * STRIDE + KS;
+  extern __shared__ __align__(16) float smem[];
+  float* s_in = smem;                    // [CK][PLANE]
+  float* s_w = smem + CK * PLANE;        // [KS*KS][CK][TN]
+
+  const dvmvs_conv_desc& d = p.d;
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, ty = tid >> 3;
+  const int r = ty >> 1, x0 = (ty & 1) * 8;
+  const int tile = blockIdx.x;
+  const int ty_t = tile / p.tiles_x, tx_t = tile - ty_t * p.tiles_x;
+  const int oy0 = ty_t * TH, ox0 = tx_t * TW;
+  const int n0 = blockIdx.y * TN;
+  const int b = blockIdx.z / p.ksplit, split = blockIdx.z - b * p.ksplit;
+
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[j][n] = 0.f;
+
+  // chunk range of this split
+  const int per = (p.chunks_total + p.ksplit - 1) / p.ksplit;
+  const int chunk_begin = split * per, chunk_end = min(p.chunks_total, chunk_begin + per);
+
+  int chunk = 0;
+  for (int s = 0; s < d.n_src; ++s) {
+    const int Cs = d.src_channels[s];
+    for (int c0 = 0; c0 < Cs; c0 += CK, ++chunk) {
+      if (chunk < chunk_begin || chunk >= chunk_end) continue;
+      const int nvalid = min(CK, Cs - c0);
+      __syncthreads();   // previous chunk's compute done before overwrite
+      // ---- input patch (transposed to [ck][pixel])
+      for (int idx = tid; idx < PH * PW * CK; idx += kConvThreads) {
+        const int ck = idx & (CK - 1);
+        const int pp = idx >> 3;
+        const int py = pp / PW, px = pp - py * PW;
+        const int iy = oy0 * STRIDE - PAD + py, ix = ox0 * STRIDE - PAD + px;
+        float v = 0.f;
+        if (ck < nvalid && iy >= 0 && iy < d.Hin && ix >= 0 && ix < d.Win) v = fetch_src(d, s, b, iy, ix, c0 + ck);
+        s_in[ck * PLANE + pp] = v;
+      }
+      // ---- weights [tap][ck][TN]
+      const int cin0 = p.src_cin_offset[s] + c0;
+      if ((d.Cout & 3) == 0) {
+        for (int idx = tid; idx < KS * KS * CK * (TN / 4); idx += kConvThreads) {
+          const int n4 = idx & (TN / 4 - 1);
+          const int ck = (idx >> 3) & (CK - 1);
+          const int tap = idx >> 6;
+          float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ck < nvalid && n0 + n4 * 4 < d.Cout)
+            wv = __ldg(reinterpret_cast<const float4*>(d.weight + ((size_t)tap * p.Cin + cin0 + ck) * d.Cout + n0 + n4 * 4));
+          *reinterpret_cast<float4*>(s_w + (tap * CK + ck) * TN + n4 * 4) = wv;
+        }
+      } else {
+        for (int idx = tid; idx < KS * KS * CK * TN; idx += kConvThreads) {
+          const int n = idx & (TN - 1);
+          const int ck = (idx >> 5) & (CK - 1);
+          const int tap = idx >> 8;
+          float wv = 0.f;
+          if (ck < nvalid && n0 + n < d.Cout) wv = __ldg(d.weight + ((size_t)tap * p.Cin + cin0 + ck) * d.Cout + n0 + n);
+          s_w[(tap * CK + ck) * TN + n] = wv;
+        }
+      }
+      __syncthreads();
+      // ---- compute
+#pragma unroll 1
+      for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll 2
+        for (int ck = 0; ck < CK; ++ck) {
+          const float* inrow = s_in + ck * PLANE + (r * STRIDE + ky) * PW + x0 * STRIDE;
+          float iv[NIV];
+#pragma unroll
+          for (int i = 0; i < NIV; ++i) iv[i] = inrow[i];
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) {
+            const float4 wv = *reinterpret_cast<const float4*>(s_w + ((ky * KS + kx) * CK + ck) * TN + tx * 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a = iv[j * STRIDE + kx];
+              acc[j][0] = fmaf(a, wv.x, acc[j][0]);
+              acc[j][1] = fmaf(a, wv.y, acc[j][1]);
+              acc[j][2] = fmaf(a, wv.z, acc[j][2]);
+              acc[j][3] = fmaf(a, wv.w, acc[j][3]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue
+  const int oy = oy0 + r;
+  if (oy >= p.Hout) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ox = ox0 + x0 + j;
+    if (ox >= p.Wout) continue;
+    const size_t o = (((size_t)b * p.Hout + oy) * p.Wout + ox) * d.Cout;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int c = n0 + tx * 4 + n;
+      if (c >= d.Cout) continue;
+      if (p.ksplit > 1) {
+        atomicAdd(d.out + o + c, acc[j][n]);
+      } else {
+        float v = acc[j][n];
+        if (d.bias) v += __ldg(d.bias + c);
+        if (d.residual_mode != DVMVS_RES_NONE) v += residual_at(d, p.Hout, p.Wout, b, oy, ox, c);
+        v = apply_act(v, d.act);
+        d.out[o + c] = v;
+        if (d.aux_out) d.aux_out[o + c] = 1.f / (d.aux_mult * v + d.aux_base);
+      }
+    }
+  }
+}
+
+// bias / residual / activation pass for split-K launches (in place on the accumulated sums)
+__global__ void conv_epilogue_kernel(ConvParams p) {
+  const dvmvs_conv_desc& d = p.d;
+  const size_t total = (size_t)d.B * p.Hout * p.Wout * d.Cout;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % d.Cout);
+  const size_t pix = idx / d.Cout;
+  const int ox = (int)(pix % p.Wout);
+  const int oy = (int)((pix / p.Wout) % p.Hout);
+  const int b = (int)(pix / ((size_t)p.Wout * p.Hout));
+  float v = d.out[idx];
+  if (d.bias) v += __ldg(d.bias + c);
+  if (d.residual_mode != DVMVS_RES_NONE) v += residual_at(d, p.Hout, p.Wout, b, oy, ox, c);
+  v = apply_act(v, d.act);
+  d.out[idx] = v;
+  if (d.aux_out) d.aux_out[idx] = 1.f / (d.aux_mult * v + d.aux_base);
+}
+
+// Single-output-channel 3x3 head (depth_layer_3x3): a quarter warp per output pixel, 128-byte channel reads.
+__global__ void __launch_bounds__(256) conv_head_kernel(ConvParams p) {
+  const dvmvs_conv_desc& d = p.d;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 7, quad = lane >> 3;
+  const size_t npix = (size_t)d.B * p.Hout * p.Wout;
+  const size_t pix = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + quad;
+  const bool active = pix < npix;
+  const size_t pc = active ? pix : 0;
+  const int ox = (int)(pc % p.Wout);
+  const int oy = (int)((pc / p.Wout) % p.Hout);
+  const int b = (int)(pc / ((size_t)p.Wout * p.Hout));
+  const int C = p.Cin;
+  float acc = 0.f;
+  if (active) {
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy + ky - 1;
+      if (iy < 0 || iy >= d.Hin) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox + kx - 1;
+        if (ix < 0 || ix >= d.Win) continue;
+        const float* xp = d.src[0] + (((size_t)b * d.Hin + iy) * d.Win + ix) * C;
+        const float* wp = d.weight + (size_t)(ky * 3 + kx) * C;
+        for (int c = sub * 4; c < C; c += 32) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(xp + c));
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wp + c));
+          acc = fmaf(xv.x, wv.x, acc);
+          acc = fmaf(xv.y, wv.y, acc);
+          acc = fmaf(xv.z, wv.z, acc);
+          acc = fmaf(xv.w, wv.w, acc);
+        }
+      }
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (active && sub == 0) {
+    float v = acc + (d.bias ? __ldg(d.bias) : 0.f);
+    v = apply_act(v, d.act);
+    d.out[pix] = v;
+    if (d.aux_out) d.aux_out[pix] = 1.f / (d.aux_mult * v + d.aux_base);
+  }
+}
+
+template <int KS, int STRIDE>
+static int launch_conv(const ConvParams& p, cudaStream_t s) {
+  const size_t smem = (size_t)(CK * plane_stride(KS, STRIDE) + KS * KS * CK * TN) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv2d_direct_kernel<KS, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  dim3 grid(p.tiles_x * p.tiles_y, (p.d.Cout + TN - 1) / TN, p.d.B * p.ksplit);
+  conv2d_direct_kernel<KS, STRIDE><<<grid, kConvThreads, smem, s>>>(p);
+  return check_launch("conv2d_direct_kernel");
+}
+
+// =====================================================================================================
+// Depthwise convolution
+// =====================================================================================================
+__global__ void dwconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                              float* __restrict__ y, int B, int H, int W, int C, int Hout, int Wout, int ks, int stride, int act) {
+  const int c4n = C >> 2;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * Hout * Wout * c4n;
+  if (idx >= total) return;
+  const int cg = (int)(idx % c4n);
+  const size_t pix = idx / c4n;
+  const int ox = (int)(pix % Wout);
+  const int oy = (int)((pix / Wout) % Hout);
+  const int b = (int)(pix / ((size_t)Wout * Hout));
+  const int pad = ks >> 1;
+  float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int ky = 0; ky < ks; ++ky) {
+    const int iy = oy * stride - pad + ky;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < ks; ++kx) {
+      const int ix = ox * stride - pad + kx;
+      if (ix < 0 || ix >= W) continue;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + iy) * W + ix) * C) + cg);
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ky * ks + kx) * C) + cg);
+      acc.x = fmaf(xv.x, wv.x, acc.x);
+      acc.y = fmaf(xv.y, wv.y, acc.y);
+      acc.z = fmaf(xv.z, wv.z, acc.z);
+      acc.w = fmaf(xv.w, wv.w, acc.w);
+    }
+  }
+  if (act == DVMVS_ACT_RELU) {
+    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+  }
+  reinterpret_cast<float4*>(y + pix * C)[cg] = acc;
+}
+
+// =====================================================================================================
+// x2 bilinear upsampling (align_corners=True)
+// =====================================================================================================
+__global__ void upsample2x_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * Ho * Wo * C;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const size_t pix = idx / C;
+  const int ox = (int)(pix % Wo);
+  const int oy = (int)((pix / Wo) % Ho);
+  const int b = (int)(pix / ((size_t)Wo * Ho));
+  const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  const float sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const float fy = sh * oy, fx = sw * ox;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+  const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float* base = x + (size_t)b * H * W * C + c;
+  const float v00 = __ldg(base + ((size_t)y0 * W + x0) * C), v01 = __ldg(base + ((size_t)y0 * W + x1) * C);
+  const float v10 = __ldg(base + ((size_t)y1 * W + x0) * C), v11 = __ldg(base + ((size_t)y1 * W + x1) * C);
+  y[idx] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+}
+
+// =====================================================================================================
+// Layout: per batch, transpose the [R][Cc] matrix to [Cc][R] through a 32x33 shared tile
+// =====================================================================================================
+__global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const size_t boff = (size_t)blockIdx.z * R * Cc;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[i][threadIdx.x] = x[boff + (size_t)r * Cc + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) y[boff + (size_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+// =====================================================================================================
+// ConvLSTM gate epilogue (convlstm.py:45-59).  Block = 32 channels (lanes) x NW warps striding over pixels.
+// =====================================================================================================
+__device__ __forceinline__ float celu1(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+constexpr int kLstmWarps = 8;
+
+__global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float* __restrict__ gates, const float* __restrict__ c_in,
+                                                                     float* __restrict__ h_out, float* __restrict__ c_out, int hw, int C) {
+  extern __shared__ float sm[];           // [hw][32] values + reduction scratch
+  float* s_val = sm;
+  float* s_red = sm + (size_t)hw * 32;    // [kLstmWarps][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int b = blockIdx.y;
+  const float* g = gates + (size_t)b * hw * 4 * C;
+  const float inv_n = 1.f / (float)hw;
+
+  auto block_sum = [&](float v) -> float {
+    __syncthreads();
+    s_red[warp * 32 + lane] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLstmWarps; ++i) t += s_red[i * 32 + lane];
+    return t;
+  };
+
+  // pass 1: LayerNorm statistics of cc_g over the spatial positions (two-pass: mean, then centred variance)
+  float s = 0.f;
+  for (int p = warp; p < hw; p += kLstmWarps) {
+    const float v = g[(size_t)p * 4 * C + 3 * C + c];
+    s_val[p * 32 + lane] = v;
+    s += v;
+  }
+  const float mean_g = block_sum(s) * inv_n;
+  s = 0.f;
+  for (int p = warp; p < hw; p += kLstmWarps) {
+    const float dlt = s_val[p * 32 + lane] - mean_g;
+    s += dlt * dlt;
+  }
+  const float rstd_g = rsqrtf(block_sum(s) * inv_n + 1e-5f);
+  // pass 2: c_next (pre-LN) = f*c + i*celu(LN(cc_g))
+  s = 0.f;
+  for (int p = warp; p < hw; p += kLstmWarps) {
+    const float* gp = g + (size_t)p * 4 * C;
+    const float ig = sigmoidf_(gp[c]), fg = sigmoidf_(gp[C + c]);
+    const float gg = celu1((s_val[p * 32 + lane] - mean_g) * rstd_g);
+    const float cn = fg * c_in[((size_t)b * hw + p) * C + c] + ig * gg;
+    s_val[p * 32 + lane] = cn;
+    s += cn;
+  }
+  const float mean_c = block_sum(s) * inv_n;
+  s = 0.f;
+  for (int p = warp; p < hw; p += kLstmWarps) {
+    const float dlt = s_val[p * 32 + lane] - mean_c;
+    s += dlt * dlt;
+  }
+  const float rstd_c = rsqrtf(block_sum(s) * inv_n + 1e-5f);
+  for (int p = warp; p < hw; p += kLstmWarps) {
+    const float cn = (s_val[p * 32 + lane] - mean_c) * rstd_c;
+    const float og = sigmoidf_(g[(size_t)p * 4 * C + 2 * C + c]);
+    c_out[((size_t)b * hw + p) * C + c] = cn;
+    h_out[((size_t)b * hw + p) * C + c] = og * celu1(cn);
+  }
+}
+
+}  // namespace dvmvs
+
+using namespace dvmvs;
+
+extern "C" int dvmvs_conv2d(const dvmvs_conv_desc* desc, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(desc != nullptr, "conv2d: null descriptor");
+  ConvParams p;
+  p.d = *desc;
+  const dvmvs_conv_desc& d = p.d;
+  DVMVS_REQUIRE(d.n_src >= 1 && d.n_src <= 3, "conv2d: n_src=%d", d.n_src);
+  DVMVS_REQUIRE(d.ksize == 1 || d.ksize == 3 || d.ksize == 5, "conv2d: ksize=%d", d.ksize);
+  DVMVS_REQUIRE(d.stride == 1 || d.stride == 2, "conv2d: stride=%d", d.stride);
+  DVMVS_REQUIRE(d.B > 0 && d.Hin > 0 && d.Win > 0 && d.Cout > 0 && d.weight && d.out, "conv2d: bad shape / null pointer");
+  DVMVS_REQUIRE(d.act >= 0 && d.act <= 2, "conv2d: act=%d", d.act);
+  p.Cin = 0;
+  p.chunks_total = 0;
+  for (int s = 0; s < d.n_src; ++s) {
+    DVMVS_REQUIRE(d.src[s] && d.src_channels[s] > 0, "conv2d: source %d null/empty", s);
+    DVMVS_REQUIRE(d.src_mode[s] == DVMVS_SRC_DIRECT || (d.src_mode[s] == DVMVS_SRC_UPSAMPLE2X && d.Hin % 2 == 0 && d.Win % 2 == 0),
+                  "conv2d: source %d bad mode", s);
+    p.src_cin_offset[s] = p.Cin;
+    p.Cin += d.src_channels[s];
+    p.chunks_total += (d.src_channels[s] + CK - 1) / CK;
+  }
+  const int pad = (d.ksize - 1) / 2;
+  p.Hout = (d.Hin + 2 * pad - d.ksize) / d.stride + 1;
+  p.Wout = (d.Win + 2 * pad - d.ksize) / d.stride + 1;
+  DVMVS_REQUIRE(d.residual_mode == DVMVS_RES_NONE || d.residual, "conv2d: residual pointer missing");
+  DVMVS_REQUIRE(d.residual_mode != DVMVS_RES_NEAREST_UP || (d.Hr > 0 && d.Wr > 0), "conv2d: residual size missing");
+  cudaStream_t s = (cudaStream_t)stream;
+
+  // single-channel 3x3 head
+  if (d.Cout == 1 && d.n_src == 1 && d.src_mode[0] == DVMVS_SRC_DIRECT && d.ksize == 3 && d.stride == 1 && p.Cin % 32 == 0 &&
+      d.residual_mode == DVMVS_RES_NONE && ((uintptr_t)d.src[0] % 16 == 0) && ((uintptr_t)d.weight % 16 == 0)) {
+    p.ksplit = 1;
+    const size_t npix = (size_t)d.B * p.Hout * p.Wout;
+    const unsigned blocks = (unsigned)((npix + 31) / 32);   // 8 warps x 4 pixels
+    conv_head_kernel<<<blocks, 256, 0, s>>>(p);
+    return check_launch("conv_head_kernel");
+  }
+
+  DVMVS_REQUIRE((d.Cout % 4 != 0) || ((uintptr_t)d.weight % 16 == 0), "conv2d: weight must be 16-byte aligned");
+  p.tiles_x = (p.Wout + TW - 1) / TW;
+  p.tiles_y = (p.Hout + TH - 1) / TH;
+  const int ctas = p.tiles_x * p.tiles_y * ((d.Cout + TN - 1) / TN) * d.B;
+  p.ksplit = 1;
+  if (ctas < 96 && p.chunks_total >= 8) {          // under-filled grid: split the reduction over input-channel chunks
+    int want = (296 + ctas - 1) / ctas;
+    int maxsplit = p.chunks_total / 4;
+    p.ksplit = max(1, min(want, maxsplit));
+  }
+  if (p.ksplit > 1) {
+    cudaError_t e = cudaMemsetAsync(d.out, 0, (size_t)d.B * p.Hout * p.Wout * d.Cout * sizeof(float), s);
+    if (e != cudaSuccess) { set_error("conv2d memset: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
+  }
+  int rc;
+  if (d.ksize == 1 && d.stride == 1) rc = launch_conv<1, 1>(p, s);
+  else if (d.ksize == 1 && d.stride == 2) rc = launch_conv<1, 2>(p, s);
+  else if (d.ksize == 3 && d.stride == 1) rc = launch_conv<3, 1>(p, s);
+  else if (d.ksize == 3 && d.stride == 2) rc = launch_conv<3, 2>(p, s);
+  else if (d.ksize == 5 && d.stride == 1) rc = launch_conv<5, 1>(p, s);
+  else rc = launch_conv<5, 2>(p, s);
+  if (rc != DVMVS_OK) return rc;
+  if (p.ksplit > 1) {
+    const size_t total = (size_t)d.B * p.Hout * p.Wout * d.Cout;
+    conv_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+    return check_launch("conv_epilogue_kernel");
+  }
+  return DVMVS_OK;
+}
+
+extern "C" int dvmvs_dwconv2d(const float* x, const float* weight, const float* bias, float* y, int B, int H, int W, int C,
+                              int ksize, int stride, int act, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(x && weight && y, "dwconv2d: null pointer");
+  DVMVS_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "dwconv2d: bad shape (C must be a multiple of 4)");
+  DVMVS_REQUIRE((ksize == 3 || ksize == 5) && (stride == 1 || stride == 2), "dwconv2d: ksize/stride");
+  DVMVS_REQUIRE(act == DVMVS_ACT_NONE || act == DVMVS_ACT_RELU, "dwconv2d: act");
+  DVMVS_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)weight % 16 == 0 && (uintptr_t)y % 16 == 0 && (!bias || (uintptr_t)bias % 16 == 0),
+                "dwconv2d: pointers must be 16-byte aligned");
+  const int pad = ksize / 2;
+  const int Hout = (H + 2 * pad - ksize) / stride + 1, Wout = (W + 2 * pad - ksize) / stride + 1;
+  const size_t total = (size_t)B * Hout * Wout * (C / 4);
+  dwconv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, weight, bias, y, B, H, W, C, Hout, Wout, ksize,
+                                                                                 stride, act);
+  return check_launch("dwconv_kernel");
+}
+
+extern "C" int dvmvs_lstm_gates(const float* gates, const float* c_in, float* h_out, float* c_out, int B, int h, int w, int C,
+                                dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(gates && c_in && h_out && c_out, "lstm_gates: null pointer");
+  DVMVS_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && C % 32 == 0, "lstm_gates: bad shape (C must be a multiple of 32)");
+  const int hw = h * w;
+  const size_t smem = ((size_t)hw * 32 + kLstmWarps * 32) * sizeof(float);
+  DVMVS_REQUIRE(smem <= 200 * 1024, "lstm_gates: h*w=%d too large", hw);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(lstm_gates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  dim3 grid(C / 32, B);
+  lstm_gates_kernel<<<grid, 32 * kLstmWarps, smem, (cudaStream_t)stream>>>(gates, c_in, h_out, c_out, hw, C);
+  return check_launch("lstm_gates_kernel");
+}
+
+extern "C" int dvmvs_upsample2x(const float* x, float* y, int B, int H, int W, int C, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0, "upsample2x: bad argument");
+  const size_t total = (size_t)B * 4 * H * W * C;
+  upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C);
+  return check_launch("upsample2x_kernel");
+}
+
+static int launch_transpose(const float* x, float* y, int B, int R, int Cc, cudaStream_t s) {
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, B), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(x, y, R, Cc);
+  return check_launch("transpose_kernel");
+}
+
+extern "C" int dvmvs_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(x && y && B > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad argument");
+  return launch_transpose(x, y, B, C, H * W, (cudaStream_t)stream);
+}
+
+extern "C" int dvmvs_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(x && y && B > 0 && C > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad argument");
+  return launch_transpose(x, y, B, H * W, C, (cudaStream_t)stream);
+}

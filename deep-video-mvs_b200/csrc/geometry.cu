@@ -1,0 +1,464 @@
+// Geometric kernels of the plane-sweep depth path: fused plane-sweep warp+correlate, pose-aware hidden-state
+// warp, forward depth re-projection.  sm_100a.
+//
+// Reference behaviour reproduced (paths relative to the reference root):
+//   dvmvs/utils.py:45-107   calculate_cost_volume_by_warping / cost_volume_fusion
+//   dvmvs/utils.py:205-258  warp_frame_depth            dvmvs/convlstm.py:30-41 (transformation, mask)
+//   dvmvs/utils.py:110-154  get_non_differentiable_rectangle_depth_estimation
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace dvmvs {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n); }
+
+// =====================================================================================================
+// Plane sweep
+// =====================================================================================================
+constexpr int kMaxMeas = 8;
+constexpr int kMaxPlanes = 256;
+
+struct SweepParams {
+  const float* ref;
+  const float* meas[kMaxMeas];
+  const float* pose2[kMaxMeas];
+  const float* pose1;
+  const float* K;
+  float* out;
+  int B, C, h, w, D, M;
+  double inv_base, inv_step;   // python doubles in the reference (utils.py:59-60)
+  int mode;
+};
+
+// Per (b, m): G = K R K^-1 (9 floats), Kt = K t (3 floats)    (utils.py:51-56)
+__host__ __device__ __forceinline__ void sweep_matrices(const float* pose1, const float* pose2, const float* K, float* G, float* Kt) {
+  float inv2[16], E[16];
+  mat4_rigid_free_inverse(pose2, inv2);
+  mat4_mul(inv2, pose1, E);
+  float R[9] = {E[0], E[1], E[2], E[4], E[5], E[6], E[8], E[9], E[10]};
+  float t[3] = {E[3], E[7], E[11]};
+  float Kinv[9], KR[9];
+  mat3_inverse(K, Kinv);
+  mat3_mul(K, R, KR);
+  mat3_mul(KR, Kinv, G);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) Kt[i] = fmaf(K[i * 3 + 2], t[2], fmaf(K[i * 3 + 1], t[1], K[i * 3 + 0] * t[0]));
+}
+
+// Sampling position of reference pixel (u,v) on plane with Kt/depth = kd (utils.py:68-73 + the align_corners
+// un-normalisation of grid_sample: ((g + 1) / 2) * (size - 1)).
+__host__ __device__ __forceinline__ void sweep_sample_pos(const float* base, const float* kd, float wn, float hn, float wm1, float hm1,
+                                                 float& xs, float& ys) {
+  float q0 = base[0] + kd[0], q1 = base[1] + kd[1], q2 = base[2] + kd[2];
+  float den = q2 + 1e-8f;
+  float x = q0 / den, y = q1 / den;
+  float gx = (x - wn) / wn, gy = (y - hn) / hn;
+  xs = ((gx + 1.f) * 0.5f) * wm1;
+  ys = ((gy + 1.f) * 0.5f) * hm1;
+}
+
+// ---- fast path: C == 32, channel-last.  A quarter warp (8 lanes x float4) owns one (pixel, plane) sample so
+// that every bilinear tap is ONE 128-byte line; a warp therefore issues 4 lines per load instruction.  The
+// CTA owns kPix consecutive reference pixels of one image row; their 128-byte feature vectors are one
+// contiguous span that is staged in shared memory by a single TMA bulk copy (cp.async.bulk -> UBLKCP).
+constexpr int kPix = 32;
+constexpr int kSweepThreads = 256;
+
+__global__ void __launch_bounds__(kSweepThreads) plane_sweep_c32_kernel(SweepParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_ref = reinterpret_cast<float*>(smem_raw);                     // [kPix][32]
+  float* s_kd = s_ref + kPix * 32;                                       // [M][D][3]  Kt / depth_i
+  float* s_G = s_kd + p.M * p.D * 3;                                     // [M][12]
+  float* s_out = s_G + kMaxMeas * 12;                                    // [kPix][D]
+  __shared__ __align__(8) unsigned long long s_bar;
+
+  const int tid = threadIdx.x;
+  const int tiles_per_row = (p.w + kPix - 1) / kPix;
+  const int tile = blockIdx.x;
+  const int b = tile / (p.h * tiles_per_row);
+  const int rem = tile - b * (p.h * tiles_per_row);
+  const int v = rem / tiles_per_row;
+  const int u0 = (rem - v * tiles_per_row) * kPix;
+  const int npix = min(kPix, p.w - u0);
+
+  // --- TMA bulk copy of the reference-feature span into shared memory
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_ref);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)npix * 32u * 4u;
+    const float* src = p.ref + (((size_t)b * p.h + v) * p.w + u0) * 32;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+  // --- geometry prologue (overlaps the copy): one thread per measurement frame
+  if (tid < p.M) {
+    float G[9], Kt[3];
+    sweep_matrices(p.pose1 + b * 16, p.pose2[tid] + b * 16, p.K + b * 9, G, Kt);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s_G[tid * 12 + i] = G[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s_G[tid * 12 + 9 + i] = Kt[i];
+  }
+  __syncthreads();
+  for (int i = tid; i < p.M * p.D; i += kSweepThreads) {
+    const int m = i / p.D, d = i - m * p.D;
+    const float this_depth = (float)(1.0 / (p.inv_base + d * p.inv_step));   // utils.py:66 (double, then fp32 divide)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s_kd[i * 3 + k] = s_G[m * 12 + 9 + k] / this_depth;   // utils.py:68
+  }
+  __syncthreads();
+  {  // wait for the TMA bytes
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(0u)
+          : "memory");
+    }
+  }
+
+  const int lane = tid & 31, warp = tid >> 5;
+  const int sub = lane & 7;        // channel group: channels sub*4 .. sub*4+3
+  const int quad = lane >> 3;      // which of the warp's 4 concurrent samples
+  const float wn = p.w * 0.5f, hn = p.h * 0.5f, wm1 = (float)(p.w - 1), hm1 = (float)(p.h - 1);
+  const float inv_C = 1.f / 32.f;
+  const size_t img_stride = (size_t)p.h * p.w * 32;
+
+  // work items: (pixel, plane); warp handles 4 per step.  Order: plane fastest within a pixel so that the 4
+  // samples of a warp step walk along one epipolar line (neighbouring taps -> L1 hits).
+  const int n_items = npix * p.D;
+  for (int item = warp * 4 + quad; item < ((n_items + 3) / 4) * 4; item += (kSweepThreads / 32) * 4) {
+    const bool active = item < n_items;
+    const int pix = active ? item / p.D : 0;
+    const int d = active ? item - pix * p.D : 0;
+    const float4 f1 = *reinterpret_cast<const float4*>(s_ref + pix * 32 + sub * 4);
+    const float uf = (float)(u0 + pix), vf = (float)v;
+    float acc = 0.f;
+    for (int m = 0; m < p.M; ++m) {
+      const float* G = s_G + m * 12;
+      float base[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) base[k] = fmaf(G[k * 3 + 0], uf, fmaf(G[k * 3 + 1], vf, G[k * 3 + 2]));
+      float xs, ys;
+      sweep_sample_pos(base, s_kd + (m * p.D + d) * 3, wn, hn, wm1, hm1, xs, ys);
+      const float x0f = floorf(xs), y0f = floorf(ys);
+      const float wx1 = xs - x0f, wx0 = (x0f + 1.f) - xs;
+      const float wy1 = ys - y0f, wy0 = (y0f + 1.f) - ys;
+      const bool vx0 = (x0f >= 0.f) && (x0f <= wm1), vx1 = (x0f + 1.f >= 0.f) && (x0f + 1.f <= wm1);
+      const bool vy0 = (y0f >= 0.f) && (y0f <= hm1), vy1 = (y0f + 1.f >= 0.f) && (y0f + 1.f <= hm1);
+      float4 wsum = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active && (vx0 || vx1) && (vy0 || vy1)) {
+        const int x0 = (int)x0f, y0 = (int)y0f;
+        const float* img = p.meas[m] + (size_t)b * img_stride + sub * 4;
+        // issue all taps first (independent loads), then blend
+        float4 t00 = make_float4(0.f, 0.f, 0.f, 0.f), t01 = t00, t10 = t00, t11 = t00;
+        if (vy0 && vx0) t00 = __ldg(reinterpret_cast<const float4*>(img + ((size_t)y0 * p.w + x0) * 32));
+        if (vy0 && vx1) t01 = __ldg(reinterpret_cast<const float4*>(img + ((size_t)y0 * p.w + x0 + 1) * 32));
+        if (vy1 && vx0) t10 = __ldg(reinterpret_cast<const float4*>(img + ((size_t)(y0 + 1) * p.w + x0) * 32));
+        if (vy1 && vx1) t11 = __ldg(reinterpret_cast<const float4*>(img + ((size_t)(y0 + 1) * p.w + x0 + 1) * 32));
+        const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+        wsum.x = fmaf(t11.x, w11, fmaf(t10.x, w10, fmaf(t01.x, w01, t00.x * w00)));
+        wsum.y = fmaf(t11.y, w11, fmaf(t10.y, w10, fmaf(t01.y, w01, t00.y * w00)));
+        wsum.z = fmaf(t11.z, w11, fmaf(t10.z, w10, fmaf(t01.z, w01, t00.z * w00)));
+        wsum.w = fmaf(t11.w, w11, fmaf(t10.w, w10, fmaf(t01.w, w01, t00.w * w00)));
+      }
+      float part;
+      if (p.mode == DVMVS_SWEEP_DOT)
+        part = fmaf(f1.w, wsum.w, fmaf(f1.z, wsum.z, fmaf(f1.y, wsum.y, f1.x * wsum.x)));
+      else
+        part = fabsf(f1.x - wsum.x) + fabsf(f1.y - wsum.y) + fabsf(f1.z - wsum.z) + fabsf(f1.w - wsum.w);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      acc += (p.mode == DVMVS_SWEEP_DOT) ? part * inv_C : part;          // utils.py:82 / :84
+    }
+    if (active && sub == 0) s_out[pix * p.D + d] = acc / (float)p.M;     // utils.py:105-106
+  }
+  __syncthreads();
+  // coalesced write-out: [npix][D] is contiguous in the channel-last cost volume
+  float* o = p.out + (((size_t)b * p.h + v) * p.w + u0) * p.D;
+  for (int i = tid; i < n_items; i += kSweepThreads) o[i] = s_out[i];
+}
+
+// ---- generic path: any C, one thread per (pixel, plane); also the on-device cross-check of the fast path.
+__global__ void plane_sweep_generic_kernel(SweepParams p) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)p.B * p.h * p.w * p.D;
+  if (idx >= total) return;
+  const int d = (int)(idx % p.D);
+  size_t pixi = idx / p.D;
+  const int u = (int)(pixi % p.w);
+  const int v = (int)((pixi / p.w) % p.h);
+  const int b = (int)(pixi / ((size_t)p.w * p.h));
+  const float wn = p.w * 0.5f, hn = p.h * 0.5f, wm1 = (float)(p.w - 1), hm1 = (float)(p.h - 1);
+  const float* f1 = p.ref + pixi * p.C;
+  const float this_depth = (float)(1.0 / (p.inv_base + d * p.inv_step));
+  float acc = 0.f;
+  for (int m = 0; m < p.M; ++m) {
+    float G[9], Kt[3];
+    sweep_matrices(p.pose1 + b * 16, p.pose2[m] + b * 16, p.K + b * 9, G, Kt);
+    float base[3], kd[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      base[k] = fmaf(G[k * 3 + 0], (float)u, fmaf(G[k * 3 + 1], (float)v, G[k * 3 + 2]));
+      kd[k] = Kt[k] / this_depth;
+    }
+    float xs, ys;
+    sweep_sample_pos(base, kd, wn, hn, wm1, hm1, xs, ys);
+    const float x0f = floorf(xs), y0f = floorf(ys);
+    const float wx[2] = {(x0f + 1.f) - xs, xs - x0f}, wy[2] = {(y0f + 1.f) - ys, ys - y0f};
+    const float* img = p.meas[m] + (size_t)b * p.h * p.w * p.C;
+    float part = 0.f;
+    for (int c = 0; c < p.C; ++c) {
+      float warped = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const float xf = x0f + dx, yf = y0f + dy;
+          if (xf >= 0.f && xf <= wm1 && yf >= 0.f && yf <= hm1)
+            warped = fmaf(img[((size_t)(int)yf * p.w + (int)xf) * p.C + c], wx[dx] * wy[dy], warped);
+        }
+      part += (p.mode == DVMVS_SWEEP_DOT) ? f1[c] * warped : fabsf(f1[c] - warped);
+    }
+    acc += (p.mode == DVMVS_SWEEP_DOT) ? part / (float)p.C : part;
+  }
+  p.out[idx] = acc / (float)p.M;
+}
+
+// =====================================================================================================
+// Hidden-state warp (+ invalid-depth mask)
+// =====================================================================================================
+__global__ void hidden_warp_kernel(const float* __restrict__ h_in, const float* __restrict__ depth,
+                                   const float* __restrict__ prev_pose, const float* __restrict__ cur_pose,
+                                   const float* __restrict__ K, float* __restrict__ h_out, int B, int C, int h, int w,
+                                   float invalid_thresh) {
+  __shared__ float s_T[16];
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    if (prev_pose != nullptr) {
+      float inv[16], T[16];
+      mat4_rigid_free_inverse(prev_pose + b * 16, inv);                  // convlstm.py:30
+      mat4_mul(inv, cur_pose + b * 16, T);
+      for (int i = 0; i < 16; ++i) s_T[i] = T[i];
+    } else {
+      for (int i = 0; i < 16; ++i) s_T[i] = cur_pose[b * 16 + i];
+    }
+  }
+  __syncthreads();
+  const int c4 = C >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= h * w * c4) return;
+  const int cg = idx % c4;
+  const int pix = idx / c4;
+  const int u = pix % w, v = pix / w;
+  const float* Kb = K + b * 9;
+  const float fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
+  const float d = depth[(size_t)b * h * w + pix];
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!(d <= invalid_thresh)) {                                          // convlstm.py:32,40-41
+    // kornia depth_to_3d / transform_points / relu(z) / project_points (guarded divide)   utils.py:241-252
+    const float X = ((float)u - cx) / fx * d, Y = ((float)v - cy) / fy * d, Z = d;
+    const float x = fmaf(s_T[0], X, fmaf(s_T[1], Y, s_T[2] * Z)) + s_T[3];
+    const float y = fmaf(s_T[4], X, fmaf(s_T[5], Y, s_T[6] * Z)) + s_T[7];
+    float z = fmaf(s_T[8], X, fmaf(s_T[9], Y, s_T[10] * Z)) + s_T[11];
+    z = fmaxf(z, 0.f);
+    const float scale = (fabsf(z) > 1e-8f) ? 1.f / z : 1.f;
+    const float us = x * scale * fx + cx, vs = y * scale * fy + cy;
+    // normalize_pixel_coordinates + align_corners=True == sample at (us, vs)
+    const float gx = us * (2.f / (float)(w - 1)) - 1.f, gy = vs * (2.f / (float)(h - 1)) - 1.f;
+    const float xs = ((gx + 1.f) * 0.5f) * (float)(w - 1), ys = ((gy + 1.f) * 0.5f) * (float)(h - 1);
+    const float x0f = floorf(xs), y0f = floorf(ys);
+    const float wx[2] = {(x0f + 1.f) - xs, xs - x0f}, wy[2] = {(y0f + 1.f) - ys, ys - y0f};
+    const float* img = h_in + (size_t)b * h * w * C + cg * 4;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const float xf = x0f + dx, yf = y0f + dy;
+        if (xf >= 0.f && xf <= (float)(w - 1) && yf >= 0.f && yf <= (float)(h - 1)) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(img + ((size_t)(int)yf * w + (int)xf) * C));
+          const float wt = wx[dx] * wy[dy];
+          o.x = fmaf(t.x, wt, o.x);
+          o.y = fmaf(t.y, wt, o.y);
+          o.z = fmaf(t.z, wt, o.z);
+          o.w = fmaf(t.w, wt, o.w);
+        }
+      }
+  }
+  *reinterpret_cast<float4*>(h_out + ((size_t)b * h * w + pix) * C + cg * 4) = o;
+}
+
+// =====================================================================================================
+// Depth re-projection: z-as-uint atomicMax scatter (z >= 0 so the float order equals the uint order)
+// =====================================================================================================
+__global__ void depth_reproject_kernel(const float* __restrict__ cur_pose, const float* __restrict__ prev_pose,
+                                       const float* __restrict__ prev_depth, const float* __restrict__ full_K,
+                                       const float* __restrict__ half_K, unsigned int* __restrict__ out, int B, int H, int W) {
+  __shared__ float s_T[16];
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    float inv[16], T[16];
+    mat4_rigid_free_inverse(cur_pose + b * 16, inv);                     // utils.py:121
+    mat4_mul(inv, prev_pose + b * 16, T);
+    for (int i = 0; i < 16; ++i) s_T[i] = T[i];
+  }
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= H * W) return;
+  const int u = pix % W, v = pix / W;
+  const float* Kf = full_K + b * 9;
+  const float* Kh = half_K + b * 9;
+  const float d = prev_depth[(size_t)b * H * W + pix];
+  const float X = ((float)u - Kf[2]) / Kf[0] * d, Y = ((float)v - Kf[5]) / Kf[4] * d, Z = d;      // utils.py:122
+  const float x = fmaf(s_T[0], X, fmaf(s_T[1], Y, s_T[2] * Z)) + s_T[3];
+  const float y = fmaf(s_T[4], X, fmaf(s_T[5], Y, s_T[6] * Z)) + s_T[7];
+  const float z = fmaf(s_T[8], X, fmaf(s_T[9], Y, s_T[10] * Z)) + s_T[11];
+  const float zr = fmaxf(z, 0.f);                                        // utils.py:129
+  const float scale = (fabsf(z) > 1e-8f) ? 1.f / z : 1.f;                // project_points on the un-relu'd point
+  const float pu = rintf(x * scale * Kh[0] + Kh[2]);                     // torch.round = half-to-even
+  const float pv = rintf(y * scale * Kh[4] + Kh[5]);
+  const int hw = W / 2, hh = H / 2;
+  if (pu >= 0.f && pv >= 0.f && pu < (float)hw && pv < (float)hh) {      // utils.py:137-139
+    atomicMax(out + (size_t)b * hh * hw + (size_t)(int)pv * hw + (int)pu, __float_as_uint(zr));
+  }
+}
+
+}  // namespace dvmvs
+
+using namespace dvmvs;
+
+extern "C" int dvmvs_abi_version(void) { return 1; }
+
+// Host-side evaluation of the geometry prologue (same code the kernels run); lets the CPU test-suite check the
+// pose algebra without a GPU.  All pointers are HOST pointers here.
+extern "C" int dvmvs_host_sweep_geometry(const float* pose1_host, const float* pose2_host, const float* K_host, float u, float v,
+                                         int h, int w, int d, int D, float min_depth, float max_depth, float* G_Kt_host,
+                                         float* xy_host) {
+  DVMVS_REQUIRE(pose1_host && pose2_host && K_host && G_Kt_host && xy_host && D >= 2, "host_sweep_geometry: bad argument");
+  float G[9], Kt[3];
+  sweep_matrices(pose1_host, pose2_host, K_host, G, Kt);
+  for (int i = 0; i < 9; ++i) G_Kt_host[i] = G[i];
+  for (int i = 0; i < 3; ++i) G_Kt_host[9 + i] = Kt[i];
+  const double inv_base = 1.0 / (double)max_depth, inv_step = (1.0 / (double)min_depth - 1.0 / (double)max_depth) / (double)(D - 1);
+  const float this_depth = (float)(1.0 / (inv_base + d * inv_step));
+  float base[3], kd[3];
+  for (int k = 0; k < 3; ++k) {
+    base[k] = fmaf(G[k * 3 + 0], u, fmaf(G[k * 3 + 1], v, G[k * 3 + 2]));
+    kd[k] = Kt[k] / this_depth;
+  }
+  sweep_sample_pos(base, kd, w * 0.5f, h * 0.5f, (float)(w - 1), (float)(h - 1), xy_host[0], xy_host[1]);
+  return DVMVS_OK;
+}
+extern "C" const char* dvmvs_last_error_string(void) { return g_err; }
+extern "C" int dvmvs_kernel_launch_count(void) { return g_launches.load(); }
+
+extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* meas_host, const float* pose1,
+                                       const float* const* pose2_host, const float* K, float* cost_out, int B, int C,
+                                       int h, int w, int D, int M, float min_depth, float max_depth, int mode,
+                                       dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(ref && meas_host && pose1 && pose2_host && K && cost_out, "plane_sweep: null pointer");
+  DVMVS_REQUIRE(B > 0 && C > 0 && h > 1 && w > 1, "plane_sweep: bad shape B=%d C=%d h=%d w=%d", B, C, h, w);
+  DVMVS_REQUIRE(D >= 2 && D <= kMaxPlanes, "plane_sweep: D=%d outside [2,%d]", D, kMaxPlanes);
+  DVMVS_REQUIRE(M >= 1 && M <= kMaxMeas, "plane_sweep: M=%d outside [1,%d]", M, kMaxMeas);
+  DVMVS_REQUIRE(mode == DVMVS_SWEEP_DOT || mode == DVMVS_SWEEP_SAD, "plane_sweep: bad mode %d", mode);
+  DVMVS_REQUIRE(min_depth > 0.f && max_depth > min_depth, "plane_sweep: bad depth range");
+  SweepParams p;
+  p.ref = ref;
+  for (int m = 0; m < M; ++m) {
+    DVMVS_REQUIRE(meas_host[m] && pose2_host[m], "plane_sweep: null measurement pointer %d", m);
+    p.meas[m] = meas_host[m];
+    p.pose2[m] = pose2_host[m];
+  }
+  p.pose1 = pose1;
+  p.K = K;
+  p.out = cost_out;
+  p.B = B; p.C = C; p.h = h; p.w = w; p.D = D; p.M = M;
+  p.inv_base = 1.0 / (double)max_depth;                                   // utils.py:59-60
+  p.inv_step = (1.0 / (double)min_depth - 1.0 / (double)max_depth) / (double)(D - 1);
+  p.mode = mode;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool aligned = ((uintptr_t)ref % 16 == 0);
+  bool fast = (C == 32) && aligned;
+  for (int m = 0; m < M && fast; ++m) fast = ((uintptr_t)meas_host[m] % 16 == 0);
+  if (fast) {
+    const int tiles = B * h * ((w + kPix - 1) / kPix);
+    const size_t smem = (size_t)(kPix * 32 + M * D * 3 + kMaxMeas * 12 + kPix * D) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(plane_sweep_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr_set = true;
+    }
+    DVMVS_REQUIRE(smem <= 96 * 1024, "plane_sweep: shared memory %zu too large", smem);
+    plane_sweep_c32_kernel<<<tiles, kSweepThreads, smem, s>>>(p);
+    return check_launch("plane_sweep_c32_kernel");
+  }
+  const size_t total = (size_t)B * h * w * D;
+  plane_sweep_generic_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(p);
+  return check_launch("plane_sweep_generic_kernel");
+}
+
+// test hook: force the generic path (used by tests to cross-check the fast path on the device)
+extern "C" int dvmvs_plane_sweep_generic(const float* ref, const float* const* meas_host, const float* pose1,
+                                         const float* const* pose2_host, const float* K, float* cost_out, int B, int C,
+                                         int h, int w, int D, int M, float min_depth, float max_depth, int mode,
+                                         dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(ref && meas_host && pose1 && pose2_host && K && cost_out, "plane_sweep: null pointer");
+  DVMVS_REQUIRE(M >= 1 && M <= kMaxMeas && D >= 2, "plane_sweep: bad M/D");
+  SweepParams p;
+  p.ref = ref;
+  for (int m = 0; m < M; ++m) { p.meas[m] = meas_host[m]; p.pose2[m] = pose2_host[m]; }
+  p.pose1 = pose1; p.K = K; p.out = cost_out;
+  p.B = B; p.C = C; p.h = h; p.w = w; p.D = D; p.M = M;
+  p.inv_base = 1.0 / (double)max_depth;
+  p.inv_step = (1.0 / (double)min_depth - 1.0 / (double)max_depth) / (double)(D - 1);
+  p.mode = mode;
+  const size_t total = (size_t)B * h * w * D;
+  plane_sweep_generic_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("plane_sweep_generic_kernel");
+}
+
+extern "C" int dvmvs_hidden_warp(const float* h_in, const float* depth, const float* prev_pose, const float* cur_pose,
+                                 const float* K, float* h_out, int B, int C, int h, int w, float invalid_thresh,
+                                 dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(h_in && depth && cur_pose && K && h_out, "hidden_warp: null pointer");
+  DVMVS_REQUIRE(B > 0 && C > 0 && C % 4 == 0 && h > 1 && w > 1, "hidden_warp: bad shape B=%d C=%d h=%d w=%d", B, C, h, w);
+  DVMVS_REQUIRE((uintptr_t)h_in % 16 == 0 && (uintptr_t)h_out % 16 == 0, "hidden_warp: pointers must be 16-byte aligned");
+  const int n = h * w * (C / 4);
+  dim3 grid((n + 127) / 128, B);
+  hidden_warp_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h_in, depth, prev_pose, cur_pose, K, h_out, B, C, h, w, invalid_thresh);
+  return check_launch("hidden_warp_kernel");
+}
+
+extern "C" int dvmvs_depth_reproject(const float* cur_pose, const float* prev_pose, const float* prev_depth,
+                                     const float* full_K, const float* half_K, float* out, int B, int H, int W,
+                                     dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(cur_pose && prev_pose && prev_depth && full_K && half_K && out, "depth_reproject: null pointer");
+  DVMVS_REQUIRE(B > 0 && H >= 2 && W >= 2, "depth_reproject: bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * (H / 2) * (W / 2) * sizeof(float), s);
+  if (e != cudaSuccess) { set_error("depth_reproject memset: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
+  dim3 grid((H * W + 255) / 256, B);
+  depth_reproject_kernel<<<grid, 256, 0, s>>>(cur_pose, prev_pose, prev_depth, full_K, half_K, (unsigned int*)out, B, H, W);
+  return check_launch("depth_reproject_kernel");
+}

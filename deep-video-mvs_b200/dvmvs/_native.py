@@ -1,0 +1,68 @@
+"""ctypes binding of libdvmvs_sm100.so (C ABI declared in include/dvmvs_b200.h).  Fails loudly when the library
+has not been built: the product path has no fallback."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdvmvs_sm100.so")
+
+c_float_p = ctypes.c_void_p
+_lib = None
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+SRC_DIRECT, SRC_UPSAMPLE2X = 0, 1
+RES_NONE, RES_SAME, RES_NEAREST_UP = 0, 1, 2
+SWEEP_DOT, SWEEP_SAD = 0, 1
+
+# every symbol include/dvmvs_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "dvmvs_abi_version", "dvmvs_last_error_string", "dvmvs_kernel_launch_count", "dvmvs_plane_sweep_fused",
+    "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
+    "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw",
+]
+
+
+class ConvDesc(ctypes.Structure):
+    """mirror of dvmvs_conv_desc"""
+    _fields_ = [
+        ("src", ctypes.c_void_p * 3), ("src_channels", ctypes.c_int * 3), ("src_mode", ctypes.c_int * 3),
+        ("n_src", ctypes.c_int),
+        ("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+        ("residual_mode", ctypes.c_int), ("Hr", ctypes.c_int), ("Wr", ctypes.c_int),
+        ("out", ctypes.c_void_p), ("aux_out", ctypes.c_void_p),
+        ("aux_mult", ctypes.c_float), ("aux_base", ctypes.c_float),
+        ("B", ctypes.c_int), ("Hin", ctypes.c_int), ("Win", ctypes.c_int), ("Cout", ctypes.c_int),
+        ("ksize", ctypes.c_int), ("stride", ctypes.c_int), ("act", ctypes.c_int),
+    ]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError("dvmvs: %s not found -- build it with `python deep-video-mvs_b200/build_native.py` "
+                               "(there is no CPU / eager fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        i, f, p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+        L.dvmvs_last_error_string.restype = ctypes.c_char_p
+        L.dvmvs_plane_sweep_fused.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
+        L.dvmvs_plane_sweep_generic.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
+        L.dvmvs_hidden_warp.argtypes = [p, p, p, p, p, p, i, i, i, i, f, p]
+        L.dvmvs_depth_reproject.argtypes = [p, p, p, p, p, p, i, i, i, p]
+        L.dvmvs_conv2d.argtypes = [ctypes.POINTER(ConvDesc), p]
+        L.dvmvs_dwconv2d.argtypes = [p, p, p, p, i, i, i, i, i, i, i, p]
+        L.dvmvs_lstm_gates.argtypes = [p, p, p, p, i, i, i, i, p]
+        L.dvmvs_upsample2x.argtypes = [p, p, i, i, i, i, p]
+        L.dvmvs_nchw_to_nhwc.argtypes = [p, p, i, i, i, i, p]
+        L.dvmvs_nhwc_to_nchw.argtypes = [p, p, i, i, i, i, p]
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("dvmvs native call %s failed (%d): %s" % (what, rc, lib().dvmvs_last_error_string().decode()))
+
+
+def launch_count():
+    return lib().dvmvs_kernel_launch_count()

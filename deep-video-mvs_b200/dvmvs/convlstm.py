@@ -1,0 +1,48 @@
+"""MVSLayernormConvLSTMCell with the reference's constructor / forward signature and parameter name
+(`conv.weight`, reference dvmvs/convlstm.py:7-64).  Forward = hidden-state warp kernel (pose algebra, bilinear
+gather and <=0.01 mask fused) -> 3x3 gate convolution over the channel-concat [input, hidden] (concat fused into
+the conv loader) -> gate epilogue kernel (sigmoid / LayerNorm over (h,w) / CELU / state update)."""
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from . import _ops as ops
+from ._base import NativeModule
+
+
+class MVSLayernormConvLSTMCell(NativeModule):
+    def __init__(self, input_dim, hidden_dim, kernel_size, activation_function=None):
+        super().__init__()
+        self.activation_function = activation_function     # kept for signature parity; the kernel implements CELU(alpha=1)
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.kernel_size = kernel_size
+        self.padding = kernel_size[0] // 2, kernel_size[1] // 2
+        if tuple(kernel_size) != (3, 3) and tuple(kernel_size) != (1, 1) and tuple(kernel_size) != (5, 5):
+            raise ValueError("kernel_size must be (1,1), (3,3) or (5,5)")
+        if activation_function is not None and activation_function is not torch.celu:
+            raise NotImplementedError("the fused gate kernel implements torch.celu (the reference's choice, fusionnet/model.py:319)")
+        self.conv = nn.Conv2d(in_channels=input_dim + hidden_dim, out_channels=4 * hidden_dim, kernel_size=self.kernel_size,
+                              padding=self.padding, bias=False)
+
+    def _pack(self):
+        return ops.PackedConv(self.conv.weight, None, None, stride=1, act=N.ACT_NONE)
+
+    def forward(self, input_tensor, cur_state, previous_pose, current_pose, estimated_current_depth, camera_matrix):
+        pc = self.packed()
+        h_cur, c_cur = cur_state
+        x = ops.to_nhwc(input_tensor, "input_tensor")
+        h = ops.to_nhwc(h_cur, "h_cur")
+        c = ops.to_nhwc(c_cur, "c_cur")
+        if previous_pose is not None:
+            # convlstm.py:30-41: transformation = inverse(previous_pose) @ current_pose, warp, mask depth <= 0.01
+            h = ops.hidden_warp(h, estimated_current_depth, previous_pose, current_pose, camera_matrix, 0.01)
+        gates = ops.conv2d([(x, N.SRC_DIRECT), (h, N.SRC_DIRECT)], pc)
+        h_next, c_next = ops.lstm_gates(gates, c)
+        return ops.to_api(h_next), ops.to_api(c_next)
+
+    def init_hidden(self, batch_size, image_size):
+        height, width = image_size
+        dev = self.conv.weight.device
+        z = torch.zeros(batch_size, height, width, self.hidden_dim, device=dev)
+        return ops.to_api(z), ops.to_api(torch.zeros_like(z))

@@ -1,0 +1,128 @@
+/*
+ * dvmvs_b200.h -- C ABI of libdvmvs_sm100.so: the B200 (sm_100a) kernels behind the DeepVideoMVS
+ * plane-sweep depth-inference path.
+ *
+ * The reference (ardaduz/deep-video-mvs) is pure Python/PyTorch and has no FFI; the "interface each entry
+ * point replaces" is therefore the Python function / nn.Module.forward it stands behind (paths relative to
+ * the reference root).  The host-side mirror of those names lives in deep-video-mvs_b200/dvmvs/ and binds
+ * this library with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - every function returns 0 on success or a negative DVMVS_E* code; it never throws, never allocates
+ *     device memory, never synchronises the device; work is enqueued on `stream`.
+ *   - activations are channel-last fp32: [B][H][W][C] ("NHWC").  Cost volumes are [B][h][w][D].
+ *   - poses are row-major 4x4 camera-to-world matrices, intrinsics row-major 3x3, fp32, on the device
+ *     (the reference keeps them on the device too; no D2H copies anywhere on the path).
+ */
+#ifndef DVMVS_B200_H
+#define DVMVS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dvmvs_stream_t; /* cudaStream_t */
+
+enum {
+  DVMVS_OK = 0,
+  DVMVS_EINVAL = -1,   /* bad argument (shape, alignment, null pointer) */
+  DVMVS_ELAUNCH = -2,  /* CUDA launch error; see dvmvs_last_error_string() */
+  DVMVS_EUNSUPPORTED = -3
+};
+
+enum { DVMVS_ACT_NONE = 0, DVMVS_ACT_RELU = 1, DVMVS_ACT_SIGMOID = 2 };
+enum { DVMVS_SRC_DIRECT = 0, DVMVS_SRC_UPSAMPLE2X = 1 };     /* conv input source modes */
+enum { DVMVS_RES_NONE = 0, DVMVS_RES_SAME = 1, DVMVS_RES_NEAREST_UP = 2 };
+enum { DVMVS_SWEEP_DOT = 0, DVMVS_SWEEP_SAD = 1 };
+
+/* Library identification / diagnostics. */
+int dvmvs_abi_version(void);                 /* bumps when a signature changes */
+const char* dvmvs_last_error_string(void);   /* thread-local, static storage */
+int dvmvs_kernel_launch_count(void);         /* kernels launched by this library since load (process-wide) */
+
+/* ------------------------------------------------------------------------------------------------------
+ * Plane-sweep warp + correlate, all planes and all measurement frames fused in ONE launch.
+ * Replaces dvmvs/utils.py:89-107 cost_volume_fusion and :45-86 calculate_cost_volume_by_warping (M = 1).
+ *   ref        [B][h][w][C]  reference-frame features (image1)
+ *   meas_host  host array of M device pointers, each [B][h][w][C] (image2s)
+ *   pose1      [B][4][4]     reference cam-to-world
+ *   pose2_host host array of M device pointers, each [B][4][4] (pose2s)
+ *   K          [B][3][3]     half-resolution intrinsics
+ *   cost_out   [B][h][w][D]  fused cost volume; mean over M of  sum_c f1*warp / C  (DOT)  or
+ *                            sum_c |f1 - warp|  (SAD)
+ * Plane i has inverse depth 1/max_depth + i*(1/min_depth - 1/max_depth)/(D-1).  M <= 8, D <= 256.
+ * C == 32 takes the fast path (quarter-warp per sample, 128-byte gathers); any other C a generic path. */
+int dvmvs_plane_sweep_fused(const float* ref, const float* const* meas_host, const float* pose1,
+                            const float* const* pose2_host, const float* K, float* cost_out,
+                            int B, int C, int h, int w, int D, int M, float min_depth, float max_depth,
+                            int mode, dvmvs_stream_t stream);
+
+/* Pose-aware hidden-state warp with the invalid-depth mask fused.
+ * Replaces dvmvs/utils.py:205-258 warp_frame_depth plus dvmvs/convlstm.py:30-41 (transformation =
+ * inverse(previous_pose) @ current_pose; h[depth <= invalid_thresh] = 0).
+ *   h_in [B][h][w][C], depth [B][h][w], prev_pose/cur_pose [B][4][4], K [B][3][3], h_out [B][h][w][C].
+ * If prev_pose is NULL, `cur_pose` is taken to be the ready-made src_trans_dst (plain warp_frame_depth)
+ * and no mask is applied when invalid_thresh < 0. */
+int dvmvs_hidden_warp(const float* h_in, const float* depth, const float* prev_pose, const float* cur_pose,
+                      const float* K, float* h_out, int B, int C, int h, int w, float invalid_thresh,
+                      dvmvs_stream_t stream);
+
+/* Forward re-projection of the previous depth map into the current view at half resolution,
+ * farthest point per pixel wins, unfilled pixels 0; no host round trip.
+ * Replaces dvmvs/utils.py:110-154 get_non_differentiable_rectangle_depth_estimation.
+ *   cur_pose ("reference_pose_torch"), prev_pose ("measurement_pose_torch") [B][4][4];
+ *   prev_depth [B][H][W]; full_K, half_K [B][3][3]; out [B][H/2][W/2] (zeroed by the call). */
+int dvmvs_depth_reproject(const float* cur_pose, const float* prev_pose, const float* prev_depth,
+                          const float* full_K, const float* half_K, float* out, int B, int H, int W,
+                          dvmvs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Dense 2-D convolution (k in {1,3,5}, stride in {1,2}, pad (k-1)/2) with fused channel-concat of up to
+ * three sources, optional on-the-fly x2 bilinear (align_corners) upsampling per source, folded-BN bias,
+ * residual add (same size, or nearest-upsampled from a coarser map = FPN top-down) and activation.
+ * Replaces torch.nn.Conv2d + BatchNorm2d(eval) + ReLU / Sigmoid as composed by dvmvs/layers.py:39-65,
+ * torch.cat at dvmvs/fusionnet/model.py:112,115,208,212,216,220,295 and dvmvs/convlstm.py:43,
+ * F.interpolate at model.py:59,114,293-294 and torchvision FeaturePyramidNetwork's top-down add. */
+typedef struct {
+  const float* src[3];   /* [B][Hs][Ws][C_i]; Hs = Hin (DIRECT) or Hin/2 (UPSAMPLE2X) */
+  int src_channels[3];
+  int src_mode[3];
+  int n_src;
+  const float* weight;   /* [k][k][Cin][Cout], Cin = sum(src_channels), BN folded */
+  const float* bias;     /* [Cout] or NULL */
+  const float* residual; /* NULL, [B][Hout][Wout][Cout] (SAME) or [B][Hr][Wr][Cout] (NEAREST_UP) */
+  int residual_mode, Hr, Wr;
+  float* out;            /* [B][Hout][Wout][Cout] */
+  float* aux_out;        /* optional [B][Hout][Wout][Cout]: 1/(aux_mult*act(y) + aux_base) (depth heads) */
+  float aux_mult, aux_base;
+  int B, Hin, Win, Cout, ksize, stride, act;
+} dvmvs_conv_desc;
+
+int dvmvs_conv2d(const dvmvs_conv_desc* desc_host, dvmvs_stream_t stream);
+
+/* Depthwise k x k convolution (MnasNet), folded-BN bias + optional ReLU.
+ * x [B][H][W][C], weight [k][k][C], bias [C], y [B][Hout][Wout][C]. */
+int dvmvs_dwconv2d(const float* x, const float* weight, const float* bias, float* y, int B, int H, int W, int C,
+                   int ksize, int stride, int act, dvmvs_stream_t stream);
+
+/* ConvLSTM gate epilogue: replaces dvmvs/convlstm.py:45-59.  gates [B][h][w][4*C] in the order i,f,o,g;
+ * c_in [B][h][w][C]; writes h_out, c_out [B][h][w][C].  LayerNorm over (h,w) per (b,channel), biased
+ * variance, eps 1e-5, no affine; CELU alpha = 1. */
+int dvmvs_lstm_gates(const float* gates, const float* c_in, float* h_out, float* c_out, int B, int h, int w, int C,
+                     dvmvs_stream_t stream);
+
+/* x2 bilinear upsampling, align_corners=True (F.interpolate at dvmvs/fusionnet/model.py:59,114,293-294). */
+int dvmvs_upsample2x(const float* x, float* y, int B, int H, int W, int C, dvmvs_stream_t stream);
+
+/* Layout helpers: NCHW <-> NHWC fp32 copies. */
+int dvmvs_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, dvmvs_stream_t stream);
+int dvmvs_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, dvmvs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVMVS_B200_H */

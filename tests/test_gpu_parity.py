@@ -1,0 +1,322 @@
+"""GPU parity tests: the sm_100a kernels, reached through the reference-facing Python API (which binds the C ABI),
+against (a) golden vectors generated from the unmodified reference, (b) the CPU oracle on seeded inputs, and
+(c) the reference's shipped end-to-end golden predictions.  Tolerances: geometry / convs are fp32 on both sides
+-> <= 2e-5 of the tensor's max magnitude; end-to-end <= 1e-3 relative L1 on inverse depth (BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers, scene_fixture
+from tests.helpers import T, rel_err
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _cuda(x):
+    return T(np.ascontiguousarray(x)).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------ plane sweep
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+def test_plane_sweep_vs_reference_golden(synth, cases, golden_ops, layout):
+    from dvmvs.utils import cost_volume_fusion, get_warp_grid_for_cost_volume_calculation
+    for name, c in cases.PLANE_SWEEP_CASES.items():
+        inp = cases.plane_sweep_inputs(synth, c)
+        conv = (lambda t: t.contiguous(memory_format=torch.channels_last)) if layout == "channels_last" else (lambda t: t)
+        grid = get_warp_grid_for_cost_volume_calculation(c["w"], c["h"], DEV)
+        out = cost_volume_fusion(conv(_cuda(inp["image1"])), [conv(_cuda(x)) for x in inp["image2s"]], _cuda(inp["pose1"]),
+                                 [_cuda(p) for p in inp["pose2s"]], _cuda(inp["K"]), grid, c["min_depth"], c["max_depth"], c["D"],
+                                 DEV, c["dot"])
+        assert tuple(out.shape) == (c["B"], c["D"], c["h"], c["w"])
+        err = rel_err(out.cpu().numpy(), golden_ops["plane_sweep/" + name])
+        assert err <= 2e-5, "plane_sweep/%s (%s): %.3e" % (name, layout, err)
+
+
+def test_plane_sweep_fast_path_equals_generic_path(synth, cases):
+    from dvmvs import _ops as ops
+    c = cases.PLANE_SWEEP_CASES["dot_m3"]
+    inp = cases.plane_sweep_inputs(synth, c)
+    ref = ops.to_nhwc(_cuda(inp["image1"]))
+    meas = [ops.to_nhwc(_cuda(x)) for x in inp["image2s"]]
+    args = (ref, meas, _cuda(inp["pose1"]), [_cuda(p) for p in inp["pose2s"]], _cuda(inp["K"]), c["min_depth"], c["max_depth"], c["D"])
+    for dot in (True, False):
+        fast = ops.plane_sweep(*args, dot_product=dot)
+        gen = ops.plane_sweep(*args, dot_product=dot, force_generic=True)
+        assert rel_err(fast.cpu().numpy(), gen.cpu().numpy()) <= 1e-5
+
+
+def test_calculate_cost_volume_by_warping_is_single_frame_fusion(oracle, synth, cases):
+    from dvmvs.utils import calculate_cost_volume_by_warping
+    c = cases.PLANE_SWEEP_CASES["dot_c1"]
+    inp = cases.plane_sweep_inputs(synth, c)
+    out = calculate_cost_volume_by_warping(_cuda(inp["image1"]), _cuda(inp["image2s"][0]), _cuda(inp["pose1"]),
+                                           _cuda(inp["pose2s"][0]), _cuda(inp["K"]), None, c["min_depth"], c["max_depth"],
+                                           c["D"], DEV, True)
+    gold = oracle.calculate_cost_volume_by_warping(T(inp["image1"]), T(inp["image2s"][0]), T(inp["pose1"]), T(inp["pose2s"][0]),
+                                                   T(inp["K"]), oracle.get_warp_grid_for_cost_volume_calculation(c["w"], c["h"]),
+                                                   c["min_depth"], c["max_depth"], c["D"], "cpu", True)
+    assert rel_err(out.cpu().numpy(), gold.numpy()) <= 2e-5
+
+
+def test_plane_sweep_full_size_configs_vs_oracle(oracle, synth):
+    """BASELINE.json configs 2 and 3 shapes (128x128 D=64 M=2; 128x160 D=96 M=4) with the synthetic-clip geometry."""
+    from dvmvs.utils import cost_volume_fusion
+    for (h, w, D, M) in ((128, 128, 64, 2), (128, 160, 96, 4)):
+        f1 = synth.tensor("full/ref", (1, 32, h, w), seed=D, scale=4.0)
+        f2s = [synth.tensor("full/m%d" % m, (1, 32, h, w), seed=D, scale=4.0) for m in range(M)]
+        pose1 = synth.camera_pose(M)[None]
+        pose2s = [synth.camera_pose(M - k)[None] for k in range(1, M + 1)]
+        K = synth.intrinsics(2 * h, 2 * w)[None].copy()
+        K[:, 0:2, :] /= 2.0
+        out = cost_volume_fusion(_cuda(f1), [_cuda(x) for x in f2s], _cuda(pose1), [_cuda(p) for p in pose2s], _cuda(K), None,
+                                 0.25, 20.0, D, DEV, True)
+        gold = oracle.cost_volume_fusion(T(f1), [T(x) for x in f2s], T(pose1), [T(p) for p in pose2s], T(K),
+                                         oracle.get_warp_grid_for_cost_volume_calculation(w, h), 0.25, 20.0, D, "cpu", True)
+        assert rel_err(out.cpu().numpy(), gold.numpy()) <= 2e-5, (h, w, D, M)
+
+
+def test_plane_sweep_linearity_and_frame_permutation(synth, cases):
+    """Size-independent properties: the cost volume is linear in the reference features and invariant to the order
+    of the measurement frames (up to fp32 summation order)."""
+    from dvmvs.utils import cost_volume_fusion
+    c = cases.PLANE_SWEEP_CASES["dot_m3"]
+    inp = cases.plane_sweep_inputs(synth, c)
+    f1, f2s = _cuda(inp["image1"]), [_cuda(x) for x in inp["image2s"]]
+    p1, p2s, K = _cuda(inp["pose1"]), [_cuda(p) for p in inp["pose2s"]], _cuda(inp["K"])
+    a = cost_volume_fusion(f1, f2s, p1, p2s, K, None, 0.25, 20.0, c["D"], DEV, True)
+    b = cost_volume_fusion(2.0 * f1, f2s, p1, p2s, K, None, 0.25, 20.0, c["D"], DEV, True)
+    assert rel_err(b.cpu().numpy(), 2.0 * a.cpu().numpy()) <= 1e-6
+    p = cost_volume_fusion(f1, f2s[::-1], p1, p2s[::-1], K, None, 0.25, 20.0, c["D"], DEV, True)
+    assert rel_err(p.cpu().numpy(), a.cpu().numpy()) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ hidden warp / re-projection
+def test_hidden_warp_vs_reference_golden(synth, cases, golden_ops):
+    from dvmvs.utils import warp_frame_depth
+    for name, c in cases.HIDDEN_WARP_CASES.items():
+        inp = cases.hidden_warp_inputs(synth, c)
+        out = warp_frame_depth(_cuda(inp["image_src"]), _cuda(inp["depth_dst"]), _cuda(inp["trans"]), _cuda(inp["K"]))
+        err = rel_err(out.cpu().numpy(), golden_ops["hidden_warp/" + name])
+        assert err <= 2e-5, "hidden_warp/%s: %.3e" % (name, err)
+
+
+def test_reprojection_vs_reference_golden(synth, cases, golden_ops):
+    from dvmvs.utils import get_non_differentiable_rectangle_depth_estimation
+    for name, c in cases.REPROJECT_CASES.items():
+        inp = cases.reproject_inputs(synth, c)
+        out = get_non_differentiable_rectangle_depth_estimation(_cuda(inp["reference_pose"]), _cuda(inp["measurement_pose"]),
+                                                                _cuda(inp["previous_depth"]), _cuda(inp["full_K"]),
+                                                                _cuda(inp["half_K"]), c["W"], c["H"]).cpu().numpy()
+        gold = golden_ops["reproject/" + name]
+        assert out.shape == gold.shape
+        mismatch = np.mean(np.abs(out - gold) > 1e-5 * np.maximum(1.0, np.abs(gold)))
+        assert mismatch <= 2e-3, "reproject/%s: %.4f%% pixels differ" % (name, 100 * mismatch)
+
+
+def test_reprojection_is_idempotent_under_identity(synth):
+    """Identity motion: every half-res pixel (i, j) receives the source points that round onto it; the winner is the
+    farthest of them -> max-pool structure, checked against a direct numpy evaluation."""
+    from dvmvs.utils import get_non_differentiable_rectangle_depth_estimation
+    H, W = 64, 96
+    depth = (1.0 + np.abs(synth.tensor("idem", (1, 1, H, W), seed=3))).astype(np.float32)
+    K = synth.intrinsics(H, W)[None]
+    hK = K.copy()
+    hK[:, 0:2, :] /= 2.0
+    eye = np.eye(4, dtype=np.float32)[None]
+    out = get_non_differentiable_rectangle_depth_estimation(_cuda(eye), _cuda(eye), _cuda(depth), _cuda(K), _cuda(hK), W, H).cpu().numpy()
+    assert out.shape == (1, 1, H // 2, W // 2)
+    assert out.max() <= depth.max() + 1e-6 and out.min() >= 0.0
+    assert (out > 0).mean() > 0.9
+
+
+# ------------------------------------------------------------------------------------------------ conv kernels vs torch fp32 (CPU)
+CONV_CASES = [
+    # B, Hin, Win, [src channels], [src modes], Cout, k, stride, act, residual
+    (1, 16, 24, [32], [0], 32, 3, 1, 1, 0),
+    (2, 17, 23, [3], [0], 32, 3, 2, 1, 0),            # stem-like, odd size, Cin=3
+    (1, 32, 32, [32, 64], [0, 0], 32, 5, 1, 1, 0),    # aggregator0-like concat
+    (1, 16, 16, [32], [0], 64, 5, 2, 1, 0),
+    (1, 8, 10, [512, 512], [0, 0], 96, 3, 1, 0, 0),   # small spatial, deep K -> split-K path
+    (1, 8, 8, [192], [0], 40, 1, 1, 0, 1),            # 1x1 + same-size residual (MnasNet)
+    (1, 16, 16, [24], [0], 32, 1, 1, 0, 2),           # 1x1 + nearest-up residual (FPN)
+    (1, 16, 16, [16, 16, 1], [0, 0, 1], 16, 3, 1, 1, 0),   # decoder concat with upsampled 1-channel depth
+    (1, 32, 32, [64], [1], 32, 3, 1, 1, 0),           # up-convolution: x2 bilinear fused
+    (1, 32, 32, [32, 1, 3], [1, 1, 0], 32, 5, 1, 1, 0),    # refine.0-like
+    (1, 12, 20, [64], [0], 1, 3, 1, 2, 0),            # depth head (sigmoid + aux depth)
+    (1, 9, 7, [20], [0], 1, 3, 1, 2, 0),              # head fallback (Cin not a multiple of 32)
+    (1, 16, 16, [1152], [0], 192, 1, 1, 0, 0),        # deep 1x1
+    (1, 8, 8, [8], [0], 24, 1, 2, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_vs_torch_fp32(synth, case):
+    import torch.nn.functional as F
+    from dvmvs import _native as N
+    from dvmvs import _ops as ops
+    B, Hin, Win, chans, modes, Cout, k, stride, act, res = case
+    key = "conv/" + "_".join(str(v) for v in (B, Hin, Win, Cout, k, stride, act, res) + tuple(chans))
+    srcs_cpu, full = [], []
+    for i, (cs, mode) in enumerate(zip(chans, modes)):
+        f = 2 if mode == 1 else 1
+        x = T(synth.tensor(key + "/x%d" % i, (B, cs, Hin // f, Win // f), seed=1))
+        srcs_cpu.append(x)
+        full.append(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True) if mode == 1 else x)
+    cin = sum(chans)
+    w = T(synth.tensor(key + "/w", (Cout, cin, k, k), seed=2, scale=(2.0 / (cin * k * k)) ** 0.5))
+    bias = T(synth.tensor(key + "/b", (Cout,), seed=3, scale=0.1))
+    ref = F.conv2d(torch.cat(full, 1), w, bias, stride, (k - 1) // 2)
+    Hout, Wout = ref.shape[-2:]
+    residual = None
+    if res == 1:
+        residual = T(synth.tensor(key + "/r", (B, Cout, Hout, Wout), seed=4))
+        ref = ref + residual
+    elif res == 2:
+        residual = T(synth.tensor(key + "/r", (B, Cout, Hout // 2, Wout // 2), seed=4))
+        ref = ref + F.interpolate(residual, size=(Hout, Wout), mode="nearest")
+    ref = {0: ref, 1: F.relu(ref), 2: torch.sigmoid(ref)}[act]
+    conv = torch.nn.Conv2d(cin, Cout, k, bias=True)
+    pc = ops.PackedConv(w, bias, None, stride=stride, act=act)
+    pc.weight, pc.bias = pc.weight.to(DEV), pc.bias.to(DEV)
+    aux = (3.95, 0.05) if act == 2 else None
+    out = ops.conv2d([(ops.to_nhwc(x.to(DEV)), m) for x, m in zip(srcs_cpu, modes)], pc,
+                     residual=None if residual is None else ops.to_nhwc(residual.to(DEV)),
+                     residual_mode={0: N.RES_NONE, 1: N.RES_SAME, 2: N.RES_NEAREST_UP}[res], aux=aux)
+    if aux is not None:
+        out, aux_out = out
+        assert rel_err(ops.to_api(aux_out).cpu().numpy(), (1.0 / (3.95 * ref + 0.05)).numpy()) <= 2e-5
+    assert rel_err(ops.to_api(out).cpu().numpy(), ref.numpy()) <= 2e-5, case
+    del conv
+
+
+@pytest.mark.parametrize("case", [(1, 16, 16, 32, 3, 1), (2, 17, 15, 48, 5, 2), (1, 8, 8, 1152, 5, 1), (1, 32, 32, 72, 3, 2)])
+def test_dwconv_vs_torch_fp32(synth, case):
+    import torch.nn.functional as F
+    from dvmvs import _ops as ops
+    B, H, W, C, k, stride = case
+    x = T(synth.tensor("dw/x%d" % C, (B, C, H, W), seed=1))
+    conv = torch.nn.Conv2d(C, C, k, padding=k // 2, stride=stride, groups=C, bias=False)
+    bn = torch.nn.BatchNorm2d(C).eval()
+    sd = synth.make_state_dict({"weight": (C,), "bias": (C,), "running_mean": (C,), "running_var": (C,)}, seed=5)
+    with torch.no_grad():
+        conv.weight.copy_(T(synth.tensor("dw/w%d" % C, (C, 1, k, k), seed=2, scale=0.3)))
+        for kk in sd:
+            getattr(bn, kk).copy_(T(sd[kk]))
+        ref = F.relu(bn(conv(x)))
+    pd = ops.PackedDepthwise(conv.weight, bn, stride)
+    pd.weight, pd.bias = pd.weight.to(DEV), pd.bias.to(DEV)
+    out = ops.dwconv2d(ops.to_nhwc(x.to(DEV)), pd)
+    assert rel_err(ops.to_api(out).cpu().numpy(), ref.numpy()) <= 2e-5
+
+
+def test_layout_roundtrip_and_upsample(synth):
+    import torch.nn.functional as F
+    from dvmvs import _ops as ops
+    x = T(synth.tensor("lay", (2, 37, 9, 13), seed=1)).to(DEV)
+    nhwc = ops.to_nhwc(x)
+    assert torch.equal(nhwc, x.permute(0, 2, 3, 1))
+    assert torch.equal(ops.to_nchw_contiguous(nhwc), x)
+    up = ops.to_api(ops.upsample2x(nhwc)).cpu()
+    assert rel_err(up.numpy(), F.interpolate(x.cpu(), scale_factor=2, mode="bilinear", align_corners=True).numpy()) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ ConvLSTM cell
+def test_lstm_cell_vs_reference_golden(synth, cases, golden_ops):
+    from dvmvs.convlstm import MVSLayernormConvLSTMCell
+    for name, c in cases.LSTM_CASES.items():
+        inp = cases.lstm_inputs(synth, c)
+        cell = MVSLayernormConvLSTMCell(512, 512, (3, 3), activation_function=torch.celu)
+        cell.load_state_dict({"conv.weight": T(inp["weight"])})
+        cell.to(DEV).eval()
+        h, cc = cell(_cuda(inp["x"]), [_cuda(inp["h"]), _cuda(inp["c"])], _cuda(inp["previous_pose"]) if c["warp"] else None,
+                     _cuda(inp["current_pose"]), _cuda(inp["depth"]), _cuda(inp["K"]))
+        assert rel_err(h.cpu().numpy(), golden_ops["lstm/%s/h" % name]) <= 1e-4, name
+        assert rel_err(cc.cpu().numpy(), golden_ops["lstm/%s/c" % name]) <= 1e-4, name
+
+
+# ------------------------------------------------------------------------------------------------ whole modules
+def test_modules_vs_reference_golden(oracle, synth, cases, golden_modules):
+    c = cases.MODULE_CASE
+    w = helpers.oracle_weights(oracle, synth, c["seed"])
+    mods = helpers.build_product_modules(w)
+    inp = cases.module_inputs(synth, c)
+    image = _cuda(inp["image"])
+    with torch.no_grad():
+        l = mods["fe"](image)
+        for i, x in enumerate(l):
+            assert rel_err(x.cpu().numpy(), golden_modules["fe/%d" % i]) <= 5e-5, "fe/%d" % i
+        f = mods["fpn"](*l)
+        for i, x in enumerate(f):
+            assert rel_err(x.cpu().numpy(), golden_modules["fpn/%d" % i]) <= 5e-5, "fpn/%d" % i
+        enc = mods["cve"](*f, _cuda(inp["cost_volume"]))
+        for i, x in enumerate(enc):
+            assert rel_err(x.cpu().numpy(), golden_modules["cve/%d" % i]) <= 1e-4, "cve/%d" % i
+        h0, c0 = mods["lstm"](enc[4], None, None, _cuda(inp["pose0"]), _cuda(inp["depth_est"]), _cuda(inp["lstm_K"]))
+        h1, c1 = mods["lstm"](enc[4], (h0, c0), _cuda(inp["pose0"]), _cuda(inp["pose1"]), _cuda(inp["depth_est"]), _cuda(inp["lstm_K"]))
+        for k, v in (("h0", h0), ("c0", c0), ("h1", h1), ("c1", c1)):
+            assert rel_err(v.cpu().numpy(), golden_modules["lstm/" + k]) <= 2e-4, "lstm/" + k
+        dec = mods["cvd"](image, enc[0], enc[1], enc[2], enc[3], h1)
+        for i, x in enumerate(dec):
+            e = oracle.rel_l1_inverse_depth(x.cpu().numpy(), golden_modules["cvd/%d" % i])
+            assert e <= 1e-4, "cvd/%d: %.3e" % (i, e)
+
+
+def test_outputs_are_fresh_fp32_tensors_and_inputs_untouched(oracle, synth, cases):
+    c = cases.MODULE_CASE
+    mods = helpers.build_product_modules(helpers.oracle_weights(oracle, synth, c["seed"]))
+    image = _cuda(cases.module_inputs(synth, c)["image"])
+    keep = image.clone()
+    a = mods["fe"](image)
+    b = mods["fe"](image)
+    assert torch.equal(image, keep)
+    for x, y in zip(a, b):
+        assert x.dtype == torch.float32 and x.is_cuda and x.data_ptr() != y.data_ptr()
+        assert torch.equal(x, y)          # deterministic
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+def test_fusionnet_end_to_end_vs_shipped_golden():
+    """Shipped fusionnet weights + fixture scene 000 (320x256, D=64, M<=3, recurrent state carried) against the
+    reference's shipped predictions: <= 1e-3 relative L1 on inverse depth per frame."""
+    w = scene_fixture.load_shipped_weights("fusionnet")
+    if w is None:
+        pytest.skip("shipped weights not fetched (tools/fetch_fixtures.py needs /root/reference in the build container)")
+    mods = helpers.build_product_modules(w)
+    frames, full_K, gold = scene_fixture.load_scene()
+    state = helpers.ProductState()
+    from oracle import dvmvs_oracle as oracle
+    errs = []
+    with torch.no_grad():
+        for i, fr in enumerate(frames):
+            pred, state = helpers.product_fusionnet_step(mods, state, _cuda(fr["reference_image"])[None], _cuda(fr["reference_pose"])[None],
+                                                         [_cuda(x)[None] for x in fr["measurement_images"]],
+                                                         [_cuda(p)[None] for p in fr["measurement_poses"]], _cuda(full_K)[None])
+            errs.append(oracle.rel_l1_inverse_depth(pred[0].cpu().numpy(), gold[i]))
+    print("rel-L1(inverse depth) vs shipped golden per frame:", ["%.2e" % e for e in errs])
+    assert max(errs) <= 1e-3, errs
+
+
+@pytest.mark.parametrize("cfg", [("c2", 256, 256, 64, 2, False), ("c3", 256, 320, 96, 4, False), ("c1", 128, 128, 32, 1, True)])
+def test_baseline_configs_vs_oracle(oracle, synth, cfg):
+    """BASELINE.json configs 1-3 on the synthetic posed stream, synthetic weights shared by both sides,
+    3 recurrent keyframes: <= 1e-3 relative L1 on inverse depth (the north-star tolerance)."""
+    name, H, W, D, M, pairnet = cfg
+    w = helpers.oracle_weights(oracle, synth, 7, n_depth_levels=D)
+    mods = helpers.build_product_modules(w, n_depth_levels=D, pairnet=pairnet)
+    clip = synth.make_clip(0, 3, H, W, M)
+    K = T(clip["K"])[None]
+    st_o, st_p = oracle.FusionnetState(), helpers.ProductState()
+    with torch.no_grad():
+        for ref_i, meas_i in clip["frames"]:
+            ri, rp = T(clip["images"][ref_i])[None], T(clip["poses"][ref_i])[None]
+            mi, mp = [T(clip["images"][j])[None] for j in meas_i], [T(clip["poses"][j])[None] for j in meas_i]
+            if pairnet:
+                gold = oracle.pairnet_step(w, ri, rp, mi, mp, K, n_depth_levels=D)
+            else:
+                gold, st_o = oracle.fusionnet_step(w, st_o, ri, rp, mi, mp, K, n_depth_levels=D)
+            pred, st_p = helpers.product_fusionnet_step(mods, st_p, ri.to(DEV), rp.to(DEV), [x.to(DEV) for x in mi],
+                                                        [p.to(DEV) for p in mp], K.to(DEV), n_depth_levels=D)
+            e = oracle.rel_l1_inverse_depth(pred.cpu().numpy(), gold.numpy())
+            assert e <= 1e-3, "%s frame ref=%d: %.3e" % (name, ref_i, e)

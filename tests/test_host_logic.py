@@ -1,0 +1,124 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/dvmvs_b200.h declares,
+argument validation works without a GPU, the drop-in modules carry the reference's state-dict contract, and the
+geometry prologue (run on the host through a test hook) matches numpy."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests import scene_fixture
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dvmvs import _native as N
+    header = open(os.path.join(REPO, "include", "dvmvs_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(dvmvs_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    lib = N.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), "libdvmvs_sm100.so does not export %s" % sym
+    assert sorted(N.EXPORTED_SYMBOLS) == declared
+    assert lib.dvmvs_abi_version() == 1
+
+
+def test_conv_desc_struct_matches_header_field_order():
+    from dvmvs import _native as N
+    header = open(os.path.join(REPO, "include", "dvmvs_b200.h")).read()
+    body = header[header.index("typedef struct {"):header.index("} dvmvs_conv_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"[\s\*]([A-Za-z_][A-Za-z0-9_]*)(?:\[3\])?\s*[;,]", body)
+    assert names == [f[0] for f in N.ConvDesc._fields_], names
+
+
+def test_argument_validation_without_gpu():
+    from dvmvs import _native as N
+    lib = N.lib()
+    rc = lib.dvmvs_plane_sweep_fused(None, None, None, None, None, None, 1, 32, 8, 8, 4, 1, 0.25, 20.0, 0, None)
+    assert rc == -1 and b"null" in lib.dvmvs_last_error_string()
+    d = N.ConvDesc()
+    d.n_src = 7
+    assert lib.dvmvs_conv2d(ctypes.byref(d), None) == -1
+    assert lib.dvmvs_dwconv2d(None, None, None, None, 1, 8, 8, 6, 3, 1, 0, None) == -1
+    assert lib.dvmvs_lstm_gates(None, None, None, None, 1, 8, 8, 512, None) == -1
+
+
+def test_ops_refuse_cpu_tensors_loudly():
+    from dvmvs.fusionnet.model import FeatureExtractor
+    from dvmvs.utils import cost_volume_fusion, warp_frame_depth
+    x = torch.zeros(1, 32, 8, 8)
+    with pytest.raises(RuntimeError):
+        cost_volume_fusion(x, [x], torch.eye(4)[None], [torch.eye(4)[None]], torch.eye(3)[None], None, 0.25, 20.0, 8, "cpu", True)
+    with pytest.raises(TypeError):
+        warp_frame_depth(None, x, x, x)
+    with pytest.raises(ValueError):
+        warp_frame_depth(x, x, torch.eye(4)[None], torch.eye(3)[None])      # depth must be (B,1,H,W)
+    fe = FeatureExtractor().eval()
+    with pytest.raises(RuntimeError):
+        fe(torch.zeros(1, 3, 64, 64))                                       # CPU module / tensor: no fallback
+    with pytest.raises(RuntimeError):
+        FeatureExtractor()(torch.zeros(1, 3, 64, 64))                       # training mode: inference only
+
+
+def test_state_dict_contract(oracle):
+    from dvmvs.fusionnet import model as fm
+    from dvmvs.pairnet import model as pm
+    shapes = oracle.state_dict_shapes(64)
+    for tag, cls in (("fe", fm.FeatureExtractor), ("fpn", fm.FeatureShrinker), ("cve", fm.CostVolumeEncoder),
+                     ("lstm", fm.LSTMFusion), ("cvd", fm.CostVolumeDecoder)):
+        sd = cls().state_dict()
+        assert list(sd.keys()) == list(shapes[tag].keys()), tag
+        assert all(tuple(sd[k].shape) == tuple(shapes[tag][k]) for k in sd), tag
+    assert not hasattr(pm, "LSTMFusion")
+    for net in ("fusionnet", "pairnet"):
+        w = scene_fixture.load_shipped_weights(net)
+        if w is None:
+            continue
+        mod = fm if net == "fusionnet" else pm
+        classes = {"fe": mod.FeatureExtractor, "fpn": mod.FeatureShrinker, "cve": mod.CostVolumeEncoder,
+                   "cvd": mod.CostVolumeDecoder}
+        if net == "fusionnet":
+            classes["lstm"] = mod.LSTMFusion
+        for tag, cls in classes.items():
+            cls().load_state_dict(w[tag], strict=True)
+
+
+def test_bn_folding_matches_conv_bn(synth):
+    from dvmvs import _ops as ops
+    conv = torch.nn.Conv2d(8, 12, 3, padding=1, bias=False)
+    bn = torch.nn.BatchNorm2d(12).eval()
+    sd = synth.make_state_dict({"weight": (12,), "bias": (12,), "running_mean": (12,), "running_var": (12,)}, seed=9)
+    with torch.no_grad():
+        for k, v in sd.items():
+            getattr(bn, k).copy_(torch.from_numpy(v))
+        pc = ops.PackedConv(conv.weight, None, bn)
+        x = torch.randn(1, 8, 6, 6)
+        ref = bn(conv(x))
+        w = pc.weight.permute(3, 2, 0, 1)        # [k][k][Cin][Cout] -> (Cout, Cin, k, k)
+        got = torch.nn.functional.conv2d(x, w, pc.bias, 1, 1)
+    assert float((ref - got).abs().max()) < 1e-5
+
+
+def test_geometry_prologue_on_host_matches_numpy(synth):
+    from dvmvs import _native as N
+    lib = N.lib()
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.dvmvs_host_sweep_geometry.argtypes = [fp, fp, fp, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_float, ctypes.c_float, fp, fp]
+    p1, p2 = synth.camera_pose(3), synth.camera_pose(1)
+    K = synth.intrinsics(256, 256).copy()
+    K[0:2] /= 2
+    out, xy = np.zeros(12, np.float32), np.zeros(2, np.float32)
+    f = lambda a: a.ctypes.data_as(fp)
+    for (u, v, d) in ((0, 0, 0), (17, 90, 31), (127, 127, 63)):
+        assert lib.dvmvs_host_sweep_geometry(f(p1), f(p2), f(K), u, v, 128, 128, d, 64, 0.25, 20.0, f(out), f(xy)) == 0
+        E = np.linalg.inv(p2.astype(np.float64)) @ p1
+        G = K @ E[:3, :3] @ np.linalg.inv(K.astype(np.float64))
+        Kt = K @ E[:3, 3]
+        assert np.abs(out[:9].reshape(3, 3) - G).max() < 1e-4 and np.abs(out[9:] - Kt).max() < 1e-4
+        q = G @ np.array([u, v, 1.0]) + Kt * (1 / 20.0 + d * (1 / 0.25 - 1 / 20.0) / 63)
+        assert abs(xy[0] - q[0] / (q[2] + 1e-8) * 127 / 128) < 2e-3 and abs(xy[1] - q[1] / (q[2] + 1e-8) * 127 / 128) < 2e-3
