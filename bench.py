@@ -42,35 +42,42 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
 
 
+def log(msg):
+    print("[bench] " + msg, file=sys.stderr, flush=True)
+
+
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region via NVML in-process (no fork of a CUDA process)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.samples, self.stop_flag, self.max_mhz = index, [], threading.Event(), None
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self.stop_flag.is_set():
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((mhz, [n for n, b in bits.items() if r & b]))
+                self.stop_flag.wait(0.05)
+        except Exception as e:  # noqa: BLE001
+            self.samples.append((None, ["nvml unavailable: %s" % e]))
 
     def summary(self):
         self.stop_flag.set()
-        self.join(timeout=6)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+        self.join(timeout=5)
+        mhz = sorted(m for m, _ in self.samples if m is not None)
+        reasons = sorted({r for _, rs in self.samples for r in rs})
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
                 "samples": len(self.samples)}
 
 
@@ -112,6 +119,7 @@ def run_ours(args, rank, world, local_rank):
         m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes, seed=7).items()}, strict=True)
         m.to(dev).eval()
 
+    log("modules built; staging %d frames" % n_frames)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
 
     def barrier():
@@ -144,6 +152,7 @@ def run_ours(args, rank, world, local_rank):
         wall1 = time.perf_counter()
         barrier()
     launches = _native.launch_count() - launches0
+    log("device-resident arm done")
     clocks = sampler.summary()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     assert bool(torch.isfinite(pred).all()), "non-finite depth"
@@ -178,6 +187,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         barrier()
     e2e_ms = e0.elapsed_time(e1)
+    log("e2e arm done")
 
     # ---------------- roofline of the dominant geometric kernel: fused plane sweep, timed alone
     from dvmvs import _ops as ops
@@ -196,6 +206,7 @@ def run_ours(args, rank, world, local_rank):
         b.record()
     torch.cuda.synchronize()
     sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in sw_ev]))
+    log("roofline arm done: plane sweep %.3f ms" % sweep_ms)
 
     # ---------------- max over ranks
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -226,12 +237,19 @@ def run_ours(args, rank, world, local_rank):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arms
+def host_threads():
+    """Threads the CPU arm uses: torch's default intra-op pool (physical cores), capped -- oversubscribing SMT
+    siblings with OpenMP spin-waits makes the many tiny ops of the plane sweep crawl."""
+    return max(1, min(torch.get_num_threads(), 64))
+
+
 def cpu_baseline(n_frames, threads):
     """The oracle (restatement of the reference's PyTorch-CPU path) on the host cores: a bounded sample of the same
     workload (n_frames recurrent keyframes of ONE c2 clip, after one warm-up frame)."""
     import synth_data as synth
     from oracle import dvmvs_oracle as oracle
     torch.set_num_threads(threads)
+    log("cpu baseline: oracle on %d threads, %d frames" % (threads, n_frames))
     shapes = oracle.state_dict_shapes(D)
     w = {tag: {k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes[tag], seed=7).items()} for tag in shapes}
     clip = synth.make_clip(0, n_frames + 1, H, W, M)
@@ -245,6 +263,8 @@ def cpu_baseline(n_frames, threads):
                                           [torch.from_numpy(clip["images"][j])[None] for j in meas_i],
                                           [torch.from_numpy(clip["poses"][j])[None] for j in meas_i], K, n_depth_levels=D)
             times.append(time.perf_counter() - t0)
+            if sum(times) > 45.0 and len(times) >= 3:          # bounded sample
+                break
     times = times[1:]
     return {"value": len(times) / sum(times), "unit": "frames/s", "cores": threads, "kind": "port",
             "sample": "%d recurrent keyframes of one c2 clip (256x256, D=64, M=2) after 1 warm-up, torch %s CPU, %d threads"
@@ -252,7 +272,7 @@ def cpu_baseline(n_frames, threads):
 
 
 def run_reference(args):
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     per_step = 2
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
@@ -294,7 +314,8 @@ def main():
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     result = run_ours(args, rank, world, local_rank)
     if rank == 0:
-        result["cpu_baseline"] = cpu_baseline(args.cpu_frames, os.cpu_count() or 1)
+        if args.cpu_frames > 0:
+            result["cpu_baseline"] = cpu_baseline(args.cpu_frames, host_threads())
         print(json.dumps(result))
     if world > 1:
         import torch.distributed as dist

@@ -19,6 +19,7 @@ constexpr int kConvThreads = 128; // 8 channel groups (x4) x 16 pixel groups (x8
 struct ConvParams {
   dvmvs_conv_desc d;
   int Hout, Wout, Cin, tiles_x, tiles_y, ksplit, chunks_total;
+  size_t out_elems;
   int src_cin_offset[3];
 };
 
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(kConvThreads) conv2d_direct_kernel(ConvParams 
       const int c = n0 + tx * 4 + n;
       if (c >= d.Cout) continue;
       if (p.ksplit > 1) {
-        atomicAdd(d.out + o + c, acc[j][n]);
+        d.workspace[(size_t)split * p.out_elems + o + c] = acc[j][n];      // partial sum; reduced in fixed order later
       } else {
         float v = acc[j][n];
         if (d.bias) v += __ldg(d.bias + c);
@@ -192,7 +193,8 @@ __global__ void conv_epilogue_kernel(ConvParams p) {
   const int ox = (int)(pix % p.Wout);
   const int oy = (int)((pix / p.Wout) % p.Hout);
   const int b = (int)(pix / ((size_t)p.Wout * p.Hout));
-  float v = d.out[idx];
+  float v = 0.f;
+  for (int sp = 0; sp < p.ksplit; ++sp) v += d.workspace[(size_t)sp * p.out_elems + idx];   // deterministic order
   if (d.bias) v += __ldg(d.bias + c);
   if (d.residual_mode != DVMVS_RES_NONE) v += residual_at(d, p.Hout, p.Wout, b, oy, ox, c);
   v = apply_act(v, d.act);
@@ -451,14 +453,12 @@ extern "C" int dvmvs_conv2d(const dvmvs_conv_desc* desc, dvmvs_stream_t stream) 
   p.tiles_y = (p.Hout + TH - 1) / TH;
   const int ctas = p.tiles_x * p.tiles_y * ((d.Cout + TN - 1) / TN) * d.B;
   p.ksplit = 1;
-  if (ctas < 96 && p.chunks_total >= 8) {          // under-filled grid: split the reduction over input-channel chunks
+  p.out_elems = (size_t)d.B * p.Hout * p.Wout * d.Cout;
+  if (ctas < 96 && p.chunks_total >= 8 && d.workspace) {   // under-filled grid: split the reduction over input-channel chunks
     int want = (296 + ctas - 1) / ctas;
     int maxsplit = p.chunks_total / 4;
-    p.ksplit = max(1, min(want, maxsplit));
-  }
-  if (p.ksplit > 1) {
-    cudaError_t e = cudaMemsetAsync(d.out, 0, (size_t)d.B * p.Hout * p.Wout * d.Cout * sizeof(float), s);
-    if (e != cudaSuccess) { set_error("conv2d memset: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
+    long long fit = d.workspace_bytes / (long long)(p.out_elems * sizeof(float));
+    p.ksplit = (int)max(1LL, min((long long)min(want, maxsplit), fit));
   }
   int rc;
   if (d.ksize == 1 && d.stride == 1) rc = launch_conv<1, 1>(p, s);

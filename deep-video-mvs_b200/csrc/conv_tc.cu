@@ -1,0 +1,549 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed tiles).
+// sm_100a only.
+//
+//   D[128 output pixels x BLOCK_N output channels] (fp32, TMEM) += A[128 x K] . W[BLOCK_N x K]^T
+//
+// * A is never materialised: for every filter tap (ky,kx) and every 32/64-channel chunk of every concatenated
+//   source, ONE 4-D TMA box {channels, TW, TH, 1} of the channel-last fp16 activation tensor is loaded at the
+//   tap-shifted coordinates; out-of-image pixels and channels beyond the tensor are zero-filled by the TMA unit
+//   (= zero padding and channel padding for free).  The box lands in shared memory as 128 rows of 64/128 bytes in
+//   the canonical K-major SWIZZLE_64B/128B layout that the UMMA shared-memory descriptor expects.
+// * torch.cat of the reference (model.py:112,115,208,...; convlstm.py:43) is a K-split over up to three sources.
+// * Precision: activations and weights are carried as fp16 (hi, lo) pairs, x = hi + lo to ~22 bits.  A k-block
+//   issues hi*hi + lo*hi + hi*lo (3 MMAs per K=16 step, fp32 accumulate), which reproduces fp32 convolution to
+//   ~1e-6 -- the parity budget (1e-3 on inverse depth) does not admit plain bf16/fp16/tf32.
+//   `terms` = 1 runs plain fp16 (hi*hi) for layers that tolerate it.
+// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+//   warps 2-5 = epilogue (tcgen05.ld -> bias/residual/activation -> fp32 and/or fp16-pair stores).
+//   smem ring of kStages stages, full/empty mbarriers, tcgen05.commit releases stages and signals the epilogue.
+// * Small-M layers (8x8 .. 16x16 maps) split K (filter taps) over blockIdx.z and reduce with fp32 red.global.add;
+//   a finishing kernel applies the epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dvmvs {
+
+// ----------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile: rows of (kchunk*2) bytes, 8-row swizzle atoms stacked at SBO bytes.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+         ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ----------------------------------------------------------------------------------------------- parameters
+constexpr int kTcThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kAStageBytes = kTileM * 128;   // one activation tile (64-channel chunk); 32-channel chunks use half
+
+struct TcParams {
+  CUtensorMap a_map[3][2];    // [source][hi/lo]
+  CUtensorMap w_map[2][2];    // [chunk kind: 0 = 32-wide (SW64), 1 = 64-wide (SW128)][hi/lo]
+  int src_chunks[3];          // number of K chunks per tap for each source
+  int src_kchunk[3];          // 32 or 64
+  int n_src, terms;           // terms: 1 = hi*hi, 3 = hi*hi + lo*hi + hi*lo
+  int ksize, pad, stride;
+  int B, Hout, Wout, Cout, tile_w, tile_h, tiles_x, tiles_y;
+  int ksplit, k_per_tap;      // k_per_tap: packed-weight columns consumed per tap
+  const float* bias;
+  const float* residual;
+  int residual_mode, Hr, Wr;
+  float* out_f32;             // [B][Hout][Wout][Cout] or null
+  __half* out_planes;         // [2][B][Hout][Wout][Cout] or null
+  float* aux_out;
+  float aux_mult, aux_base;
+  int act;
+  float* workspace;
+};
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+  if (act == DVMVS_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == DVMVS_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+template <int BLOCK_N>
+struct TcCfg {
+  static constexpr int kWStageBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = 2 * kAStageBytes + 2 * kWStageBytes;
+  static constexpr int kStages = (BLOCK_N <= 32) ? 4 : (BLOCK_N <= 64 ? 4 : 3);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+  const uint32_t bars = base + Cfg::kStages * Cfg::kStageBytes;
+  // barrier layout (8 bytes each): full[kStages], empty[kStages], tmem_full; then the TMEM base address word
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (Cfg::kStages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * Cfg::kStages);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int b = blockIdx.x / tiles_per_img;
+  const int t_in = blockIdx.x - b * tiles_per_img;
+  const int oy0 = (t_in / p.tiles_x) * p.tile_h, ox0 = (t_in % p.tiles_x) * p.tile_w;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int n_taps = p.ksize * p.ksize;
+  const int taps_per_split = (n_taps + p.ksplit - 1) / p.ksplit;
+  const int tap_begin = blockIdx.z * taps_per_split, tap_end = min(n_taps, tap_begin + taps_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_src; ++s) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map[s][0]) : "memory");
+      if (p.terms > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map[s][1]) : "memory");
+    }
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "n"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tap = tap_begin; tap < tap_end; ++tap) {
+        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+        const int iy = oy0 * p.stride - p.pad + ky, ix = ox0 * p.stride - p.pad + kx;
+        int wk = tap * p.k_per_tap;
+        for (int s = 0; s < p.n_src; ++s) {
+          const int kc = p.src_kchunk[s];
+          const int kind = (kc == 64) ? 1 : 0;
+          for (int ch = 0; ch < p.src_chunks[s]; ++ch, wk += kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sb = base + stage * Cfg::kStageBytes;
+            const uint32_t a_bytes = kTileM * kc * 2, w_bytes = BLOCK_N * kc * 2;
+            mbar_expect_tx(full_bar(stage), (p.terms > 1 ? 2u : 1u) * (a_bytes + w_bytes));
+            tma_load_4d(sb, &p.a_map[s][0], full_bar(stage), ch * kc, ix, iy, b);
+            tma_load_2d(sb + 2 * kAStageBytes, &p.w_map[kind][0], full_bar(stage), wk, n0);
+            if (p.terms > 1) {
+              tma_load_4d(sb + kAStageBytes, &p.a_map[s][1], full_bar(stage), ch * kc, ix, iy, b);
+              tma_load_2d(sb + 2 * kAStageBytes + Cfg::kWStageBytes, &p.w_map[kind][1], full_bar(stage), wk, n0);
+            }
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer (one thread) ==============================
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=F16, both K-major, N = BLOCK_N, M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      for (int tap = tap_begin; tap < tap_end; ++tap) {
+        for (int s = 0; s < p.n_src; ++s) {
+          const int kc = p.src_kchunk[s];
+          const uint32_t layout = (kc == 64) ? 2u : 4u;           // SWIZZLE_128B : SWIZZLE_64B
+          const uint32_t sbo = (kc == 64) ? 1024u : 512u;         // 8 rows x row bytes
+          for (int ch = 0; ch < p.src_chunks[s]; ++ch) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sb = base + stage * Cfg::kStageBytes;
+            const uint32_t a_hi = sb, a_lo = sb + kAStageBytes;
+            const uint32_t w_hi = sb + 2 * kAStageBytes, w_lo = w_hi + Cfg::kWStageBytes;
+            for (int term = 0; term < p.terms; ++term) {
+              const uint32_t a_s = (term == 1) ? a_lo : a_hi;
+              const uint32_t w_s = (term == 2) ? w_lo : w_hi;
+              for (int k = 0; k < kc / 16; ++k) {
+                tc_mma_f16(tmem_base, umma_desc(a_s + k * 32, sbo, layout), umma_desc(w_s + k * 32, sbo, layout), idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            tc_commit(empty_bar(stage));     // stage reusable once these MMAs have consumed it
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+      tc_commit(tmem_full_bar);              // accumulator complete
+    }
+  } else {
+    // ============================== epilogue (warps 2..5) ==============================
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int ty = row / p.tile_w, tx = row - ty * p.tile_w;
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    const bool valid = (oy < p.Hout) && (ox < p.Wout);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
+    const size_t plane_stride = (size_t)p.B * p.Hout * p.Wout * p.Cout;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (!valid) continue;
+      const int cbase = n0 + c0;
+      if (p.ksplit > 1) {   // partial sums of this tap range; reduced in fixed order by conv_tc_finish_kernel
+        float* wsp = p.workspace + (size_t)blockIdx.z * plane_stride + pix * p.Cout + cbase;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cbase + j < p.Cout) wsp[j] = v[j];
+        continue;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = cbase + j;
+        if (c < p.Cout) {
+          float x = v[j];
+          if (p.bias) x += __ldg(p.bias + c);
+          if (p.residual_mode == DVMVS_RES_SAME) {
+            x += __ldg(p.residual + pix * p.Cout + c);
+          } else if (p.residual_mode == DVMVS_RES_NEAREST_UP) {
+            const int ry = (int)(((long long)oy * p.Hr) / p.Hout), rx = (int)(((long long)ox * p.Wr) / p.Wout);
+            x += __ldg(p.residual + (((size_t)b * p.Hr + ry) * p.Wr + rx) * p.Cout + c);
+          }
+          v[j] = tc_act(x, p.act);
+        }
+      }
+      const bool vec = ((p.Cout & 7) == 0) && (cbase + 32 <= p.Cout);
+      if (p.out_f32) {
+        float* o = p.out_f32 + pix * p.Cout + cbase;
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (cbase + j < p.Cout) o[j] = v[j];
+        }
+      }
+      if (p.aux_out) {
+        for (int j = 0; j < 32; ++j)
+          if (cbase + j < p.Cout) p.aux_out[pix * p.Cout + cbase + j] = 1.f / (p.aux_mult * v[j] + p.aux_base);
+      }
+      if (p.out_planes) {
+        __half* oh = p.out_planes + pix * p.Cout + cbase;
+        __half* ol = oh + plane_stride;
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              hi[e] = __float2half_rn(v[j + e]);
+              lo[e] = __float2half_rn(v[j + e] - __half2float(hi[e]));
+            }
+            *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(ol + j) = *reinterpret_cast<const uint4*>(lo);
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (cbase + j < p.Cout) {
+              const __half h = __float2half_rn(v[j]);
+              oh[j] = h;
+              ol[j] = __float2half_rn(v[j] - __half2float(h));
+            }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// finishing pass for split-K launches: bias / residual / activation in place, fp16-pair copy
+__global__ void conv_tc_finish_kernel(TcParams p) {
+  const size_t total = (size_t)p.B * p.Hout * p.Wout * p.Cout;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % p.Cout);
+  const size_t pix = idx / p.Cout;
+  const int ox = (int)(pix % p.Wout);
+  const int oy = (int)((pix / p.Wout) % p.Hout);
+  const int b = (int)(pix / ((size_t)p.Wout * p.Hout));
+  float x = 0.f;
+  for (int sp = 0; sp < p.ksplit; ++sp) x += p.workspace[(size_t)sp * total + idx];
+  if (p.bias) x += __ldg(p.bias + c);
+  if (p.residual_mode == DVMVS_RES_SAME) {
+    x += __ldg(p.residual + idx);
+  } else if (p.residual_mode == DVMVS_RES_NEAREST_UP) {
+    const int ry = (int)(((long long)oy * p.Hr) / p.Hout), rx = (int)(((long long)ox * p.Wr) / p.Wout);
+    x += __ldg(p.residual + (((size_t)b * p.Hr + ry) * p.Wr + rx) * p.Cout + c);
+  }
+  x = tc_act(x, p.act);
+  if (p.out_f32) p.out_f32[idx] = x;
+  if (p.aux_out) p.aux_out[idx] = 1.f / (p.aux_mult * x + p.aux_base);
+  if (p.out_planes) {
+    const __half h = __float2half_rn(x);
+    p.out_planes[idx] = h;
+    p.out_planes[total + idx] = __float2half_rn(x - __half2float(h));
+  }
+}
+
+// fp32 channel-last -> fp16 (hi, lo) planes with the channel count padded to Cs (zeros); optional x2 bilinear
+// (align_corners) upsampling on the way (materialises F.interpolate for the TMA-fed consumer).
+__global__ void split_planes_kernel(const float* __restrict__ x, __half* __restrict__ planes, int B, int H, int W, int C, int Cs,
+                                    int upsample) {
+  const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
+  const size_t total = (size_t)B * Ho * Wo * Cs;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % Cs);
+  const size_t pix = idx / Cs;
+  float v = 0.f;
+  if (c < C) {
+    if (!upsample) {
+      v = x[pix * C + c];
+    } else {
+      const int ox = (int)(pix % Wo);
+      const int oy = (int)((pix / Wo) % Ho);
+      const int b = (int)(pix / ((size_t)Wo * Ho));
+      const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+      const float sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+      const float fy = sh * oy, fx = sw * ox;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+      const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+      const float* bp = x + (size_t)b * H * W * C + c;
+      v = ly0 * (lx0 * bp[((size_t)y0 * W + x0) * C] + lx1 * bp[((size_t)y0 * W + x1) * C]) +
+          ly1 * (lx0 * bp[((size_t)y1 * W + x0) * C] + lx1 * bp[((size_t)y1 * W + x1) * C]);
+    }
+  }
+  const __half h = __float2half_rn(v);
+  planes[idx] = h;
+  planes[total + idx] = __float2half_rn(v - __half2float(h));
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static int make_act_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int Cs, int kchunk, int tile_w, int tile_h,
+                        int stride) {
+  cuuint64_t dims[4] = {(cuuint64_t)Cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kchunk, (cuuint32_t)((tile_w - 1) * stride + 1), (cuuint32_t)((tile_h - 1) * stride + 1), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, kchunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation B=%d H=%d W=%d C=%d chunk=%d) failed: %d", B, H, W, Cs, kchunk, (int)r);
+    return DVMVS_EINVAL;
+  }
+  return DVMVS_OK;
+}
+
+static int make_w_map(CUtensorMap* map, const void* ptr, int rows, int ktot, int kchunk, int block_n) {
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kchunk, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, kchunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weights rows=%d K=%d chunk=%d) failed: %d", rows, ktot, kchunk, (int)r);
+    return DVMVS_EINVAL;
+  }
+  return DVMVS_OK;
+}
+
+template <int BLOCK_N>
+static int launch_tc(const TcParams& p, dim3 grid, cudaStream_t s) {
+  using Cfg = TcCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("conv_tc smem attribute: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
+    attr_set = true;
+  }
+  conv_tc_kernel<BLOCK_N><<<grid, kTcThreads, Cfg::kSmemBytes, s>>>(p);
+  return check_launch("conv_tc_kernel");
+}
+
+}  // namespace dvmvs
+
+using namespace dvmvs;
+
+extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(d != nullptr, "conv2d_tc: null descriptor");
+  DVMVS_REQUIRE(encode_fn() != nullptr, "conv2d_tc: cuTensorMapEncodeTiled entry point not available");
+  DVMVS_REQUIRE(d->n_src >= 1 && d->n_src <= 3, "conv2d_tc: n_src=%d", d->n_src);
+  DVMVS_REQUIRE(d->ksize == 1 || d->ksize == 3 || d->ksize == 5, "conv2d_tc: ksize=%d", d->ksize);
+  DVMVS_REQUIRE(d->stride == 1 || d->stride == 2, "conv2d_tc: stride=%d", d->stride);
+  DVMVS_REQUIRE(d->terms == 1 || d->terms == 3, "conv2d_tc: terms=%d", d->terms);
+  DVMVS_REQUIRE(d->B > 0 && d->Hin > 0 && d->Win > 0 && d->Cout > 0 && d->w_hi && (d->terms == 1 || d->w_lo),
+                "conv2d_tc: bad shape / null weights");
+  DVMVS_REQUIRE(d->out_f32 || d->out_planes, "conv2d_tc: no output");
+  DVMVS_REQUIRE(d->block_n == 32 || d->block_n == 64 || d->block_n == 128, "conv2d_tc: block_n=%d", d->block_n);
+  DVMVS_REQUIRE(d->w_rows % d->block_n == 0 && d->w_rows >= d->Cout, "conv2d_tc: weight rows %d not a multiple of block_n", d->w_rows);
+  DVMVS_REQUIRE(d->out_planes == nullptr || d->Cout % 8 == 0, "conv2d_tc: fp16-pair output needs Cout %% 8 == 0");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const int pad = (d->ksize - 1) / 2;
+  p.ksize = d->ksize; p.pad = pad; p.stride = d->stride;
+  p.Hout = (d->Hin + 2 * pad - d->ksize) / d->stride + 1;
+  p.Wout = (d->Win + 2 * pad - d->ksize) / d->stride + 1;
+  p.B = d->B; p.Cout = d->Cout;
+  // output-pixel tile: 16 wide x 8 high, or 8 x 16 for narrow maps
+  p.tile_w = (p.Wout <= 8 && p.Hout > 8) ? 8 : 16;
+  p.tile_h = kTileM / p.tile_w;
+  p.tiles_x = (p.Wout + p.tile_w - 1) / p.tile_w;
+  p.tiles_y = (p.Hout + p.tile_h - 1) / p.tile_h;
+  p.n_src = d->n_src; p.terms = d->terms;
+  int k_per_tap = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    const int Cs = d->src_channels[s];
+    DVMVS_REQUIRE(d->src_planes[s] && Cs > 0 && Cs % 8 == 0, "conv2d_tc: source %d needs a channel count that is a multiple of 8", s);
+    DVMVS_REQUIRE((uintptr_t)d->src_planes[s] % 16 == 0, "conv2d_tc: source %d not 16-byte aligned", s);
+    p.src_kchunk[s] = (Cs % 64 == 0) ? 64 : 32;
+    p.src_chunks[s] = (Cs + p.src_kchunk[s] - 1) / p.src_kchunk[s];
+    k_per_tap += p.src_chunks[s] * p.src_kchunk[s];
+    const size_t plane = (size_t)d->B * d->Hin * d->Win * Cs;
+    int rc = make_act_map(&p.a_map[s][0], d->src_planes[s], d->B, d->Hin, d->Win, Cs, p.src_kchunk[s], p.tile_w, p.tile_h, d->stride);
+    if (rc != DVMVS_OK) return rc;
+    if (d->terms > 1) {
+      rc = make_act_map(&p.a_map[s][1], (const __half*)d->src_planes[s] + plane, d->B, d->Hin, d->Win, Cs, p.src_kchunk[s], p.tile_w,
+                        p.tile_h, d->stride);
+      if (rc != DVMVS_OK) return rc;
+    }
+  }
+  p.k_per_tap = k_per_tap;
+  DVMVS_REQUIRE(d->ktot == k_per_tap * d->ksize * d->ksize, "conv2d_tc: packed weight K=%d, expected %d", d->ktot,
+                k_per_tap * d->ksize * d->ksize);
+  for (int kind = 0; kind < 2; ++kind) {
+    const int kc = kind ? 64 : 32;
+    int rc = make_w_map(&p.w_map[kind][0], d->w_hi, d->w_rows, d->ktot, kc, d->block_n);
+    if (rc != DVMVS_OK) return rc;
+    if (d->terms > 1) {
+      rc = make_w_map(&p.w_map[kind][1], d->w_lo, d->w_rows, d->ktot, kc, d->block_n);
+      if (rc != DVMVS_OK) return rc;
+    }
+  }
+  p.bias = d->bias; p.residual = d->residual; p.residual_mode = d->residual_mode; p.Hr = d->Hr; p.Wr = d->Wr;
+  DVMVS_REQUIRE(d->residual_mode == DVMVS_RES_NONE || d->residual, "conv2d_tc: residual pointer missing");
+  p.out_f32 = d->out_f32; p.out_planes = (__half*)d->out_planes; p.aux_out = d->aux_out;
+  p.aux_mult = d->aux_mult; p.aux_base = d->aux_base; p.act = d->act;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_tiles = (d->Cout + d->block_n - 1) / d->block_n;
+  const int ctas = p.tiles_x * p.tiles_y * d->B * n_tiles;
+  p.ksplit = 1;
+  const int n_taps = d->ksize * d->ksize;
+  p.workspace = d->workspace;
+  const size_t out_elems = (size_t)d->B * p.Hout * p.Wout * d->Cout;
+  if (d->allow_split && d->workspace && ctas < 74 && n_taps > 1) {
+    long long fit = d->workspace_bytes / (long long)(out_elems * sizeof(float));
+    p.ksplit = (int)max(1LL, min((long long)min(n_taps, (148 + ctas - 1) / ctas), fit));
+    const int per = (n_taps + p.ksplit - 1) / p.ksplit;
+    p.ksplit = (n_taps + per - 1) / per;              // no empty splits
+  }
+  dim3 grid(p.tiles_x * p.tiles_y * d->B, n_tiles, p.ksplit);
+  int rc;
+  if (d->block_n == 32) rc = launch_tc<32>(p, grid, s);
+  else if (d->block_n == 64) rc = launch_tc<64>(p, grid, s);
+  else rc = launch_tc<128>(p, grid, s);
+  if (rc != DVMVS_OK) return rc;
+  if (p.ksplit > 1) {
+    const size_t total = (size_t)d->B * p.Hout * p.Wout * d->Cout;
+    conv_tc_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+    return check_launch("conv_tc_finish_kernel");
+  }
+  return DVMVS_OK;
+}
+
+extern "C" int dvmvs_split_planes(const float* x, void* planes, int B, int H, int W, int C, int Cs, int upsample2x,
+                                  dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(x && planes && B > 0 && H > 0 && W > 0 && C > 0 && Cs >= C && Cs % 8 == 0, "split_planes: bad argument");
+  const size_t total = (size_t)B * H * W * Cs * (upsample2x ? 4 : 1);
+  split_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)planes, B, H, W, C, Cs, upsample2x);
+  return check_launch("split_planes_kernel");
+}

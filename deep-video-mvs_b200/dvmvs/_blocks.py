@@ -31,14 +31,14 @@ class StandardLayer(NativeModule):
         self.conv2 = conv_layer(channels, channels, kernel_size, 1, apply_bn_relu)
 
     def _pack(self):
-        return pack_cbr(self.conv1), pack_cbr(self.conv2)
+        return ops.ConvLayer(pack_cbr(self.conv1)), ops.ConvLayer(pack_cbr(self.conv2))
 
     def run(self, x):
         c1, c2 = self.packed()
-        return ops.conv2d([(ops.conv2d([(x, D)], c1), D)], c2)
+        return c2.run([(c1.run([(x, D)]), D)])
 
     def forward(self, x):
-        return ops.to_api(self.run(ops.to_nhwc(x)))
+        return ops.act_to_api(self.run(ops.to_act(x)))
 
 
 class DownconvolutionLayer(NativeModule):
@@ -47,13 +47,13 @@ class DownconvolutionLayer(NativeModule):
         self.down_conv = conv_layer(input_channels, output_channels, kernel_size, 2, True)
 
     def _pack(self):
-        return pack_cbr(self.down_conv, stride=2)
+        return ops.ConvLayer(pack_cbr(self.down_conv, stride=2))
 
     def run(self, x):
-        return ops.conv2d([(x, D)], self.packed())
+        return self.packed().run([(x, D)])
 
     def forward(self, x):
-        return ops.to_api(self.run(ops.to_nhwc(x)))
+        return ops.act_to_api(self.run(ops.to_act(x)))
 
 
 class UpconvolutionLayer(NativeModule):
@@ -62,13 +62,13 @@ class UpconvolutionLayer(NativeModule):
         self.conv = conv_layer(input_channels, output_channels, kernel_size, 1, True)
 
     def _pack(self):
-        return pack_cbr(self.conv)
+        return ops.ConvLayer(pack_cbr(self.conv))
 
     def run(self, x):
-        return ops.conv2d([(x, U)], self.packed())        # F.interpolate(x2, bilinear, align_corners) fused into the loader
+        return self.packed().run([(x, U)])                # F.interpolate(x2, bilinear, align_corners) fused / staged by the loader
 
     def forward(self, x):
-        return ops.to_api(self.run(ops.to_nhwc(x)))
+        return ops.act_to_api(self.run(ops.to_act(x)))
 
 
 class EncoderBlock(NativeModule):
@@ -84,27 +84,30 @@ class EncoderBlock(NativeModule):
         return self.standard_convolution.run(self.down_convolution.run(x))
 
     def forward(self, x):
-        return ops.to_api(self.run(ops.to_nhwc(x)))
+        return ops.act_to_api(self.run(ops.to_act(x)))
 
 
 class DecoderBlock(NativeModule):
     def __init__(self, input_channels, output_channels, kernel_size, apply_bn_relu, plus_one):
         super().__init__()
+        self.plus_one = plus_one
         self.up_convolution = UpconvolutionLayer(input_channels, output_channels, kernel_size)
         self.convolution1 = conv_layer(input_channels + 1 if plus_one else input_channels, output_channels, kernel_size, 1, True)
         self.convolution2 = conv_layer(output_channels, output_channels, kernel_size, 1, apply_bn_relu)
 
     def _pack(self):
-        return pack_cbr(self.convolution1), pack_cbr(self.convolution2)
+        cout = self.convolution2[0].in_channels
+        split = [cout, self.convolution1[0].in_channels - cout - (1 if self.plus_one else 0)] + ([1] if self.plus_one else [])
+        return ops.ConvLayer(pack_cbr(self.convolution1), split), ops.ConvLayer(pack_cbr(self.convolution2))
 
     def run(self, x, skip, depth):
         c1, c2 = self.packed()
         x = self.up_convolution.run(x)
         srcs = [(x, D), (skip, D)] if depth is None else [(x, D), (skip, D), (depth, U)]   # cat fused (model.py:112-115)
-        return ops.conv2d([(ops.conv2d(srcs, c1), D)], c2)
+        return c2.run([(c1.run(srcs), D)])
 
     def forward(self, x, skip, depth):
-        return ops.to_api(self.run(ops.to_nhwc(x), ops.to_nhwc(skip), None if depth is None else ops.to_nhwc(depth)))
+        return ops.act_to_api(self.run(ops.to_act(x), ops.to_act(skip), None if depth is None else ops.to_act(depth)))
 
 
 # ------------------------------------------------------------------------------------------ MnasNet-1.0 trunk
@@ -146,32 +149,32 @@ class FeatureExtractor(NativeModule):
 
     def _pack(self):
         l1 = self.layer1
-        stem = (ops.PackedConv(l1[0].weight, None, l1[1], stride=2, act=N.ACT_RELU),
+        stem = (ops.ConvLayer(ops.PackedConv(l1[0].weight, None, l1[1], stride=2, act=N.ACT_RELU)),
                 ops.PackedDepthwise(l1[3].weight, l1[4], stride=1),
-                ops.PackedConv(l1[6].weight, None, l1[7], stride=1, act=N.ACT_NONE))
+                ops.ConvLayer(ops.PackedConv(l1[6].weight, None, l1[7], stride=1, act=N.ACT_NONE)))
         levels = []
         for layer in (self.layer2, self.layer3, self.layer4, self.layer5):
             blocks = []
             for stack in layer:
                 for blk in stack:
                     L = blk.layers
-                    blocks.append((ops.PackedConv(L[0].weight, None, L[1], act=N.ACT_RELU),
+                    blocks.append((ops.ConvLayer(ops.PackedConv(L[0].weight, None, L[1], act=N.ACT_RELU)),
                                    ops.PackedDepthwise(L[3].weight, L[4], stride=blk.stride),
-                                   ops.PackedConv(L[6].weight, None, L[7], act=N.ACT_NONE), blk.apply_residual))
+                                   ops.ConvLayer(ops.PackedConv(L[6].weight, None, L[7], act=N.ACT_NONE)), blk.apply_residual))
             levels.append(blocks)
         return stem, levels
 
     def run(self, x):
         stem, levels = self.packed()
-        x = ops.conv2d([(x, D)], stem[0])
-        x = ops.dwconv2d(x, stem[1])
-        x = ops.conv2d([(x, D)], stem[2])
+        x = stem[0].run([(x, D)])
+        x = ops.Act(ops.dwconv2d(x.f32, stem[1]))
+        x = stem[2].run([(x, D)])
         outs = [x]
         for blocks in levels:
             for expand, dw, project, residual in blocks:
-                y = ops.dwconv2d(ops.conv2d([(x, D)], expand), dw)
-                x = ops.conv2d([(y, D)], project, residual=x if residual else None,
-                               residual_mode=N.RES_SAME if residual else N.RES_NONE)
+                y = ops.Act(ops.dwconv2d(expand.run([(x, D)]).f32, dw))
+                x = project.run([(y, D)], residual=x if residual else None,
+                                residual_mode=N.RES_SAME if residual else N.RES_NONE)
             outs.append(x)
         return outs
 
@@ -179,7 +182,7 @@ class FeatureExtractor(NativeModule):
         B, C, H, W = image.shape
         if C != 3 or H % 32 != 0 or W % 32 != 0:
             raise RuntimeError("FeatureExtractor: expected (B,3,H,W) with H, W multiples of 32, got %s" % (tuple(image.shape),))
-        return tuple(ops.to_api(t) for t in self.run(ops.to_nhwc(image, "image")))
+        return tuple(ops.act_to_api(t) for t in self.run(ops.to_act(image, "image")))
 
 
 class _FPNHolder(torch.nn.Module):
@@ -202,22 +205,22 @@ class FeatureShrinker(NativeModule):
         self.fpn = _FPNHolder([16, 24, 40, 96, 320], fpn_output_channels)
 
     def _pack(self):
-        inner = [ops.PackedConv(m.weight, m.bias) for m in self.fpn.inner_blocks]
-        layer = [ops.PackedConv(m.weight, m.bias) for m in self.fpn.layer_blocks]
+        inner = [ops.ConvLayer(ops.PackedConv(m.weight, m.bias)) for m in self.fpn.inner_blocks]
+        layer = [ops.ConvLayer(ops.PackedConv(m.weight, m.bias)) for m in self.fpn.layer_blocks]
         return inner, layer
 
     def run(self, feats):
         inner, layer = self.packed()
-        last = ops.conv2d([(feats[4], D)], inner[4])
+        last = inner[4].run([(feats[4], D)])
         outs = [None] * 4
         for i in (3, 2, 1, 0):
-            last = ops.conv2d([(feats[i], D)], inner[i], residual=last, residual_mode=N.RES_NEAREST_UP)
-            outs[i] = ops.conv2d([(last, D)], layer[i])
+            last = inner[i].run([(feats[i], D)], residual=last, residual_mode=N.RES_NEAREST_UP)
+            outs[i] = layer[i].run([(last, D)])
         return outs
 
     def forward(self, layer1, layer2, layer3, layer4, layer5):
-        feats = [ops.to_nhwc(t, "layer%d" % (i + 1)) for i, t in enumerate((layer1, layer2, layer3, layer4, layer5))]
-        return tuple(ops.to_api(t) for t in self.run(feats))
+        feats = [ops.to_act(t, "layer%d" % (i + 1)) for i, t in enumerate((layer1, layer2, layer3, layer4, layer5))]
+        return tuple(ops.act_to_api(t) for t in self.run(feats))
 
 
 # ------------------------------------------------------------------------------------------ cost-volume encoder / decoder
@@ -235,25 +238,26 @@ class CostVolumeEncoder(NativeModule):
         self.encoder_block3 = EncoderBlock(h * 8, h * 16, 3)
 
     def _pack(self):
-        return [pack_cbr(a) for a in (self.aggregator0, self.aggregator1, self.aggregator2, self.aggregator3)]
+        return [ops.ConvLayer(pack_cbr(a), [fpn_output_channels, a[0].in_channels - fpn_output_channels])
+                for a in (self.aggregator0, self.aggregator1, self.aggregator2, self.aggregator3)]
 
     def run(self, f2, f4, f8, f16, cost_volume):
         agg = self.packed()
-        inp0 = ops.conv2d([(f2, D), (cost_volume, D)], agg[0])              # cat order model.py:208
+        inp0 = agg[0].run([(f2, D), (cost_volume, D)])                      # cat order model.py:208
         out0 = self.encoder_block0.run(inp0)
-        inp1 = ops.conv2d([(f4, D), (out0, D)], agg[1])
+        inp1 = agg[1].run([(f4, D), (out0, D)])
         out1 = self.encoder_block1.run(inp1)
-        inp2 = ops.conv2d([(f8, D), (out1, D)], agg[2])
+        inp2 = agg[2].run([(f8, D), (out1, D)])
         out2 = self.encoder_block2.run(inp2)
-        inp3 = ops.conv2d([(f16, D), (out2, D)], agg[3])
+        inp3 = agg[3].run([(f16, D), (out2, D)])
         out3 = self.encoder_block3.run(inp3)
         return inp0, inp1, inp2, inp3, out3
 
     def forward(self, features_half, features_quarter, features_one_eight, features_one_sixteen, cost_volume):
-        args = [ops.to_nhwc(t, n) for t, n in ((features_half, "features_half"), (features_quarter, "features_quarter"),
-                                               (features_one_eight, "features_one_eight"),
-                                               (features_one_sixteen, "features_one_sixteen"), (cost_volume, "cost_volume"))]
-        return tuple(ops.to_api(t) for t in self.run(*args))
+        args = [ops.to_act(t, n) for t, n in ((features_half, "features_half"), (features_quarter, "features_quarter"),
+                                              (features_one_eight, "features_one_eight"),
+                                              (features_one_sixteen, "features_one_sixteen"), (cost_volume, "cost_volume"))]
+        return tuple(ops.act_to_api(t) for t in self.run(*args))
 
 
 class CostVolumeDecoder(NativeModule):
@@ -274,29 +278,29 @@ class CostVolumeDecoder(NativeModule):
         self.depth_layer_full = depth_layer_3x3(h)
 
     def _pack(self):
-        heads = [pack_head(m) for m in (self.depth_layer_one_sixteen, self.depth_layer_one_eight, self.depth_layer_quarter,
-                                        self.depth_layer_half, self.depth_layer_full)]
-        return heads, pack_cbr(self.refine[0]), pack_cbr(self.refine[1])
+        heads = [ops.ConvLayer(pack_head(m)) for m in (self.depth_layer_one_sixteen, self.depth_layer_one_eight,
+                                                       self.depth_layer_quarter, self.depth_layer_half, self.depth_layer_full)]
+        return heads, ops.ConvLayer(pack_cbr(self.refine[0]), [hyper_channels, 1, 3]), ops.ConvLayer(pack_cbr(self.refine[1]))
 
     def run(self, image, skip0, skip1, skip2, skip3, bottom):
         heads, r0, r1 = self.packed()
         aux = (float(self.inverse_depth_multiplier), float(self.inverse_depth_base))    # depth = 1/(mult*sigmoid + base)
         d1 = self.decoder_block1.run(bottom, skip3, None)
-        s16, depth16 = ops.conv2d([(d1, D)], heads[0], aux=aux)
+        s16, depth16 = heads[0].run([(d1, D)], aux=aux)
         d2 = self.decoder_block2.run(d1, skip2, s16)
-        s8, depth8 = ops.conv2d([(d2, D)], heads[1], aux=aux)
+        s8, depth8 = heads[1].run([(d2, D)], aux=aux)
         d3 = self.decoder_block3.run(d2, skip1, s8)
-        s4, depth4 = ops.conv2d([(d3, D)], heads[2], aux=aux)
+        s4, depth4 = heads[2].run([(d3, D)], aux=aux)
         d4 = self.decoder_block4.run(d3, skip0, s4)
-        s2, depth2 = ops.conv2d([(d4, D)], heads[3], aux=aux)
-        x = ops.conv2d([(d4, U), (s2, U), (image, D)], r0)                                # cat order model.py:295
-        x = ops.conv2d([(x, D)], r1)
-        _, depth1 = ops.conv2d([(x, D)], heads[4], aux=aux)
+        s2, depth2 = heads[3].run([(d4, D)], aux=aux)
+        x = r0.run([(d4, U), (s2, U), (image, D)])                                        # cat order model.py:295
+        x = r1.run([(x, D)])
+        _, depth1 = heads[4].run([(x, D)], aux=aux)
         return [t.squeeze(3) for t in (depth1, depth2, depth4, depth8, depth16)]
 
     def forward(self, image, skip0, skip1, skip2, skip3, bottom):
-        args = [ops.to_nhwc(t, n) for t, n in ((image, "image"), (skip0, "skip0"), (skip1, "skip1"), (skip2, "skip2"),
-                                               (skip3, "skip3"), (bottom, "bottom"))]
+        args = [ops.to_act(t, n) for t, n in ((image, "image"), (skip0, "skip0"), (skip1, "skip1"), (skip2, "skip2"),
+                                              (skip3, "skip3"), (bottom, "bottom"))]
         return tuple(self.run(*args))
 
 

@@ -17,7 +17,7 @@ SWEEP_DOT, SWEEP_SAD = 0, 1
 # every symbol include/dvmvs_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "dvmvs_abi_version", "dvmvs_last_error_string", "dvmvs_kernel_launch_count", "dvmvs_plane_sweep_fused",
-    "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
+    "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_split_planes", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
     "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw",
 ]
 
@@ -33,6 +33,24 @@ class ConvDesc(ctypes.Structure):
         ("aux_mult", ctypes.c_float), ("aux_base", ctypes.c_float),
         ("B", ctypes.c_int), ("Hin", ctypes.c_int), ("Win", ctypes.c_int), ("Cout", ctypes.c_int),
         ("ksize", ctypes.c_int), ("stride", ctypes.c_int), ("act", ctypes.c_int),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_longlong),
+    ]
+
+
+class ConvTcDesc(ctypes.Structure):
+    """mirror of dvmvs_conv_tc_desc"""
+    _fields_ = [
+        ("src_planes", ctypes.c_void_p * 3), ("src_channels", ctypes.c_int * 3), ("n_src", ctypes.c_int),
+        ("w_hi", ctypes.c_void_p), ("w_lo", ctypes.c_void_p),
+        ("w_rows", ctypes.c_int), ("ktot", ctypes.c_int), ("block_n", ctypes.c_int), ("terms", ctypes.c_int),
+        ("allow_split", ctypes.c_int),
+        ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+        ("residual_mode", ctypes.c_int), ("Hr", ctypes.c_int), ("Wr", ctypes.c_int),
+        ("out_f32", ctypes.c_void_p), ("out_planes", ctypes.c_void_p), ("aux_out", ctypes.c_void_p),
+        ("aux_mult", ctypes.c_float), ("aux_base", ctypes.c_float),
+        ("B", ctypes.c_int), ("Hin", ctypes.c_int), ("Win", ctypes.c_int), ("Cout", ctypes.c_int),
+        ("ksize", ctypes.c_int), ("stride", ctypes.c_int), ("act", ctypes.c_int),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_longlong),
     ]
 
 
@@ -50,6 +68,8 @@ def lib():
         L.dvmvs_hidden_warp.argtypes = [p, p, p, p, p, p, i, i, i, i, f, p]
         L.dvmvs_depth_reproject.argtypes = [p, p, p, p, p, p, i, i, i, p]
         L.dvmvs_conv2d.argtypes = [ctypes.POINTER(ConvDesc), p]
+        L.dvmvs_conv2d_tc.argtypes = [ctypes.POINTER(ConvTcDesc), p]
+        L.dvmvs_split_planes.argtypes = [p, p, i, i, i, i, i, i, p]
         L.dvmvs_dwconv2d.argtypes = [p, p, p, p, i, i, i, i, i, i, i, p]
         L.dvmvs_lstm_gates.argtypes = [p, p, p, p, i, i, i, i, p]
         L.dvmvs_upsample2x.argtypes = [p, p, i, i, i, i, p]

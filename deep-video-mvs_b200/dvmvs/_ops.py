@@ -13,6 +13,19 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_WORKSPACE = {}
+WORKSPACE_BYTES = 32 << 20
+
+
+def workspace(device):
+    """Per-device scratch for the deterministic split-K reductions of small-map convolutions (allocated once)."""
+    key = (device.type, device.index)
+    ws = _WORKSPACE.get(key)
+    if ws is None:
+        ws = _WORKSPACE[key] = torch.empty(WORKSPACE_BYTES // 4, dtype=torch.float32, device=device)
+    return ws
+
+
 def require_cuda_f32(t, name):
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor, got %s" % (name, type(t)))
@@ -126,6 +139,8 @@ def conv2d(sources, pc, residual=None, residual_mode=N.RES_NONE, aux=None):
         d.aux_mult, d.aux_base = aux
     d.B, d.Hin, d.Win, d.Cout = B, Hin, Win, pc.cout
     d.ksize, d.stride, d.act = pc.ksize, pc.stride, pc.act
+    ws = workspace(first.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), WORKSPACE_BYTES
     N.check(N.lib().dvmvs_conv2d(ctypes.byref(d), _stream()), "conv2d")
     return (out, aux_out) if aux is not None else out
 
@@ -205,3 +220,211 @@ def upsample2x(x_nhwc):
     y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=x_nhwc.device)
     N.check(N.lib().dvmvs_upsample2x(x_nhwc.data_ptr(), y.data_ptr(), B, H, W, C, _stream()), "upsample2x")
     return y
+
+
+# ================================================================================================ tensor-core path
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def split_planes(x_nhwc, upsample=False):
+    """fp32 (B,H,W,C) -> fp16 (hi, lo) planes (2,B,H',W',Cs), Cs = C rounded up to 8 (zero channels)."""
+    B, H, W, C = x_nhwc.shape
+    Cs = round_up(C, 8)
+    f = 2 if upsample else 1
+    planes = torch.empty((2, B, H * f, W * f, Cs), dtype=torch.float16, device=x_nhwc.device)
+    N.check(N.lib().dvmvs_split_planes(x_nhwc.data_ptr(), planes.data_ptr(), B, H, W, C, Cs, 1 if upsample else 0, _stream()),
+            "split_planes")
+    return planes
+
+
+def tc_chunking(cs):
+    kchunk = 64 if cs % 64 == 0 else 32
+    return kchunk, (cs + kchunk - 1) // kchunk
+
+
+class PackedConvTC:
+    """Weights for dvmvs_conv2d_tc: fp16 (hi, lo) matrices [rows][K] with the K axis ordered tap-major, then source,
+    then 32/64-channel chunks (each chunk zero-padded to full width), BN folded in fp64 beforehand."""
+
+    def __init__(self, pc, src_channels, device):
+        """pc: PackedConv (fp32, [k][k][Cin][Cout]); src_channels: real channel count of every concatenated source."""
+        k, cin, cout = pc.ksize, pc.cin, pc.cout
+        assert sum(src_channels) == cin, (src_channels, cin)
+        w = pc.weight.detach().to("cpu", torch.float32).reshape(k * k, cin, cout)       # [tap][cin][cout]
+        cols = []
+        off = 0
+        self.src_stored = []
+        for cr in src_channels:
+            cs = round_up(cr, 8)
+            kchunk, nch = tc_chunking(cs)
+            blk = torch.zeros(k * k, nch * kchunk, cout, dtype=torch.float32)
+            blk[:, :cr, :] = w[:, off:off + cr, :]
+            cols.append(blk)
+            off += cr
+            self.src_stored.append(cs)
+        wk = torch.cat(cols, dim=1)                                 # [tap][k_per_tap][cout]
+        self.k_per_tap = wk.shape[1]
+        self.ktot = k * k * self.k_per_tap
+        rows = round_up(cout, 128)
+        w2d = torch.zeros(rows, self.ktot, dtype=torch.float32)
+        w2d[:cout] = wk.reshape(self.ktot, cout).t()
+        hi = w2d.to(torch.float16)
+        lo = (w2d - hi.to(torch.float32)).to(torch.float16)
+        self.w_hi = hi.contiguous().to(device)
+        self.w_lo = lo.contiguous().to(device)
+        self.rows = rows
+        self.ksize, self.cin, self.cout, self.stride, self.act = k, cin, cout, pc.stride, pc.act
+        self.bias = pc.bias.to(device) if pc.bias is not None else None
+        self.src_channels = list(src_channels)
+
+
+def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, want_f32=True, want_planes=True, terms=3,
+              block_n=None, allow_split=True):
+    """sources: list of fp16-pair plane tensors (2,B,Hin,Win,Cs_i) matching ptc.src_stored.  Returns
+    (out_f32 or None, out_planes or None[, aux_out])."""
+    d = N.ConvTcDesc()
+    first = sources[0]
+    B, Hin, Win = first.shape[1], first.shape[2], first.shape[3]
+    if len(sources) != len(ptc.src_stored):
+        raise ValueError("conv2d_tc: %d sources given, weights packed for %d" % (len(sources), len(ptc.src_stored)))
+    for i, t in enumerate(sources):
+        if t.dtype != torch.float16 or tuple(t.shape[:4]) != (2, B, Hin, Win) or t.shape[4] != ptc.src_stored[i]:
+            raise ValueError("conv2d_tc: source %d has shape %s / %s, expected (2,%d,%d,%d,%d) fp16"
+                             % (i, tuple(t.shape), t.dtype, B, Hin, Win, ptc.src_stored[i]))
+        d.src_planes[i] = t.data_ptr()
+        d.src_channels[i] = t.shape[4]
+    d.n_src = len(sources)
+    pad = (ptc.ksize - 1) // 2
+    Hout = (Hin + 2 * pad - ptc.ksize) // ptc.stride + 1
+    Wout = (Win + 2 * pad - ptc.ksize) // ptc.stride + 1
+    if block_n is None:
+        tiles = B * ((Hout + 7) // 8) * ((Wout + 15) // 16)
+        if ptc.cout <= 32 or tiles < 16:
+            block_n = 32
+        elif ptc.cout <= 64 or tiles < 64:
+            block_n = 64
+        else:
+            block_n = 128
+    if want_planes and ptc.cout % 8 != 0:
+        raise ValueError("conv2d_tc: fp16-pair output needs Cout % 8 == 0")
+    dev = first.device
+    out_f32 = torch.empty((B, Hout, Wout, ptc.cout), dtype=torch.float32, device=dev) if want_f32 else None
+    out_planes = torch.empty((2, B, Hout, Wout, ptc.cout), dtype=torch.float16, device=dev) if want_planes else None
+    d.w_hi, d.w_lo = ptc.w_hi.data_ptr(), ptc.w_lo.data_ptr()
+    d.w_rows, d.ktot, d.block_n, d.terms, d.allow_split = ptc.rows, ptc.ktot, block_n, terms, 1 if allow_split else 0
+    d.bias = ptc.bias.data_ptr() if ptc.bias is not None else None
+    d.residual_mode = residual_mode
+    if residual is not None:
+        d.residual = residual.data_ptr()
+        d.Hr, d.Wr = residual.shape[1], residual.shape[2]
+    d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+    d.out_planes = out_planes.data_ptr() if out_planes is not None else None
+    aux_out = None
+    if aux is not None:
+        aux_out = torch.empty((B, Hout, Wout, ptc.cout), dtype=torch.float32, device=dev)
+        d.aux_out = aux_out.data_ptr()
+        d.aux_mult, d.aux_base = aux
+    d.B, d.Hin, d.Win, d.Cout = B, Hin, Win, ptc.cout
+    d.ksize, d.stride, d.act = ptc.ksize, ptc.stride, ptc.act
+    if allow_split:
+        ws = workspace(dev)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), WORKSPACE_BYTES
+    N.check(N.lib().dvmvs_conv2d_tc(ctypes.byref(d), _stream()), "conv2d_tc")
+    if aux is not None:
+        return out_f32, out_planes, aux_out
+    return out_f32, out_planes
+
+
+# ================================================================================================ backend dispatch
+import os as _os
+
+_BACKEND = _os.environ.get("DVMVS_CONV_BACKEND", "fp32")     # "fp32": CUDA-core kernels; "tc": tcgen05 where eligible
+_TC_TERMS = int(_os.environ.get("DVMVS_TC_TERMS", "3"))
+_TC_STRIDE2 = _os.environ.get("DVMVS_TC_STRIDE2", "0") == "1"
+
+
+def set_conv_backend(name, terms=None, stride2=None):
+    """'fp32' = exact-fp32 CUDA-core convolutions everywhere; 'tc' = tcgen05 implicit GEMM (fp16-pair operands, fp32
+    accumulate) for every dense convolution it supports, CUDA-core kernels for the rest."""
+    global _BACKEND, _TC_TERMS, _TC_STRIDE2
+    if name not in ("fp32", "tc"):
+        raise ValueError("backend must be 'fp32' or 'tc'")
+    _BACKEND = name
+    if terms is not None:
+        _TC_TERMS = int(terms)
+    if stride2 is not None:
+        _TC_STRIDE2 = bool(stride2)
+
+
+def conv_backend():
+    return _BACKEND
+
+
+class Act:
+    """An activation inside a module: fp32 channel-last tensor and/or its fp16 (hi, lo) planes (created on demand,
+    cached).  `up` planes = planes of the x2-bilinear-upsampled tensor (F.interpolate materialised for the TMA loader)."""
+    __slots__ = ("f32", "planes", "planes_up", "version")
+
+    def __init__(self, f32=None, planes=None):
+        self.f32, self.planes, self.planes_up, self.version = f32, planes, None, None
+
+    @property
+    def channels(self):
+        return self.f32.shape[3]
+
+    def get_planes(self, upsample=False):
+        if upsample:
+            if self.planes_up is None:
+                self.planes_up = split_planes(self.f32, upsample=True)
+            return self.planes_up
+        if self.planes is None:
+            self.planes = split_planes(self.f32)
+        return self.planes
+
+
+def to_act(x, name="input"):
+    """API tensor (B,C,H,W) -> Act; re-uses the producer's Act (and its fp16 planes) when the tensor is the untouched
+    output of one of our modules."""
+    a = getattr(x, "_dvmvs_act", None)
+    if a is not None and a.f32.data_ptr() == x.data_ptr() and a.version == x._version and tuple(a.f32.shape) == (
+            x.shape[0], x.shape[2], x.shape[3], x.shape[1]):
+        return a
+    return Act(to_nhwc(x, name))
+
+
+def act_to_api(a):
+    t = to_api(a.f32)
+    a.version = t._version
+    t._dvmvs_act = a
+    return t
+
+
+class ConvLayer:
+    """One dense convolution of the network: BN-folded weights for both backends + the channel split of its sources."""
+
+    def __init__(self, pc, src_channels=None):
+        self.pc = pc
+        self.src_channels = list(src_channels) if src_channels is not None else [pc.cin]
+        self._ptc = None
+
+    def tc_eligible(self):
+        pc = self.pc
+        return pc.cout % 8 == 0 and pc.cout >= 16 and (pc.stride == 1 or _TC_STRIDE2) and pc.cin >= 16
+
+    def run(self, sources, residual=None, residual_mode=N.RES_NONE, aux=None):
+        """sources: list of (Act, mode).  Returns Act (or (Act, aux tensor))."""
+        pc = self.pc
+        if _BACKEND == "tc" and self.tc_eligible():
+            if self._ptc is None:
+                self._ptc = PackedConvTC(pc, self.src_channels, pc.weight.device)
+            planes = [a.get_planes(upsample=(mode == N.SRC_UPSAMPLE2X)) for a, mode in sources]
+            res = residual.f32 if residual is not None else None
+            r = conv2d_tc(planes, self._ptc, residual=res, residual_mode=residual_mode, aux=aux, terms=_TC_TERMS)
+            out = Act(r[0], r[1])
+            return (out, r[2]) if aux is not None else out
+        r = conv2d([(a.f32, mode) for a, mode in sources], pc, residual=residual.f32 if residual is not None else None,
+                   residual_mode=residual_mode, aux=aux)
+        if aux is not None:
+            return Act(r[0]), r[1]
+        return Act(r)

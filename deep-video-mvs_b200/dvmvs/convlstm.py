@@ -26,20 +26,20 @@ class MVSLayernormConvLSTMCell(NativeModule):
                               padding=self.padding, bias=False)
 
     def _pack(self):
-        return ops.PackedConv(self.conv.weight, None, None, stride=1, act=N.ACT_NONE)
+        return ops.ConvLayer(ops.PackedConv(self.conv.weight, None, None, stride=1, act=N.ACT_NONE), [self.input_dim, self.hidden_dim])
 
     def forward(self, input_tensor, cur_state, previous_pose, current_pose, estimated_current_depth, camera_matrix):
         pc = self.packed()
         h_cur, c_cur = cur_state
-        x = ops.to_nhwc(input_tensor, "input_tensor")
-        h = ops.to_nhwc(h_cur, "h_cur")
+        x = ops.to_act(input_tensor, "input_tensor")
+        h = ops.to_act(h_cur, "h_cur")
         c = ops.to_nhwc(c_cur, "c_cur")
         if previous_pose is not None:
             # convlstm.py:30-41: transformation = inverse(previous_pose) @ current_pose, warp, mask depth <= 0.01
-            h = ops.hidden_warp(h, estimated_current_depth, previous_pose, current_pose, camera_matrix, 0.01)
-        gates = ops.conv2d([(x, N.SRC_DIRECT), (h, N.SRC_DIRECT)], pc)
-        h_next, c_next = ops.lstm_gates(gates, c)
-        return ops.to_api(h_next), ops.to_api(c_next)
+            h = ops.Act(ops.hidden_warp(h.f32, estimated_current_depth, previous_pose, current_pose, camera_matrix, 0.01))
+        gates = pc.run([(x, N.SRC_DIRECT), (h, N.SRC_DIRECT)])
+        h_next, c_next = ops.lstm_gates(gates.f32, c)
+        return ops.act_to_api(ops.Act(h_next)), ops.to_api(c_next)
 
     def init_hidden(self, batch_size, image_size):
         height, width = image_size

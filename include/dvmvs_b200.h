@@ -100,9 +100,48 @@ typedef struct {
   float* aux_out;        /* optional [B][Hout][Wout][Cout]: 1/(aux_mult*act(y) + aux_base) (depth heads) */
   float aux_mult, aux_base;
   int B, Hin, Win, Cout, ksize, stride, act;
+  float* workspace;      /* optional scratch for deterministic split-K on small maps (partial sums, reduced in a */
+  long long workspace_bytes; /* fixed order by a finishing kernel); NULL / too small => no split */
 } dvmvs_conv_desc;
 
 int dvmvs_conv2d(const dvmvs_conv_desc* desc_host, dvmvs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * The same convolution on the 5th-generation tensor cores: implicit GEMM, tcgen05.mma with TMEM accumulators,
+ * operand tiles fed by TMA (one 4-D box per filter tap and channel chunk; zero padding = TMA out-of-bounds fill).
+ * Activations and weights are fp16 (hi, lo) pairs, x = hi + lo; terms = 3 issues hi*hi + lo*hi + hi*lo with fp32
+ * accumulation (fp32-equivalent results), terms = 1 plain fp16.
+ *   src_planes[i]  fp16 [2][B][Hin][Win][C_i]: plane 0 = hi, plane 1 = lo (plane 1 unused when terms == 1);
+ *                  C_i a multiple of 8 (dvmvs_split_planes pads with zero channels)
+ *   w_hi / w_lo    fp16 [w_rows][ktot], row n = output channel n (rows >= Cout are zero), BN folded; the K axis is
+ *                  ordered tap-major, then source, then 32- or 64-channel chunks (64 when C_i % 64 == 0, else 32),
+ *                  each chunk zero-padded to its full width -- see dvmvs/_ops.py pack_tc_weights
+ *   out_f32 / out_planes   either or both; same epilogue options as dvmvs_conv2d. */
+typedef struct {
+  const void* src_planes[3];
+  int src_channels[3];
+  int n_src;
+  const void* w_hi;
+  const void* w_lo;
+  int w_rows, ktot, block_n, terms, allow_split;
+  const float* bias;
+  const float* residual;
+  int residual_mode, Hr, Wr;
+  float* out_f32;
+  void* out_planes;
+  float* aux_out;
+  float aux_mult, aux_base;
+  int B, Hin, Win, Cout, ksize, stride, act;
+  float* workspace;      /* as in dvmvs_conv_desc (split over filter taps) */
+  long long workspace_bytes;
+} dvmvs_conv_tc_desc;
+
+int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* desc_host, dvmvs_stream_t stream);
+
+/* fp32 channel-last [B][H][W][C] -> fp16 (hi, lo) planes [2][B][H'][W'][Cs] (Cs >= C, multiple of 8, zero padded);
+ * upsample2x != 0 applies the x2 bilinear (align_corners) interpolation on the way (H' = 2H). */
+int dvmvs_split_planes(const float* x, void* planes, int B, int H, int W, int C, int Cs, int upsample2x,
+                       dvmvs_stream_t stream);
 
 /* Depthwise k x k convolution (MnasNet), folded-BN bias + optional ReLU.
  * x [B][H][W][C], weight [k][k][C], bias [C], y [B][Hout][Wout][C]. */
