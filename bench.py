@@ -105,6 +105,8 @@ def run_ours(args, rank, world, local_rank):
     from dvmvs.fusionnet.model import CostVolumeDecoder, CostVolumeEncoder, FeatureExtractor, FeatureShrinker, LSTMFusion
     from dvmvs.utils import cost_volume_fusion
     from dvmvs import pipeline
+    from dvmvs import _ops as ops
+    ops.set_conv_backend(args.backend, terms=args.tc_terms, stride2=True)
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -133,25 +135,38 @@ def run_ours(args, rank, world, local_rank):
         frames_dev.append((torch.from_numpy(ref).to(dev), torch.from_numpy(rpose).to(dev), [torch.from_numpy(x).to(dev) for x in meas],
                            [torch.from_numpy(p).to(dev) for p in mpose], torch.from_numpy(K).to(dev)))
     state = pipeline.KeyframeState()
+    engine = pipeline.GraphedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, n_depth_levels=D) if args.mode == "graph" else None
+
+    def dev_step(t, state):
+        if engine is not None:
+            return engine.step(*frames_dev[t]), state
+        return pipeline.keyframe(mods, state, *frames_dev[t], n_depth_levels=D)
+
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     with torch.no_grad():
         for t in range(args.warmup):
-            _, state = pipeline.keyframe(mods, state, *frames_dev[t], n_depth_levels=D)
+            _, state = dev_step(t, state)
         torch.cuda.synchronize()
         barrier()
         sampler.start()
         launches0 = _native.launch_count()
+        if os.environ.get("DVMVS_PROFILE") == "1":
+            torch.cuda.profiler.start()
         wall0 = time.perf_counter()
         for i in range(args.steps):
             flush.zero_()
             ev[i][0].record()
-            pred, state = pipeline.keyframe(mods, state, *frames_dev[args.warmup + i], n_depth_levels=D)
+            pred, state = dev_step(args.warmup + i, state)
             ev[i][1].record()
         torch.cuda.synchronize()
         wall1 = time.perf_counter()
+        if os.environ.get("DVMVS_PROFILE") == "1":
+            torch.cuda.profiler.stop()
         barrier()
     launches = _native.launch_count() - launches0
+    if engine is not None:
+        launches = engine.kernels_per_replay[True] * args.steps
     log("device-resident arm done")
     clocks = sampler.summary()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -166,11 +181,17 @@ def run_ours(args, rank, world, local_rank):
     out_host = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
     d2h_bytes = out_host.numel() * 4
     state = pipeline.KeyframeState()
+    if engine is not None:
+        engine.reset()
 
     def e2e_step(t, state):
-        hs = [a.to(dev, non_blocking=True) for a in frames_host[t]]
-        ref, rpose, meas, mpose, K = hs[0], hs[1], hs[2:2 + M], hs[2 + M:2 + 2 * M], hs[2 + 2 * M]
-        pred, state = pipeline.keyframe(mods, state, ref, rpose, meas, mpose, K, n_depth_levels=D)
+        fh = frames_host[t]
+        if engine is not None:          # H2D copies into the graph's static buffers happen inside step()
+            pred = engine.step(fh[0], fh[1], fh[2:2 + M], fh[2 + M:2 + 2 * M], fh[2 + 2 * M])
+        else:
+            hs = [a.to(dev, non_blocking=True) for a in fh]
+            ref, rpose, meas, mpose, K = hs[0], hs[1], hs[2:2 + M], hs[2 + M:2 + 2 * M], hs[2 + 2 * M]
+            pred, state = pipeline.keyframe(mods, state, ref, rpose, meas, mpose, K, n_depth_levels=D)
         out_host.copy_(pred, non_blocking=True)
         return state
 
@@ -221,9 +242,10 @@ def run_ours(args, rank, world, local_rank):
     result = {
         "metric": "fusionnet depth frames/sec @256x256x64planes", "value": total_frames / (dev_ms * 1e-3), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.backend == "fp32" else "f16x2+f32acc", "data": "synthetic",
         "config": {"workload": WORKLOAD % B, "clips_per_gpu": B, "height": H, "width": W, "planes": D, "measurement_frames": M,
-                   "weights": "random-init (seeded) reference architecture", "l2": "flushed (256 MiB write) between timed steps",
+                   "weights": "random-init (seeded) reference architecture", "mode": args.mode,
+                   "conv_backend": args.backend + ("" if args.backend == "fp32" else " (tcgen05, fp16-pair operands x%d terms, fp32 accumulate)" % args.tc_terms), "l2": "flushed (256 MiB write) between timed steps",
                    "parallelism": "clip-sharded x%d, no data-path collective" % world, "host_loop_wall_ms_per_step": (wall1 - wall0) * 1e3 / args.steps},
         "clocks": clocks,
         "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
@@ -295,6 +317,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--clips", type=int, default=1, help="independent clips per GPU (batched through the modules)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("DVMVS_BENCH_MODE", "graph"), choices=["graph", "eager"],
+                    help="graph: keyframe captured in CUDA graphs (default); eager: one host launch per kernel")
+    ap.add_argument("--backend", default=os.environ.get("DVMVS_CONV_BACKEND", "tc"), choices=["tc", "fp32"])
+    ap.add_argument("--tc-terms", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=6, help="frames of the bounded CPU-baseline sample")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

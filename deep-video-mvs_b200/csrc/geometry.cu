@@ -69,18 +69,68 @@ __host__ __device__ __forceinline__ void sweep_sample_pos(const float* base, con
   ys = ((gy + 1.f) * 0.5f) * hm1;
 }
 
-// ---- fast path: C == 32, channel-last.  A quarter warp (8 lanes x float4) owns one (pixel, plane) sample so
-// that every bilinear tap is ONE 128-byte line; a warp therefore issues 4 lines per load instruction.  The
-// CTA owns kPix consecutive reference pixels of one image row; their 128-byte feature vectors are one
-// contiguous span that is staged in shared memory by a single TMA bulk copy (cp.async.bulk -> UBLKCP).
+// ---- fast path: C == 32, channel-last.  A quarter warp (8 lanes x float4) owns one reference pixel and walks its D
+// planes; every bilinear tap is ONE 128-byte line, so a warp load instruction touches 4 lines (one per pixel).
+// The CTA owns kPix consecutive reference pixels of one image row; their 128-byte feature vectors are one
+// contiguous span staged in shared memory by a single TMA bulk copy (cp.async.bulk -> UBLKCP).  Per-plane Kt/depth
+// and the per-frame homographies live in shared memory; the per-sample coordinate math is 3 adds, one reciprocal
+// and 4 multiplies (x*(w-1)/w folded into one scale: <= 3 ulp from the reference's op sequence, i.e. ~1e-5 px).
 constexpr int kPix = 32;
 constexpr int kSweepThreads = 256;
 
-__global__ void __launch_bounds__(kSweepThreads) plane_sweep_c32_kernel(SweepParams p) {
+struct SweepTap {
+  float4 t00, t01, t10, t11;
+  float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ void sweep_fetch(const float* __restrict__ img, const float* G, const float* kd, float uf, float vf,
+                                            float sx, float sy, int w, int h, bool active, SweepTap& t) {
+  const float q0 = fmaf(G[0], uf, fmaf(G[1], vf, G[2])) + kd[0];
+  const float q1 = fmaf(G[3], uf, fmaf(G[4], vf, G[5])) + kd[1];
+  const float q2 = fmaf(G[6], uf, fmaf(G[7], vf, G[8])) + kd[2];
+  const float r = __frcp_rn(q2 + 1e-8f);
+  const float xs = q0 * r * sx, ys = q1 * r * sy;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  t.t00 = z; t.t01 = z; t.t10 = z; t.t11 = z;
+  t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
+  // some tap inside the image  <=>  -1 < xs < w  and  -1 < ys < h   (false for NaN / Inf)
+  if (active && xs > -1.f && xs < (float)w && ys > -1.f && ys < (float)h) {
+    const float x0f = floorf(xs), y0f = floorf(ys);
+    const float fx = xs - x0f, fy = ys - y0f;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const bool vx0 = x0 >= 0, vx1 = x0 + 1 < w, vy0 = y0 >= 0, vy1 = y0 + 1 < h;
+    const float* p00 = img + ((long long)y0 * w + x0) * 32;
+    if (vy0 && vx0) t.t00 = __ldg(reinterpret_cast<const float4*>(p00));
+    if (vy0 && vx1) t.t01 = __ldg(reinterpret_cast<const float4*>(p00 + 32));
+    if (vy1 && vx0) t.t10 = __ldg(reinterpret_cast<const float4*>(p00 + (long long)w * 32));
+    if (vy1 && vx1) t.t11 = __ldg(reinterpret_cast<const float4*>(p00 + (long long)w * 32 + 32));
+    const float gx = (x0f + 1.f) - xs, gy = (y0f + 1.f) - ys;     // the reference's (x0+1-x) weights
+    t.w00 = gx * gy; t.w01 = fx * gy; t.w10 = gx * fy; t.w11 = fx * fy;
+  }
+}
+
+__device__ __forceinline__ float sweep_reduce(const SweepTap& t, const float4& f1, int mode) {
+  float4 ws;
+  ws.x = fmaf(t.t11.x, t.w11, fmaf(t.t10.x, t.w10, fmaf(t.t01.x, t.w01, t.t00.x * t.w00)));
+  ws.y = fmaf(t.t11.y, t.w11, fmaf(t.t10.y, t.w10, fmaf(t.t01.y, t.w01, t.t00.y * t.w00)));
+  ws.z = fmaf(t.t11.z, t.w11, fmaf(t.t10.z, t.w10, fmaf(t.t01.z, t.w01, t.t00.z * t.w00)));
+  ws.w = fmaf(t.t11.w, t.w11, fmaf(t.t10.w, t.w10, fmaf(t.t01.w, t.w01, t.t00.w * t.w00)));
+  float part;
+  if (mode == DVMVS_SWEEP_DOT)
+    part = fmaf(f1.w, ws.w, fmaf(f1.z, ws.z, fmaf(f1.y, ws.y, f1.x * ws.x)));
+  else
+    part = fabsf(f1.x - ws.x) + fabsf(f1.y - ws.y) + fabsf(f1.z - ws.z) + fabsf(f1.w - ws.w);
+  part += __shfl_xor_sync(0xffffffffu, part, 1);
+  part += __shfl_xor_sync(0xffffffffu, part, 2);
+  part += __shfl_xor_sync(0xffffffffu, part, 4);
+  return part;
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 3) plane_sweep_c32_kernel(SweepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_ref = reinterpret_cast<float*>(smem_raw);                     // [kPix][32]
-  float* s_kd = s_ref + kPix * 32;                                       // [M][D][3]  Kt / depth_i
-  float* s_G = s_kd + p.M * p.D * 3;                                     // [M][12]
+  float* s_kd = s_ref + kPix * 32;                                       // [M][D][4]  Kt / depth_i (padded to 4)
+  float* s_G = s_kd + p.M * p.D * 4;                                     // [M][12]
   float* s_out = s_G + kMaxMeas * 12;                                    // [kPix][D]
   __shared__ __align__(8) unsigned long long s_bar;
 
@@ -123,7 +173,7 @@ __global__ void __launch_bounds__(kSweepThreads) plane_sweep_c32_kernel(SweepPar
     const int m = i / p.D, d = i - m * p.D;
     const float this_depth = (float)(1.0 / (p.inv_base + d * p.inv_step));   // utils.py:66 (double, then fp32 divide)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) s_kd[i * 3 + k] = s_G[m * 12 + 9 + k] / this_depth;   // utils.py:68
+    for (int k = 0; k < 3; ++k) s_kd[i * 4 + k] = s_G[m * 12 + 9 + k] / this_depth;   // utils.py:68
   }
   __syncthreads();
   {  // wait for the TMA bytes
@@ -139,64 +189,39 @@ __global__ void __launch_bounds__(kSweepThreads) plane_sweep_c32_kernel(SweepPar
 
   const int lane = tid & 31, warp = tid >> 5;
   const int sub = lane & 7;        // channel group: channels sub*4 .. sub*4+3
-  const int quad = lane >> 3;      // which of the warp's 4 concurrent samples
-  const float wn = p.w * 0.5f, hn = p.h * 0.5f, wm1 = (float)(p.w - 1), hm1 = (float)(p.h - 1);
+  const int pix = warp * 4 + (lane >> 3);
+  const bool active = pix < npix;
+  const float sx = (float)(p.w - 1) / (float)p.w, sy = (float)(p.h - 1) / (float)p.h;   // the align_corners "shrink" (App. A.1)
   const float inv_C = 1.f / 32.f;
-  const size_t img_stride = (size_t)p.h * p.w * 32;
+  const float uf = (float)(u0 + pix), vf = (float)v;
+  const float4 f1 = *reinterpret_cast<const float4*>(s_ref + (active ? pix : 0) * 32 + sub * 4);
+  const size_t img_off = (size_t)b * p.h * p.w * 32 + sub * 4;
+  const float inv_M = 1.f;
+  (void)inv_M;
 
-  // work items: (pixel, plane); warp handles 4 per step.  Order: plane fastest within a pixel so that the 4
-  // samples of a warp step walk along one epipolar line (neighbouring taps -> L1 hits).
-  const int n_items = npix * p.D;
-  for (int item = warp * 4 + quad; item < ((n_items + 3) / 4) * 4; item += (kSweepThreads / 32) * 4) {
-    const bool active = item < n_items;
-    const int pix = active ? item / p.D : 0;
-    const int d = active ? item - pix * p.D : 0;
-    const float4 f1 = *reinterpret_cast<const float4*>(s_ref + pix * 32 + sub * 4);
-    const float uf = (float)(u0 + pix), vf = (float)v;
-    float acc = 0.f;
+  // walk the planes two at a time (both samples' taps in flight before either is reduced)
+  for (int d = 0; d < p.D; d += 2) {
+    const bool has2 = d + 1 < p.D;
+    float acc0 = 0.f, acc1 = 0.f;
     for (int m = 0; m < p.M; ++m) {
+      const float* img = p.meas[m] + img_off;
       const float* G = s_G + m * 12;
-      float base[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) base[k] = fmaf(G[k * 3 + 0], uf, fmaf(G[k * 3 + 1], vf, G[k * 3 + 2]));
-      float xs, ys;
-      sweep_sample_pos(base, s_kd + (m * p.D + d) * 3, wn, hn, wm1, hm1, xs, ys);
-      const float x0f = floorf(xs), y0f = floorf(ys);
-      const float wx1 = xs - x0f, wx0 = (x0f + 1.f) - xs;
-      const float wy1 = ys - y0f, wy0 = (y0f + 1.f) - ys;
-      const bool vx0 = (x0f >= 0.f) && (x0f <= wm1), vx1 = (x0f + 1.f >= 0.f) && (x0f + 1.f <= wm1);
-      const bool vy0 = (y0f >= 0.f) && (y0f <= hm1), vy1 = (y0f + 1.f >= 0.f) && (y0f + 1.f <= hm1);
-      float4 wsum = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (active && (vx0 || vx1) && (vy0 || vy1)) {
-        const int x0 = (int)x0f, y0 = (int)y0f;
-        const float* img = p.meas[m] + (size_t)b * img_stride + sub * 4;
-        // issue all taps first (independent loads), then blend
-        float4 t00 = make_float4(0.f, 0.f, 0.f, 0.f), t01 = t00, t10 = t00, t11 = t00;
-        if (vy0 && vx0) t00 = __ldg(reinterpret_cast<const float4*>(img + ((size_t)y0 * p.w + x0) * 32));
-        if (vy0 && vx1) t01 = __ldg(reinterpret_cast<const float4*>(img + ((size_t)y0 * p.w + x0 + 1) * 32));
-        if (vy1 && vx0) t10 = __ldg(reinterpret_cast<const float4*>(img + ((size_t)(y0 + 1) * p.w + x0) * 32));
-        if (vy1 && vx1) t11 = __ldg(reinterpret_cast<const float4*>(img + ((size_t)(y0 + 1) * p.w + x0 + 1) * 32));
-        const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
-        wsum.x = fmaf(t11.x, w11, fmaf(t10.x, w10, fmaf(t01.x, w01, t00.x * w00)));
-        wsum.y = fmaf(t11.y, w11, fmaf(t10.y, w10, fmaf(t01.y, w01, t00.y * w00)));
-        wsum.z = fmaf(t11.z, w11, fmaf(t10.z, w10, fmaf(t01.z, w01, t00.z * w00)));
-        wsum.w = fmaf(t11.w, w11, fmaf(t10.w, w10, fmaf(t01.w, w01, t00.w * w00)));
-      }
-      float part;
-      if (p.mode == DVMVS_SWEEP_DOT)
-        part = fmaf(f1.w, wsum.w, fmaf(f1.z, wsum.z, fmaf(f1.y, wsum.y, f1.x * wsum.x)));
-      else
-        part = fabsf(f1.x - wsum.x) + fabsf(f1.y - wsum.y) + fabsf(f1.z - wsum.z) + fabsf(f1.w - wsum.w);
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      part += __shfl_xor_sync(0xffffffffu, part, 4);
-      acc += (p.mode == DVMVS_SWEEP_DOT) ? part * inv_C : part;          // utils.py:82 / :84
+      SweepTap ta, tb;
+      sweep_fetch(img, G, s_kd + (m * p.D + d) * 4, uf, vf, sx, sy, p.w, p.h, active, ta);
+      sweep_fetch(img, G, s_kd + (m * p.D + (has2 ? d + 1 : d)) * 4, uf, vf, sx, sy, p.w, p.h, active && has2, tb);
+      const float pa = sweep_reduce(ta, f1, p.mode), pb = sweep_reduce(tb, f1, p.mode);
+      acc0 += (p.mode == DVMVS_SWEEP_DOT) ? pa * inv_C : pa;              // utils.py:82 / :84
+      acc1 += (p.mode == DVMVS_SWEEP_DOT) ? pb * inv_C : pb;
     }
-    if (active && sub == 0) s_out[pix * p.D + d] = acc / (float)p.M;     // utils.py:105-106
+    if (active && sub == 0) {
+      s_out[pix * p.D + d] = acc0 / (float)p.M;                           // utils.py:105-106
+      if (has2) s_out[pix * p.D + d + 1] = acc1 / (float)p.M;
+    }
   }
   __syncthreads();
   // coalesced write-out: [npix][D] is contiguous in the channel-last cost volume
   float* o = p.out + (((size_t)b * p.h + v) * p.w + u0) * p.D;
+  const int n_items = npix * p.D;
   for (int i = tid; i < n_items; i += kSweepThreads) o[i] = s_out[i];
 }
 
@@ -403,7 +428,7 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
   for (int m = 0; m < M && fast; ++m) fast = ((uintptr_t)meas_host[m] % 16 == 0);
   if (fast) {
     const int tiles = B * h * ((w + kPix - 1) / kPix);
-    const size_t smem = (size_t)(kPix * 32 + M * D * 3 + kMaxMeas * 12 + kPix * D) * sizeof(float);
+    const size_t smem = (size_t)(kPix * 32 + M * D * 4 + kMaxMeas * 12 + kPix * D) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(plane_sweep_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

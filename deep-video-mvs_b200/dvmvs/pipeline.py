@@ -42,19 +42,29 @@ def build_modules(weights, device="cuda", n_depth_levels=64, pairnet=False):
 
 
 def keyframe(mods, state, reference_image, reference_pose, measurement_images, measurement_poses, full_K,
-             min_depth=0.25, max_depth=20.0, n_depth_levels=64):
+             min_depth=0.25, max_depth=20.0, n_depth_levels=64, batch_features=True):
     """One keyframe for B independent clips (tensors batched on dim 0, all CUDA).  With 'lstm' in mods this is the
-    fusionnet loop body, without it the pairnet one.  Returns (depth (B,H,W), state)."""
+    fusionnet loop body, without it the pairnet one.  Returns (depth (B,H,W), state).
+
+    batch_features=True runs FeatureExtractor + FeatureShrinker ONCE over the reference and the M measurement images
+    stacked on the batch axis (eval-mode BatchNorm: identical results, 1/(M+1) of the launches); False reproduces the
+    script's M+1 separate passes (run-testing.py:153-159)."""
     B, _, H, W = reference_image.shape
     device = reference_image.device
     half_K = full_K.clone()
     half_K[:, 0:2, :] = half_K[:, 0:2, :] / 2.0
     warp_grid = None    # ignored by the fused kernel (kept in the signature for API compatibility)
-    meas_half = []
-    for im in measurement_images:
-        half, _, _, _ = mods["fpn"](*mods["fe"](im))
-        meas_half.append(half)
-    f2, f4, f8, f16 = mods["fpn"](*mods["fe"](reference_image))
+    if batch_features and len(measurement_images) > 0:
+        stacked = torch.cat([reference_image] + list(measurement_images), dim=0)
+        a2, a4, a8, a16 = mods["fpn"](*mods["fe"](stacked))
+        f2, f4, f8, f16 = a2[:B], a4[:B], a8[:B], a16[:B]
+        meas_half = [a2[(m + 1) * B:(m + 2) * B] for m in range(len(measurement_images))]
+    else:
+        meas_half = []
+        for im in measurement_images:
+            half, _, _, _ = mods["fpn"](*mods["fe"](im))
+            meas_half.append(half)
+        f2, f4, f8, f16 = mods["fpn"](*mods["fe"](reference_image))
     cv = cost_volume_fusion(image1=f2, image2s=meas_half, pose1=reference_pose, pose2s=measurement_poses, K=half_K,
                             warp_grid=warp_grid, min_depth=min_depth, max_depth=max_depth, n_depth_levels=n_depth_levels,
                             device=device, dot_product=True)
@@ -80,3 +90,99 @@ def keyframe(mods, state, reference_image, reference_pose, measurement_images, m
     state.previous_depth = pred.view(B, 1, H, W)
     state.previous_pose = reference_pose
     return pred, state
+
+
+class GraphedFusionnet:
+    """The keyframe loop body captured once into CUDA graphs (static shapes) and replayed: removes the ~300 host-side
+    launches per keyframe.  Built from the same drop-in modules; two graphs are captured lazily -- keyframe without
+    recurrent state (first frame / after reset) and steady state (hidden-state warp + depth re-projection on).
+
+        eng = GraphedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M)
+        depth = eng.step(ref_img, ref_pose, [meas_imgs], [meas_poses], full_K)      # CPU (pinned) or CUDA tensors
+
+    step() copies the inputs into static device buffers on the current stream (H2D when they are host tensors),
+    replays the graph and returns the static (B,H,W) depth buffer (valid until the next step)."""
+
+    def __init__(self, mods, batch, height, width, n_measurement_frames, min_depth=0.25, max_depth=20.0, n_depth_levels=64,
+                 device=None):
+        self.mods, self.B, self.H, self.W, self.M = mods, batch, height, width, n_measurement_frames
+        self.min_depth, self.max_depth, self.D = min_depth, max_depth, n_depth_levels
+        dev = device or next(mods["fe"].parameters()).device
+        self.device = dev
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.ref_image, self.ref_pose, self.full_K = z(batch, 3, height, width), z(batch, 4, 4), z(batch, 3, 3)
+        self.meas_images = [z(batch, 3, height, width) for _ in range(n_measurement_frames)]
+        self.meas_poses = [z(batch, 4, 4) for _ in range(n_measurement_frames)]
+        self.state = KeyframeState()
+        self._graphs = {}
+        self.kernels_per_replay = {}
+        self._static_state = None     # (h, c, prev_depth, prev_pose) buffers the steady-state graph reads and rewrites
+        self._out = None
+        self._has_state = False
+
+    def reset(self):
+        self._has_state = False
+
+    def _load_inputs(self, reference_image, reference_pose, measurement_images, measurement_poses, full_K):
+        self.ref_image.copy_(reference_image, non_blocking=True)
+        self.ref_pose.copy_(reference_pose, non_blocking=True)
+        self.full_K.copy_(full_K, non_blocking=True)
+        for dst, src in zip(self.meas_images, measurement_images):
+            dst.copy_(src, non_blocking=True)
+        for dst, src in zip(self.meas_poses, measurement_poses):
+            dst.copy_(src, non_blocking=True)
+
+    def _body(self, with_state):
+        st = KeyframeState()
+        if with_state:
+            h, c, pd, pp = self._static_state
+            st.lstm_state, st.previous_depth, st.previous_pose = (h, c), pd, pp
+        pred, st = keyframe(self.mods, st, self.ref_image, self.ref_pose, self.meas_images, self.meas_poses, self.full_K,
+                            self.min_depth, self.max_depth, self.D)
+        return pred, st
+
+    def _capture(self, with_state):
+        # warm-up on a side stream (allocations, weight packing, function attributes), then capture
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(2):
+                pred, st = self._body(with_state)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        if self._static_state is None:
+            self._static_state = (st.lstm_state[0].clone(), st.lstm_state[1].clone(), st.previous_depth.clone(), self.ref_pose.clone())
+            self._out = torch.empty_like(pred)
+        from . import _native
+        g = torch.cuda.CUDAGraph()
+        n0 = _native.launch_count()
+        with torch.no_grad(), torch.cuda.graph(g):
+            pred, st = self._body(with_state)
+            self.kernels_per_replay[with_state] = _native.launch_count() - n0   # our kernels captured in this graph
+            h, c, pd, pp = self._static_state
+            self._out.copy_(pred)
+            # new recurrent state -> static buffers (read by the next replay)
+            h.copy_(st.lstm_state[0])
+            c.copy_(st.lstm_state[1])
+            pd.copy_(st.previous_depth)
+            pp.copy_(self.ref_pose)
+        self._graphs[with_state] = g
+
+    def step(self, reference_image, reference_pose, measurement_images, measurement_poses, full_K):
+        if len(measurement_images) != self.M:
+            raise ValueError("GraphedFusionnet was built for %d measurement frames, got %d" % (self.M, len(measurement_images)))
+        with_state = self._has_state
+        if with_state not in self._graphs:
+            if with_state and self._static_state is None:
+                raise RuntimeError("steady-state graph requested before any keyframe ran")
+            saved = None
+            if self._static_state is not None:
+                saved = [t.clone() for t in self._static_state]
+            self._load_inputs(reference_image, reference_pose, measurement_images, measurement_poses, full_K)
+            self._capture(with_state)
+            if saved is not None:                      # capture warm-ups must not advance the recurrent state
+                for dst, src in zip(self._static_state, saved):
+                    dst.copy_(src)
+        self._load_inputs(reference_image, reference_pose, measurement_images, measurement_poses, full_K)
+        self._graphs[with_state].replay()
+        self._has_state = True
+        return self._out

@@ -320,3 +320,122 @@ def test_baseline_configs_vs_oracle(oracle, synth, cfg):
                                                         [p.to(DEV) for p in mp], K.to(DEV), n_depth_levels=D)
             e = oracle.rel_l1_inverse_depth(pred.cpu().numpy(), gold.numpy())
             assert e <= 1e-3, "%s frame ref=%d: %.3e" % (name, ref_i, e)
+
+
+def test_pipeline_keyframe_and_cuda_graph_engine_match_script_sequence(oracle, synth):
+    """dvmvs.pipeline.keyframe (features batched over the M+1 images) and the CUDA-graph engine reproduce the
+    reference script's call sequence bit-for-bit / to fp32 round-off over 4 recurrent keyframes."""
+    from dvmvs import pipeline
+    H, W, D, M = 64, 96, 64, 2
+    w = helpers.oracle_weights(oracle, synth, 11, n_depth_levels=D)
+    mods = helpers.build_product_modules(w, n_depth_levels=D)
+    clip = synth.make_clip(5, 4, H, W, M)
+    K = _cuda(clip["K"])[None]
+    st_a, st_b = helpers.ProductState(), pipeline.KeyframeState()
+    eng = pipeline.GraphedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
+    with torch.no_grad():
+        for ref_i, meas_i in clip["frames"]:
+            args = (_cuda(clip["images"][ref_i])[None], _cuda(clip["poses"][ref_i])[None], [_cuda(clip["images"][j])[None] for j in meas_i],
+                    [_cuda(clip["poses"][j])[None] for j in meas_i], K)
+            a, st_a = helpers.product_fusionnet_step(mods, st_a, *args, n_depth_levels=D)
+            b, st_b = pipeline.keyframe(mods, st_b, *args, n_depth_levels=D)
+            c = eng.step(*args)
+            assert oracle.rel_l1_inverse_depth(b.cpu().numpy(), a.cpu().numpy()) <= 1e-6
+            assert oracle.rel_l1_inverse_depth(c.cpu().numpy(), a.cpu().numpy()) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 backend
+TC_CASES = [
+    # name, B, H, W, [src real channels], Cout, k, stride, act, block_n, terms, tol
+    ("k1_c64", 1, 16, 16, [64], 32, 1, 1, 0, 32, 3, 2e-5),
+    ("k3_c32_n64", 1, 32, 32, [32], 64, 3, 1, 1, 64, 3, 2e-5),
+    ("k5_concat", 1, 64, 64, [32, 64], 32, 5, 1, 1, 32, 3, 5e-5),
+    ("k3_odd_batched", 2, 24, 40, [32, 128], 128, 3, 1, 1, 128, 3, 5e-5),
+    ("k3_lstm_like", 1, 8, 10, [512, 512], 96, 3, 1, 0, 32, 3, 1e-4),
+    ("k3_decoder_concat", 1, 16, 16, [128, 128, 1], 128, 3, 1, 1, 64, 3, 5e-5),
+    ("k5_refine_like", 1, 32, 32, [32, 1, 3], 32, 5, 1, 1, 32, 3, 5e-5),
+    ("k3_stride2", 1, 32, 32, [64], 128, 3, 2, 1, 64, 3, 2e-5),
+    ("k5_stride2", 1, 64, 64, [32], 64, 5, 2, 1, 64, 3, 2e-5),
+    ("k3_plain_fp16", 1, 32, 32, [64], 64, 3, 1, 1, 64, 1, 2e-3),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv2d_tc_vs_fp32_kernel_and_torch(synth, case):
+    """tcgen05 implicit GEMM (TMA-fed, TMEM accumulators, fp16-pair operands) vs torch fp32 on the CPU and vs the fp32
+    CUDA-core kernel; also the deterministic split-K variant and the fp16-pair output planes."""
+    import torch.nn.functional as F
+    from dvmvs import _native as N
+    from dvmvs import _ops as ops
+    name, B, H, W, chans, Cout, k, stride, act, block_n, terms, tol = case
+    cin = sum(chans)
+    xs = [T(synth.tensor("tc/%s/x%d" % (name, i), (B, c, H, W), seed=1)) for i, c in enumerate(chans)]
+    w = T(synth.tensor("tc/%s/w" % name, (Cout, cin, k, k), seed=2, scale=(2.0 / (cin * k * k)) ** 0.5))
+    bias = T(synth.tensor("tc/%s/b" % name, (Cout,), seed=3, scale=0.1))
+    ref = F.conv2d(torch.cat(xs, 1), w, bias, stride, (k - 1) // 2)
+    ref = F.relu(ref) if act == 1 else ref
+    pc = ops.PackedConv(w, bias, None, stride=stride, act=act)
+    ptc = ops.PackedConvTC(pc, chans, DEV)
+    pc.weight, pc.bias = pc.weight.to(DEV), pc.bias.to(DEV)
+    x_dev = [ops.to_nhwc(x.to(DEV)) for x in xs]
+    fp32 = ops.conv2d([(x, N.SRC_DIRECT) for x in x_dev], pc)
+    planes = [ops.split_planes(x) for x in x_dev]
+    out, out_planes = ops.conv2d_tc(planes, ptc, terms=terms, block_n=block_n, allow_split=False)
+    out_split, _ = ops.conv2d_tc(planes, ptc, terms=terms, block_n=block_n, allow_split=True)
+    again, _ = ops.conv2d_tc(planes, ptc, terms=terms, block_n=block_n, allow_split=True)
+    assert torch.equal(out_split, again)                                     # split-K reduction is deterministic
+    for got in (out, out_split, out_planes[0].float() + out_planes[1].float()):
+        assert rel_err(ops.to_api(got).cpu().numpy(), ref.numpy()) <= tol, name
+        assert rel_err(got.cpu().numpy(), fp32.cpu().numpy()) <= tol, name
+
+
+def test_fusionnet_c2_tensor_core_backend_vs_oracle(oracle, synth):
+    """BASELINE config 2 through the modules with the tcgen05 backend (stride-2 convs included): <= 1e-3 rel-L1 on
+    inverse depth vs the CPU oracle (the north-star tolerance); measured ~1e-6 with 3-term fp16 pairs."""
+    from dvmvs import _ops as ops
+    from dvmvs import pipeline
+    H, W, D, M = 256, 256, 64, 2
+    w = helpers.oracle_weights(oracle, synth, 7, n_depth_levels=D)
+    clip = synth.make_clip(0, 3, H, W, M)
+    K = T(clip["K"])[None]
+    old = ops.conv_backend()
+    ops.set_conv_backend("tc", terms=3, stride2=True)
+    try:
+        mods = helpers.build_product_modules(w, n_depth_levels=D)
+        st_o, st_p = oracle.FusionnetState(), pipeline.KeyframeState()
+        with torch.no_grad():
+            for ref_i, meas_i in clip["frames"]:
+                ri, rp = T(clip["images"][ref_i])[None], T(clip["poses"][ref_i])[None]
+                mi, mp = [T(clip["images"][j])[None] for j in meas_i], [T(clip["poses"][j])[None] for j in meas_i]
+                gold, st_o = oracle.fusionnet_step(w, st_o, ri, rp, mi, mp, K, n_depth_levels=D)
+                pred, st_p = pipeline.keyframe(mods, st_p, ri.to(DEV), rp.to(DEV), [x.to(DEV) for x in mi], [p.to(DEV) for p in mp],
+                                               K.to(DEV), n_depth_levels=D)
+                e = oracle.rel_l1_inverse_depth(pred.cpu().numpy(), gold.numpy())
+                assert e <= 1e-3, "tc backend, frame ref=%d: %.3e" % (ref_i, e)
+    finally:
+        ops.set_conv_backend(old)
+
+
+def test_fusionnet_shipped_weights_tensor_core_backend_vs_shipped_golden():
+    w = scene_fixture.load_shipped_weights("fusionnet")
+    if w is None:
+        pytest.skip("shipped weights not fetched (tools/fetch_fixtures.py needs /root/reference in the build container)")
+    from dvmvs import _ops as ops
+    from oracle import dvmvs_oracle as oracle
+    old = ops.conv_backend()
+    ops.set_conv_backend("tc", terms=3, stride2=True)
+    try:
+        mods = helpers.build_product_modules(w)
+        frames, full_K, gold = scene_fixture.load_scene()
+        state = helpers.ProductState()
+        errs = []
+        with torch.no_grad():
+            for i, fr in enumerate(frames):
+                pred, state = helpers.product_fusionnet_step(mods, state, _cuda(fr["reference_image"])[None], _cuda(fr["reference_pose"])[None],
+                                                             [_cuda(x)[None] for x in fr["measurement_images"]],
+                                                             [_cuda(p)[None] for p in fr["measurement_poses"]], _cuda(full_K)[None])
+                errs.append(oracle.rel_l1_inverse_depth(pred[0].cpu().numpy(), gold[i]))
+        print("tc backend rel-L1(inverse depth) vs shipped golden per frame:", ["%.2e" % e for e in errs])
+        assert max(errs) <= 1e-3, errs
+    finally:
+        ops.set_conv_backend(old)
