@@ -4,6 +4,8 @@
 // Replaces (reference root relative): dvmvs/layers.py:39-65 conv_layer / depth_layer_3x3,
 // dvmvs/fusionnet/model.py:15-119 building blocks (torch.cat / F.interpolate fused into the input loader),
 // torchvision MnasNet _InvertedResidual depthwise convs and FeaturePyramidNetwork's top-down add.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dvmvs {
@@ -264,7 +266,8 @@ static int launch_conv(const ConvParams& p, cudaStream_t s) {
 // Depthwise convolution
 // =====================================================================================================
 __global__ void dwconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                              float* __restrict__ y, int B, int H, int W, int C, int Hout, int Wout, int ks, int stride, int act) {
+                              float* __restrict__ y, __half* __restrict__ planes, int B, int H, int W, int C, int Hout, int Wout,
+                              int ks, int stride, int act) {
   const int c4n = C >> 2;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * Hout * Wout * c4n;
@@ -293,7 +296,19 @@ __global__ void dwconv_kernel(const float* __restrict__ x, const float* __restri
   if (act == DVMVS_ACT_RELU) {
     acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
   }
-  reinterpret_cast<float4*>(y + pix * C)[cg] = acc;
+  if (y) reinterpret_cast<float4*>(y + pix * C)[cg] = acc;
+  if (planes) {   // fp16 (hi, lo) pair for the tensor-core consumer (the pointwise projection)
+    const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    __align__(8) __half hi[4];
+    __align__(8) __half lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = __float2half_rn(v[e]);
+      lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+    }
+    *reinterpret_cast<uint2*>(planes + pix * C + cg * 4) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(planes + total * 4 + pix * C + cg * 4) = *reinterpret_cast<const uint2*>(lo);
+  }
 }
 
 // =====================================================================================================
@@ -476,19 +491,21 @@ extern "C" int dvmvs_conv2d(const dvmvs_conv_desc* desc, dvmvs_stream_t stream) 
   return DVMVS_OK;
 }
 
-extern "C" int dvmvs_dwconv2d(const float* x, const float* weight, const float* bias, float* y, int B, int H, int W, int C,
-                              int ksize, int stride, int act, dvmvs_stream_t stream) {
-  DVMVS_REQUIRE(x && weight && y, "dwconv2d: null pointer");
+extern "C" int dvmvs_dwconv2d(const float* x, const float* weight, const float* bias, float* y, void* y_planes, int B, int H, int W,
+                              int C, int ksize, int stride, int act, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(x && weight && (y || y_planes), "dwconv2d: null pointer");
+  DVMVS_REQUIRE(!y_planes || C % 8 == 0, "dwconv2d: fp16-pair output needs C %% 8 == 0");
   DVMVS_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "dwconv2d: bad shape (C must be a multiple of 4)");
   DVMVS_REQUIRE((ksize == 3 || ksize == 5) && (stride == 1 || stride == 2), "dwconv2d: ksize/stride");
   DVMVS_REQUIRE(act == DVMVS_ACT_NONE || act == DVMVS_ACT_RELU, "dwconv2d: act");
-  DVMVS_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)weight % 16 == 0 && (uintptr_t)y % 16 == 0 && (!bias || (uintptr_t)bias % 16 == 0),
+  DVMVS_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)weight % 16 == 0 && (uintptr_t)y % 16 == 0 && (!bias || (uintptr_t)bias % 16 == 0) &&
+                    (uintptr_t)y_planes % 16 == 0,
                 "dwconv2d: pointers must be 16-byte aligned");
   const int pad = ksize / 2;
   const int Hout = (H + 2 * pad - ksize) / stride + 1, Wout = (W + 2 * pad - ksize) / stride + 1;
   const size_t total = (size_t)B * Hout * Wout * (C / 4);
-  dwconv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, weight, bias, y, B, H, W, C, Hout, Wout, ksize,
-                                                                                 stride, act);
+  dwconv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, weight, bias, y, (__half*)y_planes, B, H, W, C, Hout,
+                                                                                 Wout, ksize, stride, act);
   return check_launch("dwconv_kernel");
 }
 

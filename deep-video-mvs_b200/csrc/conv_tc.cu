@@ -16,8 +16,8 @@
 // * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
 //   warps 2-5 = epilogue (tcgen05.ld -> bias/residual/activation -> fp32 and/or fp16-pair stores).
 //   smem ring of kStages stages, full/empty mbarriers, tcgen05.commit releases stages and signals the epilogue.
-// * Small-M layers (8x8 .. 16x16 maps) split K (filter taps) over blockIdx.z and reduce with fp32 red.global.add;
-//   a finishing kernel applies the epilogue.
+// * Small-M layers (8x8 .. 16x16 maps) split K (filter taps) over blockIdx.z: every split publishes fp32 partial sums,
+//   the last CTA to arrive (atomic counter) reduces them in split order (deterministic) and runs the epilogue.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <string.h>
@@ -109,7 +109,9 @@ struct TcParams {
   float* aux_out;
   float aux_mult, aux_base;
   int act;
-  float* workspace;
+  float* workspace;           // split-K partial sums [ksplit][out elements]
+  int* tile_counters;         // split-K arrival counters, one per (tile, n-block); zero before and after the launch
+  int num_stages, stage_bytes, a_bytes, w_bytes;   // smem ring geometry (runtime: sized by the widest K chunk in use)
 };
 
 __device__ __forceinline__ float tc_act(float v, int act) {
@@ -118,28 +120,31 @@ __device__ __forceinline__ float tc_act(float v, int act) {
   return v;
 }
 
+constexpr int kMaxStages = 8;
+constexpr int kBarrierBytes = 256;   // full[8] + empty[8] + tmem_full + TMEM slot + split-K flag
+constexpr int kMaxSmemBytes = 227 * 1024;
+
 template <int BLOCK_N>
 struct TcCfg {
-  static constexpr int kWStageBytes = BLOCK_N * 128;
-  static constexpr int kStageBytes = 2 * kAStageBytes + 2 * kWStageBytes;
-  static constexpr int kStages = (BLOCK_N <= 32) ? 4 : (BLOCK_N <= 64 ? 4 : 3);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_constant__ TcParams p) {
   using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* base_ptr = smem_raw + (base - raw_addr);
-  const uint32_t bars = base + Cfg::kStages * Cfg::kStageBytes;
-  // barrier layout (8 bytes each): full[kStages], empty[kStages], tmem_full; then the TMEM base address word
+  const int n_stages = p.num_stages;
+  const uint32_t bars = base + n_stages * p.stage_bytes;
+  // barrier layout (8 bytes each): full[8], empty[8], tmem_full; then the TMEM base address word and the split-K flag
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (Cfg::kStages + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * Cfg::kStages);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 1));
+  auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * kMaxStages);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + n_stages * p.stage_bytes + 8 * (2 * kMaxStages + 1));
+  volatile uint32_t* last_flag = tmem_slot + 1;
+  const uint32_t off_a_lo = p.a_bytes, off_w_hi = (p.terms > 1 ? 2u : 1u) * p.a_bytes, off_w_lo = off_w_hi + p.w_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map[s][0]) : "memory");
       if (p.terms > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map[s][1]) : "memory");
     }
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -188,16 +193,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           const int kind = (kc == 64) ? 1 : 0;
           for (int ch = 0; ch < p.src_chunks[s]; ++ch, wk += kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sb = base + stage * Cfg::kStageBytes;
+            const uint32_t sb = base + stage * p.stage_bytes;
             const uint32_t a_bytes = kTileM * kc * 2, w_bytes = BLOCK_N * kc * 2;
             mbar_expect_tx(full_bar(stage), (p.terms > 1 ? 2u : 1u) * (a_bytes + w_bytes));
             tma_load_4d(sb, &p.a_map[s][0], full_bar(stage), ch * kc, ix, iy, b);
-            tma_load_2d(sb + 2 * kAStageBytes, &p.w_map[kind][0], full_bar(stage), wk, n0);
+            tma_load_2d(sb + off_w_hi, &p.w_map[kind][0], full_bar(stage), wk, n0);
             if (p.terms > 1) {
-              tma_load_4d(sb + kAStageBytes, &p.a_map[s][1], full_bar(stage), ch * kc, ix, iy, b);
-              tma_load_2d(sb + 2 * kAStageBytes + Cfg::kWStageBytes, &p.w_map[kind][1], full_bar(stage), wk, n0);
+              tma_load_4d(sb + off_a_lo, &p.a_map[s][1], full_bar(stage), ch * kc, ix, iy, b);
+              tma_load_2d(sb + off_w_lo, &p.w_map[kind][1], full_bar(stage), wk, n0);
             }
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -218,9 +223,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           for (int ch = 0; ch < p.src_chunks[s]; ++ch) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint32_t sb = base + stage * Cfg::kStageBytes;
-            const uint32_t a_hi = sb, a_lo = sb + kAStageBytes;
-            const uint32_t w_hi = sb + 2 * kAStageBytes, w_lo = w_hi + Cfg::kWStageBytes;
+            const uint32_t sb = base + stage * p.stage_bytes;
+            const uint32_t a_hi = sb, a_lo = sb + off_a_lo;
+            const uint32_t w_hi = sb + off_w_hi, w_lo = sb + off_w_lo;
             for (int term = 0; term < p.terms; ++term) {
               const uint32_t a_s = (term == 1) ? a_lo : a_hi;
               const uint32_t w_s = (term == 2) ? w_lo : w_hi;
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               }
             }
             tc_commit(empty_bar(stage));     // stage reusable once these MMAs have consumed it
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -247,72 +252,107 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     tc_fence_after();
     const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
     const size_t plane_stride = (size_t)p.B * p.Hout * p.Wout * p.Cout;
+    bool is_last = true;
+    if (p.ksplit > 1) {
+      // ---- split-K: publish this tap range's partial sums; the last CTA to arrive for this (tile, n-block) reduces
+      // all partials in split order (deterministic) and runs the epilogue.
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (!valid) continue;
-      const int cbase = n0 + c0;
-      if (p.ksplit > 1) {   // partial sums of this tap range; reduced in fixed order by conv_tc_finish_kernel
-        float* wsp = p.workspace + (size_t)blockIdx.z * plane_stride + pix * p.Cout + cbase;
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (!valid) continue;
+        float* wsp = p.workspace + (size_t)blockIdx.z * plane_stride + pix * p.Cout + n0 + c0;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (cbase + j < p.Cout) wsp[j] = v[j];
-        continue;
+          if (n0 + c0 + j < p.Cout) wsp[j] = v[j];
       }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = cbase + j;
-        if (c < p.Cout) {
-          float x = v[j];
-          if (p.bias) x += __ldg(p.bias + c);
-          if (p.residual_mode == DVMVS_RES_SAME) {
-            x += __ldg(p.residual + pix * p.Cout + c);
-          } else if (p.residual_mode == DVMVS_RES_NEAREST_UP) {
-            const int ry = (int)(((long long)oy * p.Hr) / p.Hout), rx = (int)(((long long)ox * p.Wr) / p.Wout);
-            x += __ldg(p.residual + (((size_t)b * p.Hr + ry) * p.Wr + rx) * p.Cout + c);
-          }
-          v[j] = tc_act(x, p.act);
-        }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const int slot = blockIdx.y * gridDim.x + blockIdx.x;
+        const int prev = atomicAdd(p.tile_counters + slot, 1);
+        const bool last = (prev == p.ksplit - 1);
+        if (last) p.tile_counters[slot] = 0;             // self-cleaning for the next launch
+        *last_flag = last ? 1u : 0u;
       }
-      const bool vec = ((p.Cout & 7) == 0) && (cbase + 32 <= p.Cout);
-      if (p.out_f32) {
-        float* o = p.out_f32 + pix * p.Cout + cbase;
-        if (vec) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      is_last = (*last_flag != 0u);
+      if (is_last) __threadfence();
+    }
+    if (is_last) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float v[32];
+        if (p.ksplit > 1) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (cbase + j < p.Cout) o[j] = v[j];
-        }
-      }
-      if (p.aux_out) {
-        for (int j = 0; j < 32; ++j)
-          if (cbase + j < p.Cout) p.aux_out[pix * p.Cout + cbase + j] = 1.f / (p.aux_mult * v[j] + p.aux_base);
-      }
-      if (p.out_planes) {
-        __half* oh = p.out_planes + pix * p.Cout + cbase;
-        __half* ol = oh + plane_stride;
-        if (vec) {
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          if (valid) {
+            for (int sp = 0; sp < p.ksplit; ++sp) {
+              const float* wsp = p.workspace + (size_t)sp * plane_stride + pix * p.Cout + n0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __align__(16) __half hi[8];
-            __align__(16) __half lo[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              hi[e] = __float2half_rn(v[j + e]);
-              lo[e] = __float2half_rn(v[j + e] - __half2float(hi[e]));
+              for (int j = 0; j < 32; ++j)
+                if (n0 + c0 + j < p.Cout) v[j] += __ldcg(wsp + j);
             }
-            *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(ol + j) = *reinterpret_cast<const uint4*>(lo);
           }
         } else {
-          for (int j = 0; j < 32; ++j)
-            if (cbase + j < p.Cout) {
-              const __half h = __float2half_rn(v[j]);
-              oh[j] = h;
-              ol[j] = __float2half_rn(v[j] - __half2float(h));
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        }
+        if (!valid) continue;
+        const int cbase = n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = cbase + j;
+          if (c < p.Cout) {
+            float x = v[j];
+            if (p.bias) x += __ldg(p.bias + c);
+            if (p.residual_mode == DVMVS_RES_SAME) {
+              x += __ldg(p.residual + pix * p.Cout + c);
+            } else if (p.residual_mode == DVMVS_RES_NEAREST_UP) {
+              const int ry = (int)(((long long)oy * p.Hr) / p.Hout), rx = (int)(((long long)ox * p.Wr) / p.Wout);
+              x += __ldg(p.residual + (((size_t)b * p.Hr + ry) * p.Wr + rx) * p.Cout + c);
             }
+            v[j] = tc_act(x, p.act);
+          }
+        }
+        const bool vec = ((p.Cout & 7) == 0) && (cbase + 32 <= p.Cout);
+        if (p.out_f32) {
+          float* o = p.out_f32 + pix * p.Cout + cbase;
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.Cout) o[j] = v[j];
+          }
+        }
+        if (p.aux_out) {
+          for (int j = 0; j < 32; ++j)
+            if (cbase + j < p.Cout) p.aux_out[pix * p.Cout + cbase + j] = 1.f / (p.aux_mult * v[j] + p.aux_base);
+        }
+        if (p.out_planes) {
+          __half* oh = p.out_planes + pix * p.Cout + cbase;
+          __half* ol = oh + plane_stride;
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __align__(16) __half hi[8];
+              __align__(16) __half lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                hi[e] = __float2half_rn(v[j + e]);
+                lo[e] = __float2half_rn(v[j + e] - __half2float(hi[e]));
+              }
+              *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(hi);
+              *reinterpret_cast<uint4*>(ol + j) = *reinterpret_cast<const uint4*>(lo);
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.Cout) {
+                const __half h = __float2half_rn(v[j]);
+                oh[j] = h;
+                ol[j] = __float2half_rn(v[j] - __half2float(h));
+              }
+          }
         }
       }
     }
@@ -326,45 +366,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   }
 }
 
-// finishing pass for split-K launches: bias / residual / activation in place, fp16-pair copy
-__global__ void conv_tc_finish_kernel(TcParams p) {
-  const size_t total = (size_t)p.B * p.Hout * p.Wout * p.Cout;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c = (int)(idx % p.Cout);
-  const size_t pix = idx / p.Cout;
-  const int ox = (int)(pix % p.Wout);
-  const int oy = (int)((pix / p.Wout) % p.Hout);
-  const int b = (int)(pix / ((size_t)p.Wout * p.Hout));
-  float x = 0.f;
-  for (int sp = 0; sp < p.ksplit; ++sp) x += p.workspace[(size_t)sp * total + idx];
-  if (p.bias) x += __ldg(p.bias + c);
-  if (p.residual_mode == DVMVS_RES_SAME) {
-    x += __ldg(p.residual + idx);
-  } else if (p.residual_mode == DVMVS_RES_NEAREST_UP) {
-    const int ry = (int)(((long long)oy * p.Hr) / p.Hout), rx = (int)(((long long)ox * p.Wr) / p.Wout);
-    x += __ldg(p.residual + (((size_t)b * p.Hr + ry) * p.Wr + rx) * p.Cout + c);
-  }
-  x = tc_act(x, p.act);
-  if (p.out_f32) p.out_f32[idx] = x;
-  if (p.aux_out) p.aux_out[idx] = 1.f / (p.aux_mult * x + p.aux_base);
-  if (p.out_planes) {
-    const __half h = __float2half_rn(x);
-    p.out_planes[idx] = h;
-    p.out_planes[total + idx] = __float2half_rn(x - __half2float(h));
-  }
-}
-
 // fp32 channel-last -> fp16 (hi, lo) planes with the channel count padded to Cs (zeros); optional x2 bilinear
 // (align_corners) upsampling on the way (materialises F.interpolate for the TMA-fed consumer).
 __global__ void split_planes_kernel(const float* __restrict__ x, __half* __restrict__ planes, int B, int H, int W, int C, int Cs,
-                                    int upsample) {
+                                    int upsample, int c_offset, int c_cover) {
+  // writes channels [c_offset, c_offset + c_cover) of the Cs-channel plane tensor: x for the first C of them, zeros after
   const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
   const size_t total = (size_t)B * Ho * Wo * Cs;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c = (int)(idx % Cs);
-  const size_t pix = idx / Cs;
+  if (idx >= (size_t)B * Ho * Wo * c_cover) return;
+  const int c = (int)(idx % c_cover);
+  const size_t pix = idx / c_cover;
   float v = 0.f;
   if (c < C) {
     if (!upsample) {
@@ -385,8 +397,9 @@ __global__ void split_planes_kernel(const float* __restrict__ x, __half* __restr
     }
   }
   const __half h = __float2half_rn(v);
-  planes[idx] = h;
-  planes[total + idx] = __float2half_rn(v - __half2float(h));
+  const size_t o = pix * Cs + c_offset + c;
+  planes[o] = h;
+  planes[total + o] = __float2half_rn(v - __half2float(h));
 }
 
 // ----------------------------------------------------------------------------------------------- host side
@@ -438,15 +451,26 @@ static int make_w_map(CUtensorMap* map, const void* ptr, int rows, int ktot, int
 }
 
 template <int BLOCK_N>
-static int launch_tc(const TcParams& p, dim3 grid, cudaStream_t s) {
-  using Cfg = TcCfg<BLOCK_N>;
+static int launch_tc(TcParams& p, dim3 grid, int kc_max, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess) { set_error("conv_tc smem attribute: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
     attr_set = true;
   }
-  conv_tc_kernel<BLOCK_N><<<grid, kTcThreads, Cfg::kSmemBytes, s>>>(p);
+  // smem ring sized by the widest K chunk actually used; small stages => several CTAs co-reside per SM, which is what
+  // hides the prologue / epilogue / TMA latency of these short tiles
+  p.a_bytes = kTileM * kc_max * 2;
+  p.w_bytes = BLOCK_N * kc_max * 2;
+  p.stage_bytes = (p.terms > 1 ? 2 : 1) * (p.a_bytes + p.w_bytes);
+  const int overhead = 1024 + kBarrierBytes;
+  int stages = 0;
+  const int budgets[3] = {74 * 1024, 112 * 1024, kMaxSmemBytes};
+  for (int i = 0; i < 3 && stages < 3; ++i) stages = (budgets[i] - overhead) / p.stage_bytes;
+  stages = max(2, min(kMaxStages, stages));
+  p.num_stages = stages;
+  const int smem = stages * p.stage_bytes + overhead;
+  conv_tc_kernel<BLOCK_N><<<grid, kTcThreads, smem, s>>>(p);
   return check_launch("conv_tc_kernel");
 }
 
@@ -480,13 +504,14 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   p.tiles_x = (p.Wout + p.tile_w - 1) / p.tile_w;
   p.tiles_y = (p.Hout + p.tile_h - 1) / p.tile_h;
   p.n_src = d->n_src; p.terms = d->terms;
-  int k_per_tap = 0;
+  int k_per_tap = 0, kc_max = 32;
   for (int s = 0; s < d->n_src; ++s) {
     const int Cs = d->src_channels[s];
     DVMVS_REQUIRE(d->src_planes[s] && Cs > 0 && Cs % 8 == 0, "conv2d_tc: source %d needs a channel count that is a multiple of 8", s);
     DVMVS_REQUIRE((uintptr_t)d->src_planes[s] % 16 == 0, "conv2d_tc: source %d not 16-byte aligned", s);
     p.src_kchunk[s] = (Cs % 64 == 0) ? 64 : 32;
     p.src_chunks[s] = (Cs + p.src_kchunk[s] - 1) / p.src_kchunk[s];
+    kc_max = max(kc_max, p.src_kchunk[s]);
     k_per_tap += p.src_chunks[s] * p.src_kchunk[s];
     const size_t plane = (size_t)d->B * d->Hin * d->Win * Cs;
     int rc = make_act_map(&p.a_map[s][0], d->src_planes[s], d->B, d->Hin, d->Win, Cs, p.src_kchunk[s], p.tile_w, p.tile_h, d->stride);
@@ -520,30 +545,31 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   const int n_taps = d->ksize * d->ksize;
   p.workspace = d->workspace;
   const size_t out_elems = (size_t)d->B * p.Hout * p.Wout * d->Cout;
-  if (d->allow_split && d->workspace && ctas < 74 && n_taps > 1) {
-    long long fit = d->workspace_bytes / (long long)(out_elems * sizeof(float));
+  const long long counter_bytes = 16384;        // head of the workspace: arrival counters (zero-initialised by the owner)
+  if (d->allow_split && d->workspace && d->workspace_bytes > counter_bytes && ctas < 74 && n_taps > 1 &&
+      (long long)p.tiles_x * p.tiles_y * d->B * n_tiles * (long long)sizeof(int) <= counter_bytes) {
+    p.tile_counters = (int*)d->workspace;
+    p.workspace = d->workspace + counter_bytes / sizeof(float);
+    long long fit = (d->workspace_bytes - counter_bytes) / (long long)(out_elems * sizeof(float));
     p.ksplit = (int)max(1LL, min((long long)min(n_taps, (148 + ctas - 1) / ctas), fit));
     const int per = (n_taps + p.ksplit - 1) / p.ksplit;
     p.ksplit = (n_taps + per - 1) / per;              // no empty splits
   }
   dim3 grid(p.tiles_x * p.tiles_y * d->B, n_tiles, p.ksplit);
   int rc;
-  if (d->block_n == 32) rc = launch_tc<32>(p, grid, s);
-  else if (d->block_n == 64) rc = launch_tc<64>(p, grid, s);
-  else rc = launch_tc<128>(p, grid, s);
-  if (rc != DVMVS_OK) return rc;
-  if (p.ksplit > 1) {
-    const size_t total = (size_t)d->B * p.Hout * p.Wout * d->Cout;
-    conv_tc_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
-    return check_launch("conv_tc_finish_kernel");
-  }
-  return DVMVS_OK;
+  if (d->block_n == 32) rc = launch_tc<32>(p, grid, kc_max, s);
+  else if (d->block_n == 64) rc = launch_tc<64>(p, grid, kc_max, s);
+  else rc = launch_tc<128>(p, grid, kc_max, s);
+  return rc;
 }
 
-extern "C" int dvmvs_split_planes(const float* x, void* planes, int B, int H, int W, int C, int Cs, int upsample2x,
-                                  dvmvs_stream_t stream) {
-  DVMVS_REQUIRE(x && planes && B > 0 && H > 0 && W > 0 && C > 0 && Cs >= C && Cs % 8 == 0, "split_planes: bad argument");
-  const size_t total = (size_t)B * H * W * Cs * (upsample2x ? 4 : 1);
-  split_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)planes, B, H, W, C, Cs, upsample2x);
+extern "C" int dvmvs_split_planes(const float* x, void* planes, int B, int H, int W, int C, int Cs, int upsample2x, int c_offset,
+                                  int c_cover, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(x && planes && B > 0 && H > 0 && W > 0 && C > 0 && Cs % 8 == 0, "split_planes: bad argument");
+  DVMVS_REQUIRE(c_offset >= 0 && c_cover >= C && c_offset + c_cover <= Cs, "split_planes: channel window [%d,+%d) outside %d", c_offset,
+                c_cover, Cs);
+  const size_t total = (size_t)B * H * W * c_cover * (upsample2x ? 4 : 1);
+  split_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)planes, B, H, W, C, Cs, upsample2x,
+                                                                                   c_offset, c_cover);
   return check_launch("split_planes_kernel");
 }

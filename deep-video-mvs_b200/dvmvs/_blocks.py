@@ -166,13 +166,19 @@ class FeatureExtractor(NativeModule):
 
     def run(self, x):
         stem, levels = self.packed()
+        def depthwise(t, dw, consumer):
+            # the depthwise output feeds exactly one pointwise conv: hand it the operand format that conv reads
+            if consumer.uses_tc():
+                return ops.Act(None, ops.dwconv2d(t.f32, dw, want_f32=False, want_planes=True)[1])
+            return ops.Act(ops.dwconv2d(t.f32, dw))
+
         x = stem[0].run([(x, D)])
-        x = ops.Act(ops.dwconv2d(x.f32, stem[1]))
+        x = depthwise(x, stem[1], stem[2])
         x = stem[2].run([(x, D)])
         outs = [x]
         for blocks in levels:
             for expand, dw, project, residual in blocks:
-                y = ops.Act(ops.dwconv2d(expand.run([(x, D)]).f32, dw))
+                y = depthwise(expand.run([(x, D)], want_planes=False), dw, project)
                 x = project.run([(y, D)], residual=x if residual else None,
                                 residual_mode=N.RES_SAME if residual else N.RES_NONE)
             outs.append(x)
@@ -280,7 +286,7 @@ class CostVolumeDecoder(NativeModule):
     def _pack(self):
         heads = [ops.ConvLayer(pack_head(m)) for m in (self.depth_layer_one_sixteen, self.depth_layer_one_eight,
                                                        self.depth_layer_quarter, self.depth_layer_half, self.depth_layer_full)]
-        return heads, ops.ConvLayer(pack_cbr(self.refine[0]), [hyper_channels, 1, 3]), ops.ConvLayer(pack_cbr(self.refine[1]))
+        return heads, ops.ConvLayer(pack_cbr(self.refine[0]), [hyper_channels, 1, 3], pack_sources=True), ops.ConvLayer(pack_cbr(self.refine[1]))
 
     def run(self, image, skip0, skip1, skip2, skip3, bottom):
         heads, r0, r1 = self.packed()

@@ -69,8 +69,8 @@ def lib():
         L.dvmvs_depth_reproject.argtypes = [p, p, p, p, p, p, i, i, i, p]
         L.dvmvs_conv2d.argtypes = [ctypes.POINTER(ConvDesc), p]
         L.dvmvs_conv2d_tc.argtypes = [ctypes.POINTER(ConvTcDesc), p]
-        L.dvmvs_split_planes.argtypes = [p, p, i, i, i, i, i, i, p]
-        L.dvmvs_dwconv2d.argtypes = [p, p, p, p, i, i, i, i, i, i, i, p]
+        L.dvmvs_split_planes.argtypes = [p, p, i, i, i, i, i, i, i, i, p]
+        L.dvmvs_dwconv2d.argtypes = [p, p, p, p, p, i, i, i, i, i, i, i, p]
         L.dvmvs_lstm_gates.argtypes = [p, p, p, p, i, i, i, i, p]
         L.dvmvs_upsample2x.argtypes = [p, p, i, i, i, i, p]
         L.dvmvs_nchw_to_nhwc.argtypes = [p, p, i, i, i, i, p]

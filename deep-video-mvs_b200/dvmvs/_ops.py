@@ -22,7 +22,8 @@ def workspace(device):
     key = (device.type, device.index)
     ws = _WORKSPACE.get(key)
     if ws is None:
-        ws = _WORKSPACE[key] = torch.empty(WORKSPACE_BYTES // 4, dtype=torch.float32, device=device)
+        # zero-initialised: its first 16 KiB hold the split-K arrival counters of conv_tc_kernel (self-cleaning)
+        ws = _WORKSPACE[key] = torch.zeros(WORKSPACE_BYTES // 4, dtype=torch.float32, device=device)
     return ws
 
 
@@ -140,20 +141,23 @@ def conv2d(sources, pc, residual=None, residual_mode=N.RES_NONE, aux=None):
     d.B, d.Hin, d.Win, d.Cout = B, Hin, Win, pc.cout
     d.ksize, d.stride, d.act = pc.ksize, pc.stride, pc.act
     ws = workspace(first.device)
-    d.workspace, d.workspace_bytes = ws.data_ptr(), WORKSPACE_BYTES
+    d.workspace, d.workspace_bytes = ws.data_ptr() + 16384, WORKSPACE_BYTES - 16384      # head = tensor-core path's counters
     N.check(N.lib().dvmvs_conv2d(ctypes.byref(d), _stream()), "conv2d")
     return (out, aux_out) if aux is not None else out
 
 
-def dwconv2d(x, pd):
+def dwconv2d(x, pd, want_f32=True, want_planes=False):
+    """Returns y (fp32) by default; with want_planes also / only the fp16-pair planes: (y or None, planes)."""
     B, H, W, C = x.shape
     pad = pd.ksize // 2
     Hout = (H + 2 * pad - pd.ksize) // pd.stride + 1
     Wout = (W + 2 * pad - pd.ksize) // pd.stride + 1
-    y = torch.empty((B, Hout, Wout, C), dtype=torch.float32, device=x.device)
-    N.check(N.lib().dvmvs_dwconv2d(x.data_ptr(), pd.weight.data_ptr(), pd.bias.data_ptr(), y.data_ptr(), B, H, W, C,
-                                   pd.ksize, pd.stride, pd.act, _stream()), "dwconv2d")
-    return y
+    y = torch.empty((B, Hout, Wout, C), dtype=torch.float32, device=x.device) if want_f32 else None
+    planes = torch.empty((2, B, Hout, Wout, C), dtype=torch.float16, device=x.device) if want_planes else None
+    N.check(N.lib().dvmvs_dwconv2d(x.data_ptr(), pd.weight.data_ptr(), pd.bias.data_ptr(), y.data_ptr() if want_f32 else None,
+                                   planes.data_ptr() if want_planes else None, B, H, W, C, pd.ksize, pd.stride, pd.act, _stream()),
+            "dwconv2d")
+    return (y, planes) if want_planes else y
 
 
 def plane_sweep(ref_nhwc, meas_nhwc_list, pose1, pose2_list, K, min_depth, max_depth, n_depth_levels, dot_product=True,
@@ -233,8 +237,27 @@ def split_planes(x_nhwc, upsample=False):
     Cs = round_up(C, 8)
     f = 2 if upsample else 1
     planes = torch.empty((2, B, H * f, W * f, Cs), dtype=torch.float16, device=x_nhwc.device)
-    N.check(N.lib().dvmvs_split_planes(x_nhwc.data_ptr(), planes.data_ptr(), B, H, W, C, Cs, 1 if upsample else 0, _stream()),
+    N.check(N.lib().dvmvs_split_planes(x_nhwc.data_ptr(), planes.data_ptr(), B, H, W, C, Cs, 1 if upsample else 0, 0, Cs, _stream()),
             "split_planes")
+    return planes
+
+
+def concat_planes(sources):
+    """torch.cat([...], dim=channels) staged directly as ONE fp16-pair operand tensor: sources = [(fp32 nhwc, upsample)]."""
+    shapes = [(t.shape[1] * (2 if up else 1), t.shape[2] * (2 if up else 1)) for t, up in sources]
+    B, (Ho, Wo) = sources[0][0].shape[0], shapes[0]
+    if any(s != (Ho, Wo) for s in shapes):
+        raise ValueError("concat_planes: spatial sizes differ: %s" % (shapes,))
+    c_total = sum(t.shape[3] for t, _ in sources)
+    Cs = round_up(c_total, 8)
+    planes = torch.empty((2, B, Ho, Wo, Cs), dtype=torch.float16, device=sources[0][0].device)
+    off = 0
+    for i, (t, up) in enumerate(sources):
+        C = t.shape[3]
+        cover = C if i + 1 < len(sources) else Cs - off          # the last source also zero-fills the padding channels
+        N.check(N.lib().dvmvs_split_planes(t.data_ptr(), planes.data_ptr(), B, t.shape[1], t.shape[2], C, Cs, 1 if up else 0, off, cover,
+                                           _stream()), "split_planes")
+        off += C
     return planes
 
 
@@ -371,9 +394,11 @@ class Act:
 
     @property
     def channels(self):
-        return self.f32.shape[3]
+        return self.f32.shape[3] if self.f32 is not None else self.planes.shape[4]
 
     def get_planes(self, upsample=False):
+        if self.f32 is None and (upsample or self.planes is None):
+            raise RuntimeError("activation has no fp32 representation to derive planes from")
         if upsample:
             if self.planes_up is None:
                 self.planes_up = split_planes(self.f32, upsample=True)
@@ -403,24 +428,35 @@ def act_to_api(a):
 class ConvLayer:
     """One dense convolution of the network: BN-folded weights for both backends + the channel split of its sources."""
 
-    def __init__(self, pc, src_channels=None):
+    def __init__(self, pc, src_channels=None, pack_sources=False):
+        """pack_sources: on the tensor-core path stage all sources into ONE concatenated operand tensor (fewer, fuller K
+        chunks when the sources are narrow, e.g. refine.0's [32, 1, 3])."""
         self.pc = pc
         self.src_channels = list(src_channels) if src_channels is not None else [pc.cin]
+        self.pack_sources = pack_sources
         self._ptc = None
 
     def tc_eligible(self):
         pc = self.pc
         return pc.cout % 8 == 0 and pc.cout >= 16 and (pc.stride == 1 or _TC_STRIDE2) and pc.cin >= 16
 
-    def run(self, sources, residual=None, residual_mode=N.RES_NONE, aux=None):
-        """sources: list of (Act, mode).  Returns Act (or (Act, aux tensor))."""
+    def uses_tc(self):
+        return _BACKEND == "tc" and self.tc_eligible()
+
+    def run(self, sources, residual=None, residual_mode=N.RES_NONE, aux=None, want_f32=True, want_planes=True):
+        """sources: list of (Act, mode).  Returns Act (or (Act, aux tensor)).  want_* only prune outputs of the
+        tensor-core path (the fp32 path always produces fp32)."""
         pc = self.pc
-        if _BACKEND == "tc" and self.tc_eligible():
+        if self.uses_tc():
             if self._ptc is None:
-                self._ptc = PackedConvTC(pc, self.src_channels, pc.weight.device)
-            planes = [a.get_planes(upsample=(mode == N.SRC_UPSAMPLE2X)) for a, mode in sources]
+                self._ptc = PackedConvTC(pc, [pc.cin] if self.pack_sources else self.src_channels, pc.weight.device)
+            if self.pack_sources:
+                planes = [concat_planes([(a.f32, mode == N.SRC_UPSAMPLE2X) for a, mode in sources])]
+            else:
+                planes = [a.get_planes(upsample=(mode == N.SRC_UPSAMPLE2X)) for a, mode in sources]
             res = residual.f32 if residual is not None else None
-            r = conv2d_tc(planes, self._ptc, residual=res, residual_mode=residual_mode, aux=aux, terms=_TC_TERMS)
+            r = conv2d_tc(planes, self._ptc, residual=res, residual_mode=residual_mode, aux=aux, terms=_TC_TERMS,
+                          want_f32=want_f32, want_planes=want_planes)
             out = Act(r[0], r[1])
             return (out, r[2]) if aux is not None else out
         r = conv2d([(a.f32, mode) for a, mode in sources], pc, residual=residual.f32 if residual is not None else None,

@@ -138,15 +138,18 @@ typedef struct {
 
 int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* desc_host, dvmvs_stream_t stream);
 
-/* fp32 channel-last [B][H][W][C] -> fp16 (hi, lo) planes [2][B][H'][W'][Cs] (Cs >= C, multiple of 8, zero padded);
- * upsample2x != 0 applies the x2 bilinear (align_corners) interpolation on the way (H' = 2H). */
-int dvmvs_split_planes(const float* x, void* planes, int B, int H, int W, int C, int Cs, int upsample2x,
-                       dvmvs_stream_t stream);
+/* fp32 channel-last [B][H][W][C] -> channels [c_offset, c_offset + c_cover) of fp16 (hi, lo) planes
+ * [2][B][H'][W'][Cs] (Cs a multiple of 8): the C values of x, then zeros up to c_cover.  Several calls with different
+ * offsets stage a channel concatenation (torch.cat) into one operand tensor.  upsample2x != 0 applies the x2 bilinear
+ * (align_corners) interpolation on the way (H' = 2H). */
+int dvmvs_split_planes(const float* x, void* planes, int B, int H, int W, int C, int Cs, int upsample2x, int c_offset,
+                       int c_cover, dvmvs_stream_t stream);
 
 /* Depthwise k x k convolution (MnasNet), folded-BN bias + optional ReLU.
- * x [B][H][W][C], weight [k][k][C], bias [C], y [B][Hout][Wout][C]. */
-int dvmvs_dwconv2d(const float* x, const float* weight, const float* bias, float* y, int B, int H, int W, int C,
-                   int ksize, int stride, int act, dvmvs_stream_t stream);
+ * x [B][H][W][C], weight [k][k][C], bias [C]; outputs (either or both): y fp32 [B][Hout][Wout][C],
+ * y_planes fp16 (hi, lo) [2][B][Hout][Wout][C] for a tensor-core consumer. */
+int dvmvs_dwconv2d(const float* x, const float* weight, const float* bias, float* y, void* y_planes, int B, int H, int W,
+                   int C, int ksize, int stride, int act, dvmvs_stream_t stream);
 
 /* ConvLSTM gate epilogue: replaces dvmvs/convlstm.py:45-59.  gates [B][h][w][4*C] in the order i,f,o,g;
  * c_in [B][h][w][C]; writes h_out, c_out [B][h][w][C].  LayerNorm over (h,w) per (b,channel), biased

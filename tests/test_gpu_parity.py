@@ -209,6 +209,10 @@ def test_dwconv_vs_torch_fp32(synth, case):
     pd.weight, pd.bias = pd.weight.to(DEV), pd.bias.to(DEV)
     out = ops.dwconv2d(ops.to_nhwc(x.to(DEV)), pd)
     assert rel_err(ops.to_api(out).cpu().numpy(), ref.numpy()) <= 2e-5
+    if C % 8 == 0:
+        out2, planes = ops.dwconv2d(ops.to_nhwc(x.to(DEV)), pd, want_f32=True, want_planes=True)
+        assert torch.equal(out2, out)
+        assert rel_err((planes[0].float() + planes[1].float()).cpu().numpy(), out.cpu().numpy()) <= 2e-6
 
 
 def test_layout_roundtrip_and_upsample(synth):

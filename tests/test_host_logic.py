@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), "libdvmvs_sm100.so does not export %s" % sym
     assert sorted(N.EXPORTED_SYMBOLS) == declared
-    assert lib.dvmvs_abi_version() == 1
+    assert lib.dvmvs_abi_version() == 2
 
 
 def test_conv_desc_struct_matches_header_field_order():
@@ -44,7 +44,7 @@ def test_argument_validation_without_gpu():
     d = N.ConvDesc()
     d.n_src = 7
     assert lib.dvmvs_conv2d(ctypes.byref(d), None) == -1
-    assert lib.dvmvs_dwconv2d(None, None, None, None, 1, 8, 8, 6, 3, 1, 0, None) == -1
+    assert lib.dvmvs_dwconv2d(None, None, None, None, None, 1, 8, 8, 6, 3, 1, 0, None) == -1
     assert lib.dvmvs_lstm_gates(None, None, None, None, 1, 8, 8, 512, None) == -1
 
 
