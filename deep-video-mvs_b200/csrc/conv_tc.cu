@@ -17,7 +17,7 @@
 //   warps 2-5 = epilogue (tcgen05.ld -> bias/residual/activation -> fp32 and/or fp16-pair stores).
 //   smem ring of kStages stages, full/empty mbarriers, tcgen05.commit releases stages and signals the epilogue.
 // * Small-M layers (8x8 .. 16x16 maps) split K (filter taps) over blockIdx.z: every split publishes fp32 partial sums,
-//   the last CTA to arrive (atomic counter) reduces them in split order (deterministic) and runs the epilogue.
+//   a finishing kernel reduces them in split order (deterministic) and applies the epilogue.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <string.h>
@@ -110,7 +110,6 @@ struct TcParams {
   float aux_mult, aux_base;
   int act;
   float* workspace;           // split-K partial sums [ksplit][out elements]
-  int* tile_counters;         // split-K arrival counters, one per (tile, n-block); zero before and after the launch
   int num_stages, stage_bytes, a_bytes, w_bytes;   // smem ring geometry (runtime: sized by the widest K chunk in use)
 };
 
@@ -143,7 +142,6 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
   const uint32_t tmem_full_bar = bars + 8u * (2 * kMaxStages);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + n_stages * p.stage_bytes + 8 * (2 * kMaxStages + 1));
-  volatile uint32_t* last_flag = tmem_slot + 1;
   const uint32_t off_a_lo = p.a_bytes, off_w_hi = (p.terms > 1 ? 2u : 1u) * p.a_bytes, off_w_lo = off_w_hi + p.w_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -252,51 +250,30 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     tc_fence_after();
     const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
     const size_t plane_stride = (size_t)p.B * p.Hout * p.Wout * p.Cout;
-    bool is_last = true;
     if (p.ksplit > 1) {
-      // ---- split-K: publish this tap range's partial sums; the last CTA to arrive for this (tile, n-block) reduces
-      // all partials in split order (deterministic) and runs the epilogue.
+      // ---- split-K: publish this tap range's partial sums (128 contiguous bytes per thread and 32 columns);
+      // conv_tc_finish_kernel reduces the splits in fixed order (deterministic) and applies the epilogue.
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         if (!valid) continue;
         float* wsp = p.workspace + (size_t)blockIdx.z * plane_stride + pix * p.Cout + n0 + c0;
+        if (((p.Cout & 3) == 0) && (n0 + c0 + 32 <= p.Cout)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c0 + j < p.Cout) wsp[j] = v[j];
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(wsp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.Cout) wsp[j] = v[j];
+        }
       }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        const int slot = blockIdx.y * gridDim.x + blockIdx.x;
-        const int prev = atomicAdd(p.tile_counters + slot, 1);
-        const bool last = (prev == p.ksplit - 1);
-        if (last) p.tile_counters[slot] = 0;             // self-cleaning for the next launch
-        *last_flag = last ? 1u : 0u;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      is_last = (*last_flag != 0u);
-      if (is_last) __threadfence();
     }
+    const bool is_last = (p.ksplit == 1);
     if (is_last) {
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         float v[32];
-        if (p.ksplit > 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          if (valid) {
-            for (int sp = 0; sp < p.ksplit; ++sp) {
-              const float* wsp = p.workspace + (size_t)sp * plane_stride + pix * p.Cout + n0 + c0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + c0 + j < p.Cout) v[j] += __ldcg(wsp + j);
-            }
-          }
-        } else {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        }
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         if (!valid) continue;
         const int cbase = n0 + c0;
 #pragma unroll
@@ -363,6 +340,36 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// finishing pass for split-K launches: sum the per-split partials in split order, bias / residual / activation,
+// fp32 and / or fp16-pair stores
+__global__ void conv_tc_finish_kernel(TcParams p) {
+  const size_t total = (size_t)p.B * p.Hout * p.Wout * p.Cout;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % p.Cout);
+  const size_t pix = idx / p.Cout;
+  const int ox = (int)(pix % p.Wout);
+  const int oy = (int)((pix / p.Wout) % p.Hout);
+  const int b = (int)(pix / ((size_t)p.Wout * p.Hout));
+  float x = 0.f;
+  for (int sp = 0; sp < p.ksplit; ++sp) x += p.workspace[(size_t)sp * total + idx];
+  if (p.bias) x += __ldg(p.bias + c);
+  if (p.residual_mode == DVMVS_RES_SAME) {
+    x += __ldg(p.residual + idx);
+  } else if (p.residual_mode == DVMVS_RES_NEAREST_UP) {
+    const int ry = (int)(((long long)oy * p.Hr) / p.Hout), rx = (int)(((long long)ox * p.Wr) / p.Wout);
+    x += __ldg(p.residual + (((size_t)b * p.Hr + ry) * p.Wr + rx) * p.Cout + c);
+  }
+  x = tc_act(x, p.act);
+  if (p.out_f32) p.out_f32[idx] = x;
+  if (p.aux_out) p.aux_out[idx] = 1.f / (p.aux_mult * x + p.aux_base);
+  if (p.out_planes) {
+    const __half h = __float2half_rn(x);
+    p.out_planes[idx] = h;
+    p.out_planes[total + idx] = __float2half_rn(x - __half2float(h));
   }
 }
 
@@ -545,12 +552,8 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   const int n_taps = d->ksize * d->ksize;
   p.workspace = d->workspace;
   const size_t out_elems = (size_t)d->B * p.Hout * p.Wout * d->Cout;
-  const long long counter_bytes = 16384;        // head of the workspace: arrival counters (zero-initialised by the owner)
-  if (d->allow_split && d->workspace && d->workspace_bytes > counter_bytes && ctas < 74 && n_taps > 1 &&
-      (long long)p.tiles_x * p.tiles_y * d->B * n_tiles * (long long)sizeof(int) <= counter_bytes) {
-    p.tile_counters = (int*)d->workspace;
-    p.workspace = d->workspace + counter_bytes / sizeof(float);
-    long long fit = (d->workspace_bytes - counter_bytes) / (long long)(out_elems * sizeof(float));
+  if (d->allow_split && d->workspace && ctas < 74 && n_taps > 1) {
+    long long fit = d->workspace_bytes / (long long)(out_elems * sizeof(float));
     p.ksplit = (int)max(1LL, min((long long)min(n_taps, (148 + ctas - 1) / ctas), fit));
     const int per = (n_taps + p.ksplit - 1) / p.ksplit;
     p.ksplit = (n_taps + per - 1) / per;              // no empty splits
@@ -560,7 +563,12 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   if (d->block_n == 32) rc = launch_tc<32>(p, grid, kc_max, s);
   else if (d->block_n == 64) rc = launch_tc<64>(p, grid, kc_max, s);
   else rc = launch_tc<128>(p, grid, kc_max, s);
-  return rc;
+  if (rc != DVMVS_OK) return rc;
+  if (p.ksplit > 1) {
+    conv_tc_finish_kernel<<<(unsigned)((out_elems + 255) / 256), 256, 0, s>>>(p);
+    return check_launch("conv_tc_finish_kernel");
+  }
+  return DVMVS_OK;
 }
 
 extern "C" int dvmvs_split_planes(const float* x, void* planes, int B, int H, int W, int C, int Cs, int upsample2x, int c_offset,

@@ -69,69 +69,70 @@ __host__ __device__ __forceinline__ void sweep_sample_pos(const float* base, con
   ys = ((gy + 1.f) * 0.5f) * hm1;
 }
 
-// ---- fast path: C == 32, channel-last.  A quarter warp (8 lanes x float4) owns one reference pixel and walks its D
-// planes; every bilinear tap is ONE 128-byte line, so a warp load instruction touches 4 lines (one per pixel).
-// The CTA owns kPix consecutive reference pixels of one image row; their 128-byte feature vectors are one
-// contiguous span staged in shared memory by a single TMA bulk copy (cp.async.bulk -> UBLKCP).  Per-plane Kt/depth
-// and the per-frame homographies live in shared memory; the per-sample coordinate math is 3 adds, one reciprocal
-// and 4 multiplies (x*(w-1)/w folded into one scale: <= 3 ulp from the reference's op sequence, i.e. ~1e-5 px).
+// ---- fast path: C == 32, channel-last.
+// The CTA owns kPix consecutive reference pixels of one image row; their 128-byte feature vectors are one contiguous
+// span staged in shared memory by a single TMA bulk copy (cp.async.bulk -> UBLKCP).  Work proceeds in steps of
+// (kGroup planes x one measurement frame):
+//   phase A  one THREAD per (pixel, plane): homography, perspective divide, bilinear weights (zeroed for taps outside
+//            the image) and the four clamped tap offsets -> 32 bytes in shared memory.  No redundancy across lanes.
+//   phase B  a quarter warp (8 lanes x float4 = 32 channels) per pixel walks the kGroup planes: two broadcast LDS.128
+//            for the parameters, four 128-byte-line gathers (one line per tap -- a warp instruction touches 4 lines),
+//            16 FMAs to blend + 4 for the dot product; the 8 per-plane partial sums are reduced across the 8 lanes with
+//            a transposing butterfly (7 shuffles for 8 planes) so lane j ends up owning plane j.
+// Phase A of step i+1 is issued before phase B of step i (double-buffered parameters, one __syncthreads per step).
+// Coordinate math: 3 adds, one reciprocal, 4 multiplies (x*(w-1)/w folded into one scale: <= 3 ulp from the
+// reference's op sequence, ~1e-5 px).
 constexpr int kPix = 32;
+constexpr int kGroup = 8;
 constexpr int kSweepThreads = 256;
 
-struct SweepTap {
-  float4 t00, t01, t10, t11;
-  float w00, w01, w10, w11;
+struct __align__(16) SweepTapParams {
+  int off[4];     // element offsets of the 4 taps inside one measurement feature map (channel 0)
+  float w[4];     // bilinear weights, 0 for taps outside the image
 };
 
-__device__ __forceinline__ void sweep_fetch(const float* __restrict__ img, const float* G, const float* kd, float uf, float vf,
-                                            float sx, float sy, int w, int h, bool active, SweepTap& t) {
+__device__ __forceinline__ void sweep_phase_a(const SweepParams& p, const float* s_G, const float* s_kd, SweepTapParams* buf, int m,
+                                              int d0, int u0, int v, int npix, float sx, float sy) {
+  const int pix = threadIdx.x & (kPix - 1), pl = threadIdx.x >> 5;
+  const int d = min(d0 + pl, p.D - 1);
+  const float uf = (float)(u0 + min(pix, npix - 1)), vf = (float)v;
+  const float* G = s_G + m * 12;
+  const float* kd = s_kd + (m * p.D + d) * 4;
   const float q0 = fmaf(G[0], uf, fmaf(G[1], vf, G[2])) + kd[0];
   const float q1 = fmaf(G[3], uf, fmaf(G[4], vf, G[5])) + kd[1];
   const float q2 = fmaf(G[6], uf, fmaf(G[7], vf, G[8])) + kd[2];
   const float r = __frcp_rn(q2 + 1e-8f);
   const float xs = q0 * r * sx, ys = q1 * r * sy;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  t.t00 = z; t.t01 = z; t.t10 = z; t.t11 = z;
-  t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
+  SweepTapParams t;
+  t.off[0] = t.off[1] = t.off[2] = t.off[3] = 0;
+  t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
   // some tap inside the image  <=>  -1 < xs < w  and  -1 < ys < h   (false for NaN / Inf)
-  if (active && xs > -1.f && xs < (float)w && ys > -1.f && ys < (float)h) {
+  if (xs > -1.f && xs < (float)p.w && ys > -1.f && ys < (float)p.h) {
     const float x0f = floorf(xs), y0f = floorf(ys);
     const float fx = xs - x0f, fy = ys - y0f;
+    const float gx = (x0f + 1.f) - xs, gy = (y0f + 1.f) - ys;       // the reference's (x0 + 1 - x) weights
     const int x0 = (int)x0f, y0 = (int)y0f;
-    const bool vx0 = x0 >= 0, vx1 = x0 + 1 < w, vy0 = y0 >= 0, vy1 = y0 + 1 < h;
-    const float* p00 = img + ((long long)y0 * w + x0) * 32;
-    if (vy0 && vx0) t.t00 = __ldg(reinterpret_cast<const float4*>(p00));
-    if (vy0 && vx1) t.t01 = __ldg(reinterpret_cast<const float4*>(p00 + 32));
-    if (vy1 && vx0) t.t10 = __ldg(reinterpret_cast<const float4*>(p00 + (long long)w * 32));
-    if (vy1 && vx1) t.t11 = __ldg(reinterpret_cast<const float4*>(p00 + (long long)w * 32 + 32));
-    const float gx = (x0f + 1.f) - xs, gy = (y0f + 1.f) - ys;     // the reference's (x0+1-x) weights
-    t.w00 = gx * gy; t.w01 = fx * gy; t.w10 = gx * fy; t.w11 = fx * fy;
+    const bool vx0 = x0 >= 0, vx1 = x0 + 1 < p.w, vy0 = y0 >= 0, vy1 = y0 + 1 < p.h;
+    const int xa = max(x0, 0), xb = min(x0 + 1, p.w - 1), ya = max(y0, 0), yb = min(y0 + 1, p.h - 1);
+    t.off[0] = (ya * p.w + xa) * 32;
+    t.off[1] = (ya * p.w + xb) * 32;
+    t.off[2] = (yb * p.w + xa) * 32;
+    t.off[3] = (yb * p.w + xb) * 32;
+    t.w[0] = (vy0 && vx0) ? gx * gy : 0.f;
+    t.w[1] = (vy0 && vx1) ? fx * gy : 0.f;
+    t.w[2] = (vy1 && vx0) ? gx * fy : 0.f;
+    t.w[3] = (vy1 && vx1) ? fx * fy : 0.f;
   }
-}
-
-__device__ __forceinline__ float sweep_reduce(const SweepTap& t, const float4& f1, int mode) {
-  float4 ws;
-  ws.x = fmaf(t.t11.x, t.w11, fmaf(t.t10.x, t.w10, fmaf(t.t01.x, t.w01, t.t00.x * t.w00)));
-  ws.y = fmaf(t.t11.y, t.w11, fmaf(t.t10.y, t.w10, fmaf(t.t01.y, t.w01, t.t00.y * t.w00)));
-  ws.z = fmaf(t.t11.z, t.w11, fmaf(t.t10.z, t.w10, fmaf(t.t01.z, t.w01, t.t00.z * t.w00)));
-  ws.w = fmaf(t.t11.w, t.w11, fmaf(t.t10.w, t.w10, fmaf(t.t01.w, t.w01, t.t00.w * t.w00)));
-  float part;
-  if (mode == DVMVS_SWEEP_DOT)
-    part = fmaf(f1.w, ws.w, fmaf(f1.z, ws.z, fmaf(f1.y, ws.y, f1.x * ws.x)));
-  else
-    part = fabsf(f1.x - ws.x) + fabsf(f1.y - ws.y) + fabsf(f1.z - ws.z) + fabsf(f1.w - ws.w);
-  part += __shfl_xor_sync(0xffffffffu, part, 1);
-  part += __shfl_xor_sync(0xffffffffu, part, 2);
-  part += __shfl_xor_sync(0xffffffffu, part, 4);
-  return part;
+  buf[pl * kPix + pix] = t;
 }
 
 __global__ void __launch_bounds__(kSweepThreads, 3) plane_sweep_c32_kernel(SweepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* s_ref = reinterpret_cast<float*>(smem_raw);                     // [kPix][32]
-  float* s_kd = s_ref + kPix * 32;                                       // [M][D][4]  Kt / depth_i (padded to 4)
-  float* s_G = s_kd + p.M * p.D * 4;                                     // [M][12]
-  float* s_out = s_G + kMaxMeas * 12;                                    // [kPix][D]
+  float* s_ref = reinterpret_cast<float*>(smem_raw);                                     // [kPix][32]
+  SweepTapParams* s_par = reinterpret_cast<SweepTapParams*>(s_ref + kPix * 32);          // [2][kGroup][kPix]
+  float* s_kd = reinterpret_cast<float*>(s_par + 2 * kGroup * kPix);                     // [M][D][4]  Kt / depth_i
+  float* s_G = s_kd + p.M * p.D * 4;                                                     // [M][12]
+  float* s_out = s_G + kMaxMeas * 12;                                                    // [kPix][D]
   __shared__ __align__(8) unsigned long long s_bar;
 
   const int tid = threadIdx.x;
@@ -176,6 +177,11 @@ __global__ void __launch_bounds__(kSweepThreads, 3) plane_sweep_c32_kernel(Sweep
     for (int k = 0; k < 3; ++k) s_kd[i * 4 + k] = s_G[m * 12 + 9 + k] / this_depth;   // utils.py:68
   }
   __syncthreads();
+
+  const float sx = (float)(p.w - 1) / (float)p.w, sy = (float)(p.h - 1) / (float)p.h;   // the align_corners "shrink" (App. A.1)
+  const int n_groups = (p.D + kGroup - 1) / kGroup;
+  const int n_steps = n_groups * p.M;                     // step = (plane group, measurement frame), frame fastest
+  sweep_phase_a(p, s_G, s_kd, s_par, 0, 0, u0, v, npix, sx, sy);
   {  // wait for the TMA bytes
     uint32_t done = 0;
     while (!done) {
@@ -186,39 +192,74 @@ __global__ void __launch_bounds__(kSweepThreads, 3) plane_sweep_c32_kernel(Sweep
           : "memory");
     }
   }
+  __syncthreads();
 
   const int lane = tid & 31, warp = tid >> 5;
-  const int sub = lane & 7;        // channel group: channels sub*4 .. sub*4+3
+  const int sub = lane & 7;                 // channel group: channels sub*4 .. sub*4+3
   const int pix = warp * 4 + (lane >> 3);
   const bool active = pix < npix;
-  const float sx = (float)(p.w - 1) / (float)p.w, sy = (float)(p.h - 1) / (float)p.h;   // the align_corners "shrink" (App. A.1)
-  const float inv_C = 1.f / 32.f;
-  const float uf = (float)(u0 + pix), vf = (float)v;
   const float4 f1 = *reinterpret_cast<const float4*>(s_ref + (active ? pix : 0) * 32 + sub * 4);
   const size_t img_off = (size_t)b * p.h * p.w * 32 + sub * 4;
-  const float inv_M = 1.f;
-  (void)inv_M;
+  const float scale = (p.mode == DVMVS_SWEEP_DOT) ? (1.f / 32.f) : 1.f;     // utils.py:82 (/C) vs :84
 
-  // walk the planes two at a time (both samples' taps in flight before either is reduced)
-  for (int d = 0; d < p.D; d += 2) {
-    const bool has2 = d + 1 < p.D;
-    float acc0 = 0.f, acc1 = 0.f;
-    for (int m = 0; m < p.M; ++m) {
-      const float* img = p.meas[m] + img_off;
-      const float* G = s_G + m * 12;
-      SweepTap ta, tb;
-      sweep_fetch(img, G, s_kd + (m * p.D + d) * 4, uf, vf, sx, sy, p.w, p.h, active, ta);
-      sweep_fetch(img, G, s_kd + (m * p.D + (has2 ? d + 1 : d)) * 4, uf, vf, sx, sy, p.w, p.h, active && has2, tb);
-      const float pa = sweep_reduce(ta, f1, p.mode), pb = sweep_reduce(tb, f1, p.mode);
-      acc0 += (p.mode == DVMVS_SWEEP_DOT) ? pa * inv_C : pa;              // utils.py:82 / :84
-      acc1 += (p.mode == DVMVS_SWEEP_DOT) ? pb * inv_C : pb;
+  float acc[kGroup];
+#pragma unroll
+  for (int k = 0; k < kGroup; ++k) acc[k] = 0.f;
+
+  for (int step = 0; step < n_steps; ++step) {
+    const int g = step / p.M, m = step - g * p.M;
+    if (step + 1 < n_steps) {
+      const int g1 = (step + 1) / p.M, m1 = (step + 1) - g1 * p.M;
+      sweep_phase_a(p, s_G, s_kd, s_par + ((step + 1) & 1) * kGroup * kPix, m1, g1 * kGroup, u0, v, npix, sx, sy);
     }
-    if (active && sub == 0) {
-      s_out[pix * p.D + d] = acc0 / (float)p.M;                           // utils.py:105-106
-      if (has2) s_out[pix * p.D + d + 1] = acc1 / (float)p.M;
+    const SweepTapParams* par = s_par + (step & 1) * kGroup * kPix + (active ? pix : 0);
+    const float* img = p.meas[m] + img_off;
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) {
+      const int4 off = *reinterpret_cast<const int4*>(par[k * kPix].off);
+      const float4 wt = *reinterpret_cast<const float4*>(par[k * kPix].w);
+      const float4 t00 = __ldg(reinterpret_cast<const float4*>(img + off.x));
+      const float4 t01 = __ldg(reinterpret_cast<const float4*>(img + off.y));
+      const float4 t10 = __ldg(reinterpret_cast<const float4*>(img + off.z));
+      const float4 t11 = __ldg(reinterpret_cast<const float4*>(img + off.w));
+      float4 ws;
+      ws.x = fmaf(t11.x, wt.w, fmaf(t10.x, wt.z, fmaf(t01.x, wt.y, t00.x * wt.x)));
+      ws.y = fmaf(t11.y, wt.w, fmaf(t10.y, wt.z, fmaf(t01.y, wt.y, t00.y * wt.x)));
+      ws.z = fmaf(t11.z, wt.w, fmaf(t10.z, wt.z, fmaf(t01.z, wt.y, t00.z * wt.x)));
+      ws.w = fmaf(t11.w, wt.w, fmaf(t10.w, wt.z, fmaf(t01.w, wt.y, t00.w * wt.x)));
+      float part;
+      if (p.mode == DVMVS_SWEEP_DOT)
+        part = fmaf(f1.w, ws.w, fmaf(f1.z, ws.z, fmaf(f1.y, ws.y, f1.x * ws.x)));
+      else
+        part = fabsf(f1.x - ws.x) + fabsf(f1.y - ws.y) + fabsf(f1.z - ws.z) + fabsf(f1.w - ws.w);
+      acc[k] = fmaf(part, scale, acc[k]);
     }
+    if (m == p.M - 1) {
+      // transposing butterfly over the 8 lanes of the quarter warp: lane `sub` ends up with the sum for plane `sub`
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float send = (sub & 4) ? acc[k] : acc[k + 4];
+        const float keep = (sub & 4) ? acc[k + 4] : acc[k];
+        acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float send = (sub & 2) ? acc[k] : acc[k + 2];
+        const float keep = (sub & 2) ? acc[k + 2] : acc[k];
+        acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      {
+        const float send = (sub & 1) ? acc[0] : acc[1];
+        const float keep = (sub & 1) ? acc[1] : acc[0];
+        acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      const int d = g * kGroup + sub;
+      if (active && d < p.D) s_out[pix * p.D + d] = acc[0] / (float)p.M;     // utils.py:105-106
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k) acc[k] = 0.f;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // coalesced write-out: [npix][D] is contiguous in the channel-last cost volume
   float* o = p.out + (((size_t)b * p.h + v) * p.w + u0) * p.D;
   const int n_items = npix * p.D;
@@ -428,7 +469,7 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
   for (int m = 0; m < M && fast; ++m) fast = ((uintptr_t)meas_host[m] % 16 == 0);
   if (fast) {
     const int tiles = B * h * ((w + kPix - 1) / kPix);
-    const size_t smem = (size_t)(kPix * 32 + M * D * 4 + kMaxMeas * 12 + kPix * D) * sizeof(float);
+    const size_t smem = (size_t)(kPix * 32 + M * D * 4 + kMaxMeas * 12 + kPix * D) * sizeof(float) + 2 * kGroup * kPix * sizeof(SweepTapParams);
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(plane_sweep_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
