@@ -87,6 +87,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ----------------------------------------------------------------------------------------------- parameters
 constexpr int kTcThreads = 192;
 constexpr int kTileM = 128;
@@ -250,85 +260,78 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     tc_fence_after();
     const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
     const size_t plane_stride = (size_t)p.B * p.Hout * p.Wout * p.Cout;
-    if (p.ksplit > 1) {
-      // ---- split-K: publish this tap range's partial sums (128 contiguous bytes per thread and 32 columns);
-      // conv_tc_finish_kernel reduces the splits in fixed order (deterministic) and applies the epilogue.
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        if (!valid) continue;
-        float* wsp = p.workspace + (size_t)blockIdx.z * plane_stride + pix * p.Cout + n0 + c0;
-        if (((p.Cout & 3) == 0) && (n0 + c0 + 32 <= p.Cout)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(wsp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.Cout) wsp[j] = v[j];
-        }
-      }
+    const bool split = p.ksplit > 1;
+    float* wsp_row = split ? p.workspace + (size_t)blockIdx.z * plane_stride + pix * p.Cout : nullptr;
+    const float* res_row = nullptr;
+    if (p.residual_mode == DVMVS_RES_SAME) {
+      res_row = p.residual + pix * p.Cout;
+    } else if (p.residual_mode == DVMVS_RES_NEAREST_UP) {
+      const int ry = (int)(((long long)oy * p.Hr) / p.Hout), rx = (int)(((long long)ox * p.Wr) / p.Wout);
+      res_row = p.residual + (((size_t)b * p.Hr + ry) * p.Wr + rx) * p.Cout;
     }
-    const bool is_last = (p.ksplit == 1);
-    if (is_last) {
+    const bool vec8 = (p.Cout & 7) == 0;
+    // compact, rolled epilogue (8 accumulator columns per iteration): keeps the kernel's code footprint small -- these
+    // kernels are short, an unrolled 32-column epilogue costs more in instruction fetch than it saves in issue slots
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        if (!valid) continue;
-        const int cbase = n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = cbase + j;
-          if (c < p.Cout) {
-            float x = v[j];
-            if (p.bias) x += __ldg(p.bias + c);
-            if (p.residual_mode == DVMVS_RES_SAME) {
-              x += __ldg(p.residual + pix * p.Cout + c);
-            } else if (p.residual_mode == DVMVS_RES_NEAREST_UP) {
-              const int ry = (int)(((long long)oy * p.Hr) / p.Hout), rx = (int)(((long long)ox * p.Wr) / p.Wout);
-              x += __ldg(p.residual + (((size_t)b * p.Hr + ry) * p.Wr + rx) * p.Cout + c);
-            }
-            v[j] = tc_act(x, p.act);
-          }
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
+      float v[8];
+      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      const int cbase = n0 + c0;
+      if (!valid || cbase >= p.Cout) continue;
+      if (vec8) {
+        if (split) {   // partial sums of this tap range; conv_tc_finish_kernel reduces the splits in fixed order
+          *reinterpret_cast<float4*>(wsp_row + cbase) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(wsp_row + cbase + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          continue;
         }
-        const bool vec = ((p.Cout & 7) == 0) && (cbase + 32 <= p.Cout);
+        if (p.bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (res_row) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(res_row + cbase)), r1 = __ldg(reinterpret_cast<const float4*>(res_row + cbase + 4));
+          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = tc_act(v[e], p.act);
         if (p.out_f32) {
           float* o = p.out_f32 + pix * p.Cout + cbase;
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.Cout) o[j] = v[j];
-          }
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
         if (p.aux_out) {
-          for (int j = 0; j < 32; ++j)
-            if (cbase + j < p.Cout) p.aux_out[pix * p.Cout + cbase + j] = 1.f / (p.aux_mult * v[j] + p.aux_base);
+          float* o = p.aux_out + pix * p.Cout + cbase;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = 1.f / (p.aux_mult * v[e] + p.aux_base);
         }
         if (p.out_planes) {
+          __align__(16) __half hi[8];
+          __align__(16) __half lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            hi[e] = __float2half_rn(v[e]);
+            lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+          }
           __half* oh = p.out_planes + pix * p.Cout + cbase;
-          __half* ol = oh + plane_stride;
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __align__(16) __half hi[8];
-              __align__(16) __half lo[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                hi[e] = __float2half_rn(v[j + e]);
-                lo[e] = __float2half_rn(v[j + e] - __half2float(hi[e]));
-              }
-              *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(hi);
-              *reinterpret_cast<uint4*>(ol + j) = *reinterpret_cast<const uint4*>(lo);
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.Cout) {
-                const __half h = __float2half_rn(v[j]);
-                oh[j] = h;
-                ol[j] = __float2half_rn(v[j] - __half2float(h));
-              }
+          *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(hi);
+          *reinterpret_cast<uint4*>(oh + plane_stride) = *reinterpret_cast<const uint4*>(lo);
+        }
+      } else {        // generic tail (Cout not a multiple of 8): scalar, rolled
+#pragma unroll 1
+        for (int e = 0; e < 8; ++e) {
+          const int c = cbase + e;
+          if (c >= p.Cout) break;
+          float x = v[e];
+          if (split) { wsp_row[c] = x; continue; }
+          if (p.bias) x += __ldg(p.bias + c);
+          if (res_row) x += __ldg(res_row + c);
+          x = tc_act(x, p.act);
+          if (p.out_f32) p.out_f32[pix * p.Cout + c] = x;
+          if (p.aux_out) p.aux_out[pix * p.Cout + c] = 1.f / (p.aux_mult * x + p.aux_base);
+          if (p.out_planes) {
+            const __half h = __float2half_rn(x);
+            p.out_planes[pix * p.Cout + c] = h;
+            p.out_planes[plane_stride + pix * p.Cout + c] = __float2half_rn(x - __half2float(h));
           }
         }
       }

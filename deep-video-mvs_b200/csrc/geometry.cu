@@ -90,6 +90,9 @@ struct __align__(16) SweepTapParams {
   int off[4];     // element offsets of the 4 taps inside one measurement feature map (channel 0)
   float w[4];     // bilinear weights, 0 for taps outside the image
 };
+// The two 16-byte halves of entry e are stored at chunk slots 2e + (c ^ ((e >> 2) & 1)): eight consecutive threads
+// then hit eight different 4-bank groups (conflict-free STS.128); readers apply the same swizzle.
+__device__ __forceinline__ int sweep_chunk(int e, int c) { return 2 * e + (c ^ ((e >> 2) & 1)); }
 
 __device__ __forceinline__ void sweep_phase_a(const SweepParams& p, const float* s_G, const float* s_kd, SweepTapParams* buf, int m,
                                               int d0, int u0, int v, int npix, float sx, float sy) {
@@ -123,10 +126,13 @@ __device__ __forceinline__ void sweep_phase_a(const SweepParams& p, const float*
     t.w[2] = (vy1 && vx0) ? gx * fy : 0.f;
     t.w[3] = (vy1 && vx1) ? fx * fy : 0.f;
   }
-  buf[pl * kPix + pix] = t;
+  int4* chunks = reinterpret_cast<int4*>(buf);
+  const int e = pl * kPix + pix;
+  chunks[sweep_chunk(e, 0)] = *reinterpret_cast<const int4*>(t.off);
+  chunks[sweep_chunk(e, 1)] = *reinterpret_cast<const int4*>(t.w);
 }
 
-__global__ void __launch_bounds__(kSweepThreads, 3) plane_sweep_c32_kernel(SweepParams p) {
+__global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(SweepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_ref = reinterpret_cast<float*>(smem_raw);                                     // [kPix][32]
   SweepTapParams* s_par = reinterpret_cast<SweepTapParams*>(s_ref + kPix * 32);          // [2][kGroup][kPix]
@@ -212,12 +218,14 @@ __global__ void __launch_bounds__(kSweepThreads, 3) plane_sweep_c32_kernel(Sweep
       const int g1 = (step + 1) / p.M, m1 = (step + 1) - g1 * p.M;
       sweep_phase_a(p, s_G, s_kd, s_par + ((step + 1) & 1) * kGroup * kPix, m1, g1 * kGroup, u0, v, npix, sx, sy);
     }
-    const SweepTapParams* par = s_par + (step & 1) * kGroup * kPix + (active ? pix : 0);
+    const int4* par = reinterpret_cast<const int4*>(s_par + (step & 1) * kGroup * kPix);
+    const int e0 = active ? pix : 0;
     const float* img = p.meas[m] + img_off;
 #pragma unroll
     for (int k = 0; k < kGroup; ++k) {
-      const int4 off = *reinterpret_cast<const int4*>(par[k * kPix].off);
-      const float4 wt = *reinterpret_cast<const float4*>(par[k * kPix].w);
+      const int e = k * kPix + e0;
+      const int4 off = par[sweep_chunk(e, 0)];
+      const float4 wt = *reinterpret_cast<const float4*>(&par[sweep_chunk(e, 1)]);
       const float4 t00 = __ldg(reinterpret_cast<const float4*>(img + off.x));
       const float4 t01 = __ldg(reinterpret_cast<const float4*>(img + off.y));
       const float4 t10 = __ldg(reinterpret_cast<const float4*>(img + off.z));
