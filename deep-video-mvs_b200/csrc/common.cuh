@@ -22,6 +22,33 @@ inline int check_launch(const char* what) {
   return DVMVS_OK;
 }
 
+// ---- programmatic dependent launch (PDL): every kernel of the library is launched with the programmatic-stream-
+// serialization attribute, calls pdl_launch_dependents() first thing (the next kernel's CTAs may be scheduled as soon
+// as all of ours are resident) and pdl_wait() before its first access to global memory (blocks until the preceding
+// grid has completed and flushed).  Launch latency and per-kernel prologues (barrier init, TMEM allocation, tensor-map
+// prefetch) thereby overlap the predecessor's tail; also inside captured CUDA graphs.  DVMVS_PDL=0 disables it.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 #define DVMVS_REQUIRE(cond, ...)        \
   do {                                  \
     if (!(cond)) {                      \

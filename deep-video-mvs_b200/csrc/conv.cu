@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(kConvThreads) conv2d_direct_kernel(ConvParams 
   float* s_in = smem;                    // [CK][PLANE]
   float* s_w = smem + CK * PLANE;        // [KS*KS][CK][TN]
 
+  pdl_launch_dependents();
+  pdl_wait();
   const dvmvs_conv_desc& d = p.d;
   const int tid = threadIdx.x;
   const int tx = tid & 7, ty = tid >> 3;
@@ -186,6 +188,8 @@ __global__ void __launch_bounds__(kConvThreads) conv2d_direct_kernel(ConvParams 
 
 // bias / residual / activation pass for split-K launches (in place on the accumulated sums)
 __global__ void conv_epilogue_kernel(ConvParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const dvmvs_conv_desc& d = p.d;
   const size_t total = (size_t)d.B * p.Hout * p.Wout * d.Cout;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,6 +210,8 @@ __global__ void conv_epilogue_kernel(ConvParams p) {
 
 // Single-output-channel 3x3 head (depth_layer_3x3): a quarter warp per output pixel, 128-byte channel reads.
 __global__ void __launch_bounds__(256) conv_head_kernel(ConvParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const dvmvs_conv_desc& d = p.d;
   const int lane = threadIdx.x & 31;
   const int sub = lane & 7, quad = lane >> 3;
@@ -258,7 +264,7 @@ static int launch_conv(const ConvParams& p, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(p.tiles_x * p.tiles_y, (p.d.Cout + TN - 1) / TN, p.d.B * p.ksplit);
-  conv2d_direct_kernel<KS, STRIDE><<<grid, kConvThreads, smem, s>>>(p);
+  launch_k(conv2d_direct_kernel<KS, STRIDE>, grid, dim3(kConvThreads), smem, s, p);
   return check_launch("conv2d_direct_kernel");
 }
 
@@ -268,6 +274,8 @@ static int launch_conv(const ConvParams& p, cudaStream_t s) {
 __global__ void dwconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                               float* __restrict__ y, __half* __restrict__ planes, int B, int H, int W, int C, int Hout, int Wout,
                               int ks, int stride, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c4n = C >> 2;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * Hout * Wout * c4n;
@@ -315,6 +323,8 @@ __global__ void dwconv_kernel(const float* __restrict__ x, const float* __restri
 // x2 bilinear upsampling (align_corners=True)
 // =====================================================================================================
 __global__ void upsample2x_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = 2 * H, Wo = 2 * W;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * Ho * Wo * C;
@@ -340,6 +350,8 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, float* __restrict
 // Layout: per batch, transpose the [R][Cc] matrix to [Cc][R] through a 32x33 shared tile
 // =====================================================================================================
 __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int Cc) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const size_t boff = (size_t)blockIdx.z * R * Cc;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -364,6 +376,8 @@ constexpr int kLstmWarps = 8;
 
 __global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float* __restrict__ gates, const float* __restrict__ c_in,
                                                                      float* __restrict__ h_out, float* __restrict__ c_out, int hw, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];           // [hw][32] values + reduction scratch
   float* s_val = sm;
   float* s_red = sm + (size_t)hw * 32;    // [kLstmWarps][32]
@@ -459,7 +473,7 @@ extern "C" int dvmvs_conv2d(const dvmvs_conv_desc* desc, dvmvs_stream_t stream) 
     p.ksplit = 1;
     const size_t npix = (size_t)d.B * p.Hout * p.Wout;
     const unsigned blocks = (unsigned)((npix + 31) / 32);   // 8 warps x 4 pixels
-    conv_head_kernel<<<blocks, 256, 0, s>>>(p);
+    launch_k(conv_head_kernel, dim3(blocks), dim3(256), 0, s, p);
     return check_launch("conv_head_kernel");
   }
 
@@ -485,7 +499,7 @@ extern "C" int dvmvs_conv2d(const dvmvs_conv_desc* desc, dvmvs_stream_t stream) 
   if (rc != DVMVS_OK) return rc;
   if (p.ksplit > 1) {
     const size_t total = (size_t)d.B * p.Hout * p.Wout * d.Cout;
-    conv_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+    launch_k(conv_epilogue_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, p);
     return check_launch("conv_epilogue_kernel");
   }
   return DVMVS_OK;
@@ -504,8 +518,8 @@ extern "C" int dvmvs_dwconv2d(const float* x, const float* weight, const float* 
   const int pad = ksize / 2;
   const int Hout = (H + 2 * pad - ksize) / stride + 1, Wout = (W + 2 * pad - ksize) / stride + 1;
   const size_t total = (size_t)B * Hout * Wout * (C / 4);
-  dwconv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, weight, bias, y, (__half*)y_planes, B, H, W, C, Hout,
-                                                                                 Wout, ksize, stride, act);
+  launch_k(dwconv_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, x, weight, bias, y, (__half*)y_planes,
+           B, H, W, C, Hout, Wout, ksize, stride, act);
   return check_launch("dwconv_kernel");
 }
 
@@ -522,20 +536,20 @@ extern "C" int dvmvs_lstm_gates(const float* gates, const float* c_in, float* h_
     attr_set = true;
   }
   dim3 grid(C / 32, B);
-  lstm_gates_kernel<<<grid, 32 * kLstmWarps, smem, (cudaStream_t)stream>>>(gates, c_in, h_out, c_out, hw, C);
+  launch_k(lstm_gates_kernel, grid, dim3(32 * kLstmWarps), smem, (cudaStream_t)stream, gates, c_in, h_out, c_out, hw, C);
   return check_launch("lstm_gates_kernel");
 }
 
 extern "C" int dvmvs_upsample2x(const float* x, float* y, int B, int H, int W, int C, dvmvs_stream_t stream) {
   DVMVS_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0, "upsample2x: bad argument");
   const size_t total = (size_t)B * 4 * H * W * C;
-  upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C);
+  launch_k(upsample2x_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, y, B, H, W, C);
   return check_launch("upsample2x_kernel");
 }
 
 static int launch_transpose(const float* x, float* y, int B, int R, int Cc, cudaStream_t s) {
   dim3 grid((Cc + 31) / 32, (R + 31) / 32, B), block(32, 8);
-  transpose_kernel<<<grid, block, 0, s>>>(x, y, R, Cc);
+  launch_k(transpose_kernel, grid, block, 0, s, x, y, R, Cc);
   return check_launch("transpose_kernel");
 }
 

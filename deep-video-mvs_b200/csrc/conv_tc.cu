@@ -141,6 +141,7 @@ struct TcCfg {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_constant__ TcParams p) {
   using Cfg = TcCfg<BLOCK_N>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above touched only this CTA's smem / TMEM; global reads (TMA) and writes start below
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
@@ -349,6 +351,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
 // finishing pass for split-K launches: sum the per-split partials in split order, bias / residual / activation,
 // fp32 and / or fp16-pair stores
 __global__ void conv_tc_finish_kernel(TcParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = (size_t)p.B * p.Hout * p.Wout * p.Cout;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -380,6 +384,8 @@ __global__ void conv_tc_finish_kernel(TcParams p) {
 // (align_corners) upsampling on the way (materialises F.interpolate for the TMA-fed consumer).
 __global__ void split_planes_kernel(const float* __restrict__ x, __half* __restrict__ planes, int B, int H, int W, int C, int Cs,
                                     int upsample, int c_offset, int c_cover) {
+  pdl_launch_dependents();
+  pdl_wait();
   // writes channels [c_offset, c_offset + c_cover) of the Cs-channel plane tensor: x for the first C of them, zeros after
   const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
   const size_t total = (size_t)B * Ho * Wo * Cs;
@@ -480,7 +486,7 @@ static int launch_tc(TcParams& p, dim3 grid, int kc_max, cudaStream_t s) {
   stages = max(2, min(kMaxStages, stages));
   p.num_stages = stages;
   const int smem = stages * p.stage_bytes + overhead;
-  conv_tc_kernel<BLOCK_N><<<grid, kTcThreads, smem, s>>>(p);
+  launch_k(conv_tc_kernel<BLOCK_N>, grid, dim3(kTcThreads), (size_t)smem, s, p);
   return check_launch("conv_tc_kernel");
 }
 
@@ -568,7 +574,7 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   else rc = launch_tc<128>(p, grid, kc_max, s);
   if (rc != DVMVS_OK) return rc;
   if (p.ksplit > 1) {
-    conv_tc_finish_kernel<<<(unsigned)((out_elems + 255) / 256), 256, 0, s>>>(p);
+    launch_k(conv_tc_finish_kernel, dim3((unsigned)((out_elems + 255) / 256)), dim3(256), 0, s, p);
     return check_launch("conv_tc_finish_kernel");
   }
   return DVMVS_OK;
@@ -580,7 +586,7 @@ extern "C" int dvmvs_split_planes(const float* x, void* planes, int B, int H, in
   DVMVS_REQUIRE(c_offset >= 0 && c_cover >= C && c_offset + c_cover <= Cs, "split_planes: channel window [%d,+%d) outside %d", c_offset,
                 c_cover, Cs);
   const size_t total = (size_t)B * H * W * c_cover * (upsample2x ? 4 : 1);
-  split_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)planes, B, H, W, C, Cs, upsample2x,
-                                                                                   c_offset, c_cover);
+  launch_k(split_planes_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, (__half*)planes, B, H, W, C, Cs,
+           upsample2x, c_offset, c_cover);
   return check_launch("split_planes_kernel");
 }

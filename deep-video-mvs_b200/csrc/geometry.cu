@@ -6,6 +6,7 @@
 //   dvmvs/utils.py:205-258  warp_frame_depth            dvmvs/convlstm.py:30-41 (transformation, mask)
 //   dvmvs/utils.py:110-154  get_non_differentiable_rectangle_depth_estimation
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -23,6 +24,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVMVS_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // =====================================================================================================
 // Plane sweep
@@ -141,6 +150,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(Sweep
   float* s_out = s_G + kMaxMeas * 12;                                                    // [kPix][D]
   __shared__ __align__(8) unsigned long long s_bar;
 
+  pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int tiles_per_row = (p.w + kPix - 1) / kPix;
   const int tile = blockIdx.x;
@@ -158,6 +168,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(Sweep
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();
   if (tid == 0) {
     const uint32_t bytes = (uint32_t)npix * 32u * 4u;
     const float* src = p.ref + (((size_t)b * p.h + v) * p.w + u0) * 32;
@@ -276,6 +287,8 @@ __global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(Sweep
 
 // ---- generic path: any C, one thread per (pixel, plane); also the on-device cross-check of the fast path.
 __global__ void plane_sweep_generic_kernel(SweepParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)p.B * p.h * p.w * p.D;
   if (idx >= total) return;
@@ -327,6 +340,8 @@ __global__ void hidden_warp_kernel(const float* __restrict__ h_in, const float* 
                                    const float* __restrict__ prev_pose, const float* __restrict__ cur_pose,
                                    const float* __restrict__ K, float* __restrict__ h_out, int B, int C, int h, int w,
                                    float invalid_thresh) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_T[16];
   const int b = blockIdx.y;
   if (threadIdx.x == 0) {
@@ -389,6 +404,8 @@ __global__ void hidden_warp_kernel(const float* __restrict__ h_in, const float* 
 __global__ void depth_reproject_kernel(const float* __restrict__ cur_pose, const float* __restrict__ prev_pose,
                                        const float* __restrict__ prev_depth, const float* __restrict__ full_K,
                                        const float* __restrict__ half_K, unsigned int* __restrict__ out, int B, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_T[16];
   const int b = blockIdx.y;
   if (threadIdx.x == 0) {
@@ -484,11 +501,11 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
       attr_set = true;
     }
     DVMVS_REQUIRE(smem <= 96 * 1024, "plane_sweep: shared memory %zu too large", smem);
-    plane_sweep_c32_kernel<<<tiles, kSweepThreads, smem, s>>>(p);
+    launch_k(plane_sweep_c32_kernel, dim3(tiles), dim3(kSweepThreads), smem, s, p);
     return check_launch("plane_sweep_c32_kernel");
   }
   const size_t total = (size_t)B * h * w * D;
-  plane_sweep_generic_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(p);
+  launch_k(plane_sweep_generic_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, s, p);
   return check_launch("plane_sweep_generic_kernel");
 }
 
@@ -508,7 +525,7 @@ extern "C" int dvmvs_plane_sweep_generic(const float* ref, const float* const* m
   p.inv_step = (1.0 / (double)min_depth - 1.0 / (double)max_depth) / (double)(D - 1);
   p.mode = mode;
   const size_t total = (size_t)B * h * w * D;
-  plane_sweep_generic_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+  launch_k(plane_sweep_generic_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, p);
   return check_launch("plane_sweep_generic_kernel");
 }
 
@@ -520,7 +537,7 @@ extern "C" int dvmvs_hidden_warp(const float* h_in, const float* depth, const fl
   DVMVS_REQUIRE((uintptr_t)h_in % 16 == 0 && (uintptr_t)h_out % 16 == 0, "hidden_warp: pointers must be 16-byte aligned");
   const int n = h * w * (C / 4);
   dim3 grid((n + 127) / 128, B);
-  hidden_warp_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h_in, depth, prev_pose, cur_pose, K, h_out, B, C, h, w, invalid_thresh);
+  launch_k(hidden_warp_kernel, grid, dim3(128), 0, (cudaStream_t)stream, h_in, depth, prev_pose, cur_pose, K, h_out, B, C, h, w, invalid_thresh);
   return check_launch("hidden_warp_kernel");
 }
 
@@ -533,6 +550,6 @@ extern "C" int dvmvs_depth_reproject(const float* cur_pose, const float* prev_po
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * (H / 2) * (W / 2) * sizeof(float), s);
   if (e != cudaSuccess) { set_error("depth_reproject memset: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
   dim3 grid((H * W + 255) / 256, B);
-  depth_reproject_kernel<<<grid, 256, 0, s>>>(cur_pose, prev_pose, prev_depth, full_K, half_K, (unsigned int*)out, B, H, W);
+  launch_k(depth_reproject_kernel, grid, dim3(256), 0, s, cur_pose, prev_pose, prev_depth, full_K, half_K, (unsigned int*)out, B, H, W);
   return check_launch("depth_reproject_kernel");
 }
