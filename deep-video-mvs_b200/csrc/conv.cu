@@ -269,6 +269,54 @@ static int launch_conv(const ConvParams& p, cudaStream_t s) {
 }
 
 // =====================================================================================================
+// MnasNet stem: 3x3 stride-2 convolution of the (B,3,H,W) NCHW image straight to channel-last (B,H/2,W/2,32) with
+// folded BN + ReLU.  One thread per output pixel and 8 output channels (4 threads share a pixel); reads the image in
+// its native layout (no NCHW->NHWC pass), weights [3][3][3][32] broadcast from shared memory.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W,
+                                                        int Cout) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float s_w[27 * 32];
+  __shared__ float s_b[32];
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) s_w[i] = w[i];
+  if (threadIdx.x < Cout) s_b[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;      // k=3, pad=1, stride=2
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = (int)(idx & 3);
+  const size_t pix = idx >> 2;
+  if (pix >= (size_t)B * Ho * Wo) return;
+  const int ox = (int)(pix % Wo);
+  const int oy = (int)((pix / Wo) % Ho);
+  const int b = (int)(pix / ((size_t)Wo * Ho));
+  float acc[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = s_b[cg * 8 + n];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - 1 + ky;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 - 1 + kx;
+      if (ix < 0 || ix >= W) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = __ldg(img + (((size_t)b * 3 + c) * H + iy) * W + ix);
+        const float* wp = s_w + ((ky * 3 + kx) * 3 + c) * Cout + cg * 8;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) acc[n] = fmaf(v, wp[n], acc[n]);
+      }
+    }
+  }
+  float* o = y + pix * Cout + cg * 8;
+  *reinterpret_cast<float4*>(o) = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+  *reinterpret_cast<float4*>(o + 4) = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+}
+
+// =====================================================================================================
 // Depthwise convolution
 // =====================================================================================================
 __global__ void dwconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
@@ -503,6 +551,17 @@ extern "C" int dvmvs_conv2d(const dvmvs_conv_desc* desc, dvmvs_stream_t stream) 
     return check_launch("conv_epilogue_kernel");
   }
   return DVMVS_OK;
+}
+
+extern "C" int dvmvs_stem_conv(const float* image_nchw, const float* weight, const float* bias, float* y, int B, int H, int W,
+                               dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(image_nchw && weight && y && B > 0 && H > 1 && W > 1, "stem_conv: bad argument");
+  DVMVS_REQUIRE((uintptr_t)y % 16 == 0, "stem_conv: output must be 16-byte aligned");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const size_t threads = (size_t)B * Ho * Wo * 4;
+  launch_k(stem_conv_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, image_nchw, weight, bias, y, B,
+           H, W, 32);
+  return check_launch("stem_conv_kernel");
 }
 
 extern "C" int dvmvs_dwconv2d(const float* x, const float* weight, const float* bias, float* y, void* y_planes, int B, int H, int W,

@@ -172,7 +172,10 @@ class FeatureExtractor(NativeModule):
                 return ops.Act(None, ops.dwconv2d(t.f32, dw, want_f32=False, want_planes=True)[1])
             return ops.Act(ops.dwconv2d(t.f32, dw))
 
-        x = stem[0].run([(x, D)])
+        if image_nchw is not None:        # dedicated stem kernel reads the NCHW image directly (no layout pass)
+            x = ops.Act(ops.stem_conv(image_nchw, stem[0].pc))
+        else:
+            x = stem[0].run([(x, D)])
         x = depthwise(x, stem[1], stem[2])
         x = stem[2].run([(x, D)])
         outs = [x]
@@ -188,6 +191,9 @@ class FeatureExtractor(NativeModule):
         B, C, H, W = image.shape
         if C != 3 or H % 32 != 0 or W % 32 != 0:
             raise RuntimeError("FeatureExtractor: expected (B,3,H,W) with H, W multiples of 32, got %s" % (tuple(image.shape),))
+        ops.require_cuda_f32(image, "image")
+        if image.is_contiguous():
+            return tuple(ops.act_to_api(t) for t in self.run(None, image_nchw=image))
         return tuple(ops.act_to_api(t) for t in self.run(ops.to_act(image, "image")))
 
 

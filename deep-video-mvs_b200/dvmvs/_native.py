@@ -17,7 +17,7 @@ SWEEP_DOT, SWEEP_SAD = 0, 1
 # every symbol include/dvmvs_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "dvmvs_abi_version", "dvmvs_last_error_string", "dvmvs_kernel_launch_count", "dvmvs_plane_sweep_fused",
-    "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_split_planes", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
+    "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_split_planes", "dvmvs_stem_conv", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
     "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw",
 ]
 
@@ -70,6 +70,7 @@ def lib():
         L.dvmvs_conv2d.argtypes = [ctypes.POINTER(ConvDesc), p]
         L.dvmvs_conv2d_tc.argtypes = [ctypes.POINTER(ConvTcDesc), p]
         L.dvmvs_split_planes.argtypes = [p, p, i, i, i, i, i, i, i, i, p]
+        L.dvmvs_stem_conv.argtypes = [p, p, p, p, i, i, i, p]
         L.dvmvs_dwconv2d.argtypes = [p, p, p, p, p, i, i, i, i, i, i, i, p]
         L.dvmvs_lstm_gates.argtypes = [p, p, p, p, i, i, i, i, p]
         L.dvmvs_upsample2x.argtypes = [p, p, i, i, i, i, p]

@@ -146,6 +146,15 @@ def conv2d(sources, pc, residual=None, residual_mode=N.RES_NONE, aux=None):
     return (out, aux_out) if aux is not None else out
 
 
+def stem_conv(image_nchw, pc):
+    """MnasNet stem on the NCHW image (contiguous) -> channel-last (B, H/2, W/2, 32)."""
+    B, C, H, W = image_nchw.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 32), dtype=torch.float32, device=image_nchw.device)
+    N.check(N.lib().dvmvs_stem_conv(image_nchw.data_ptr(), pc.weight.data_ptr(), pc.bias.data_ptr(), y.data_ptr(), B, H, W, _stream()),
+            "stem_conv")
+    return y
+
+
 def dwconv2d(x, pd, want_f32=True, want_planes=False):
     """Returns y (fp32) by default; with want_planes also / only the fp16-pair planes: (y or None, planes)."""
     B, H, W, C = x.shape

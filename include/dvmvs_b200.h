@@ -145,6 +145,12 @@ int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* desc_host, dvmvs_stream_t stream);
 int dvmvs_split_planes(const float* x, void* planes, int B, int H, int W, int C, int Cs, int upsample2x, int c_offset,
                        int c_cover, dvmvs_stream_t stream);
 
+/* MnasNet stem (torchvision mnasnet1_0 layers[0:3], fusionnet/model.py:125-127): 3x3 stride-2 pad-1 convolution 3 -> 32
+ * + folded BN + ReLU, reading the NCHW image [B][3][H][W] directly and writing channel-last [B][H/2][W/2][32].
+ * weight [3][3][3][32] (k, k, Cin, Cout), bias [32]. */
+int dvmvs_stem_conv(const float* image_nchw, const float* weight, const float* bias, float* y, int B, int H, int W,
+                    dvmvs_stream_t stream);
+
 /* Depthwise k x k convolution (MnasNet), folded-BN bias + optional ReLU.
  * x [B][H][W][C], weight [k][k][C], bias [C]; outputs (either or both): y fp32 [B][Hout][Wout][C],
  * y_planes fp16 (hi, lo) [2][B][Hout][Wout][C] for a tensor-core consumer. */
