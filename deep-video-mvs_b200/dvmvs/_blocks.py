@@ -164,7 +164,7 @@ class FeatureExtractor(NativeModule):
             levels.append(blocks)
         return stem, levels
 
-    def run(self, x):
+    def run(self, x, image_nchw=None):
         stem, levels = self.packed()
         def depthwise(t, dw, consumer):
             # the depthwise output feeds exactly one pointwise conv: hand it the operand format that conv reads

@@ -54,8 +54,26 @@ class ConvTcDesc(ctypes.Structure):
     ]
 
 
+DRYRUN = os.environ.get("DVMVS_DRYRUN") == "1"     # host-logic smoke tests only: kernels are not executed, results are garbage
+
+
+class _DryRunLib:
+    """Stands in for the shared library when DVMVS_DRYRUN=1: every entry point returns 0 without doing anything, so the
+    Python plumbing (shapes, descriptors, module wiring) can be exercised on a machine without a GPU.  Never used by the
+    product path."""
+
+    def __getattr__(self, name):
+        if name == "dvmvs_last_error_string":
+            return lambda: b"dry run"
+        if name == "dvmvs_kernel_launch_count":
+            return lambda: 0
+        return lambda *a, **k: 0
+
+
 def lib():
     global _lib
+    if _lib is None and DRYRUN:
+        _lib = _DryRunLib()
     if _lib is None:
         if not os.path.isfile(LIB_PATH):
             raise RuntimeError("dvmvs: %s not found -- build it with `python deep-video-mvs_b200/build_native.py` "

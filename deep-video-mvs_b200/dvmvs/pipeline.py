@@ -41,19 +41,14 @@ def build_modules(weights, device="cuda", n_depth_levels=64, pairnet=False):
     return mods
 
 
-def keyframe(mods, state, reference_image, reference_pose, measurement_images, measurement_poses, full_K,
-             min_depth=0.25, max_depth=20.0, n_depth_levels=64, batch_features=True):
-    """One keyframe for B independent clips (tensors batched on dim 0, all CUDA).  With 'lstm' in mods this is the
-    fusionnet loop body, without it the pairnet one.  Returns (depth (B,H,W), state).
-
-    batch_features=True runs FeatureExtractor + FeatureShrinker ONCE over the reference and the M measurement images
-    stacked on the batch axis (eval-mode BatchNorm: identical results, 1/(M+1) of the launches); False reproduces the
-    script's M+1 separate passes (run-testing.py:153-159)."""
-    B, _, H, W = reference_image.shape
-    device = reference_image.device
+def feature_stage(mods, reference_image, reference_pose, measurement_images, measurement_poses, full_K,
+                  min_depth=0.25, max_depth=20.0, n_depth_levels=64, batch_features=True):
+    """First half of a keyframe -- everything that does not depend on the recurrent state: FeatureExtractor +
+    FeatureShrinker on the reference and measurement images and the fused plane-sweep cost volume
+    (run-testing.py:153-171).  Returns (f2, f4, f8, f16, cost_volume, half_K)."""
+    B = reference_image.shape[0]
     half_K = full_K.clone()
     half_K[:, 0:2, :] = half_K[:, 0:2, :] / 2.0
-    warp_grid = None    # ignored by the fused kernel (kept in the signature for API compatibility)
     if batch_features and len(measurement_images) > 0:
         stacked = torch.cat([reference_image] + list(measurement_images), dim=0)
         a2, a4, a8, a16 = mods["fpn"](*mods["fe"](stacked))
@@ -66,8 +61,17 @@ def keyframe(mods, state, reference_image, reference_pose, measurement_images, m
             meas_half.append(half)
         f2, f4, f8, f16 = mods["fpn"](*mods["fe"](reference_image))
     cv = cost_volume_fusion(image1=f2, image2s=meas_half, pose1=reference_pose, pose2s=measurement_poses, K=half_K,
-                            warp_grid=warp_grid, min_depth=min_depth, max_depth=max_depth, n_depth_levels=n_depth_levels,
-                            device=device, dot_product=True)
+                            warp_grid=None, min_depth=min_depth, max_depth=max_depth, n_depth_levels=n_depth_levels,
+                            device=reference_image.device, dot_product=True)
+    return f2, f4, f8, f16, cv, half_K
+
+
+def recurrent_stage(mods, state, features, reference_image, reference_pose, full_K):
+    """Second half of a keyframe: cost-volume encoder, depth re-projection + ConvLSTM fusion (fusionnet only), decoder
+    (run-testing.py:173-202).  `features` is feature_stage()'s return value.  Returns (depth (B,H,W), state)."""
+    f2, f4, f8, f16, cv, half_K = features
+    B, _, H, W = reference_image.shape
+    device = reference_image.device
     s0, s1, s2, s3, bottom = mods["cve"](features_half=f2, features_quarter=f4, features_one_eight=f8,
                                          features_one_sixteen=f16, cost_volume=cv)
     if "lstm" in mods:
@@ -90,6 +94,19 @@ def keyframe(mods, state, reference_image, reference_pose, measurement_images, m
     state.previous_depth = pred.view(B, 1, H, W)
     state.previous_pose = reference_pose
     return pred, state
+
+
+def keyframe(mods, state, reference_image, reference_pose, measurement_images, measurement_poses, full_K,
+             min_depth=0.25, max_depth=20.0, n_depth_levels=64, batch_features=True):
+    """One keyframe for B independent clips (tensors batched on dim 0, all CUDA).  With 'lstm' in mods this is the
+    fusionnet loop body, without it the pairnet one.  Returns (depth (B,H,W), state).
+
+    batch_features=True runs FeatureExtractor + FeatureShrinker ONCE over the reference and the M measurement images
+    stacked on the batch axis (eval-mode BatchNorm: identical results, 1/(M+1) of the launches); False reproduces the
+    script's M+1 separate passes (run-testing.py:153-159)."""
+    feats = feature_stage(mods, reference_image, reference_pose, measurement_images, measurement_poses, full_K, min_depth,
+                          max_depth, n_depth_levels, batch_features)
+    return recurrent_stage(mods, state, feats, reference_image, reference_pose, full_K)
 
 
 class GraphedFusionnet:
@@ -186,3 +203,132 @@ class GraphedFusionnet:
         self._graphs[with_state].replay()
         self._has_state = True
         return self._out
+
+
+class PipelinedFusionnet:
+    """Throughput engine for ONE clip (or B clips batched): consecutive keyframes are software-pipelined over two CUDA
+    streams.  Stage A(t) = feature_stage (features + plane sweep: no dependence on the recurrent state) of keyframe t runs
+    concurrently with stage B(t-1) = recurrent_stage (encoder, ConvLSTM, decoder) of the previous keyframe; each stage is
+    a captured CUDA graph over double-buffered static tensors.  Results are identical to GraphedFusionnet / keyframe():
+    the per-keyframe dataflow is unchanged, only independent work of neighbouring keyframes overlaps.
+
+        eng = PipelinedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M)
+        for frame in stream:  eng.submit(*frame, out=pinned_host_tensor_or_None)
+        eng.synchronize()
+    """
+
+    def __init__(self, mods, batch, height, width, n_measurement_frames, min_depth=0.25, max_depth=20.0, n_depth_levels=64,
+                 device=None):
+        self.mods, self.B, self.H, self.W, self.M = mods, batch, height, width, n_measurement_frames
+        self.min_depth, self.max_depth, self.D = min_depth, max_depth, n_depth_levels
+        dev = device or next(mods["fe"].parameters()).device
+        self.device = dev
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.slots = []
+        for _ in range(2):
+            self.slots.append({"ref_image": z(batch, 3, height, width), "ref_pose": z(batch, 4, 4), "full_K": z(batch, 3, 3),
+                               "meas_images": [z(batch, 3, height, width) for _ in range(n_measurement_frames)],
+                               "meas_poses": [z(batch, 4, 4) for _ in range(n_measurement_frames)],
+                               "features": None, "depth": z(batch, height, width), "graph_a": None, "graph_b": {},
+                               "a_done": torch.cuda.Event(), "b_done": torch.cuda.Event()})
+        self.stream_a, self.stream_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self._static_state = None
+        self._has_state = False
+        self.t = 0
+        self.kernels_per_keyframe = 0
+
+    def reset(self):
+        self._has_state = False
+
+    # -- capture helpers ------------------------------------------------------------------------------------------
+    def _run_a(self, slot):
+        return feature_stage(self.mods, slot["ref_image"], slot["ref_pose"], slot["meas_images"], slot["meas_poses"], slot["full_K"],
+                             self.min_depth, self.max_depth, self.D)
+
+    def _run_b(self, slot, with_state):
+        st = KeyframeState()
+        if with_state:
+            h, c, pd, pp = self._static_state
+            st.lstm_state, st.previous_depth, st.previous_pose = (h, c), pd, pp
+        return recurrent_stage(self.mods, st, slot["features"], slot["ref_image"], slot["ref_pose"], slot["full_K"])
+
+    def _capture_a(self, slot):
+        from . import _native
+        with torch.cuda.stream(self.stream_a), torch.no_grad():
+            for _ in range(2):
+                self._run_a(slot)
+        self.stream_a.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = _native.launch_count()
+        with torch.no_grad(), torch.cuda.graph(g, stream=self.stream_a):
+            slot["features"] = self._run_a(slot)
+        self._kernels_a = _native.launch_count() - n0
+        slot["graph_a"] = g
+
+    def _capture_b(self, slot, with_state):
+        from . import _native
+        saved = [t.clone() for t in self._static_state] if self._static_state is not None else None
+        with torch.cuda.stream(self.stream_b), torch.no_grad():
+            for _ in range(2):
+                pred, st = self._run_b(slot, with_state)
+        self.stream_b.synchronize()
+        if self._static_state is None:
+            self._static_state = (st.lstm_state[0].clone(), st.lstm_state[1].clone(), st.previous_depth.clone(),
+                                  slot["ref_pose"].clone())
+        g = torch.cuda.CUDAGraph()
+        n0 = _native.launch_count()
+        with torch.no_grad(), torch.cuda.graph(g, stream=self.stream_b):
+            pred, st = self._run_b(slot, with_state)
+            h, c, pd, pp = self._static_state
+            slot["depth"].copy_(pred)
+            h.copy_(st.lstm_state[0])
+            c.copy_(st.lstm_state[1])
+            pd.copy_(st.previous_depth)
+            pp.copy_(slot["ref_pose"])
+        self._kernels_b = _native.launch_count() - n0
+        slot["graph_b"][with_state] = g
+        if saved is not None:
+            for dst, src in zip(self._static_state, saved):
+                dst.copy_(src)
+        torch.cuda.synchronize(self.device)
+
+    # -- steady state ----------------------------------------------------------------------------------------------
+    def submit(self, reference_image, reference_pose, measurement_images, measurement_poses, full_K, out=None):
+        """Enqueue keyframe t (inputs CPU-pinned or CUDA).  If `out` (pinned host or CUDA tensor (B,H,W)) is given the
+        depth is copied into it on the recurrent stream; otherwise read eng.depth_of(t) after synchronisation."""
+        slot = self.slots[self.t & 1]
+        with torch.cuda.stream(self.stream_a):
+            self.stream_a.wait_event(slot["b_done"])            # slot reuse: keyframe t-2's recurrent stage has consumed it
+            slot["ref_image"].copy_(reference_image, non_blocking=True)
+            slot["ref_pose"].copy_(reference_pose, non_blocking=True)
+            slot["full_K"].copy_(full_K, non_blocking=True)
+            for dst, src in zip(slot["meas_images"], measurement_images):
+                dst.copy_(src, non_blocking=True)
+            for dst, src in zip(slot["meas_poses"], measurement_poses):
+                dst.copy_(src, non_blocking=True)
+            if slot["graph_a"] is None:
+                self.stream_a.synchronize()
+                self._capture_a(slot)
+            slot["graph_a"].replay()
+            slot["a_done"].record(self.stream_a)
+        with_state = self._has_state
+        with torch.cuda.stream(self.stream_b):
+            self.stream_b.wait_event(slot["a_done"])
+            if with_state not in slot["graph_b"]:
+                torch.cuda.synchronize(self.device)
+                self._capture_b(slot, with_state)
+            slot["graph_b"][with_state].replay()
+            if out is not None:
+                out.copy_(slot["depth"], non_blocking=True)
+            slot["b_done"].record(self.stream_b)
+        self._has_state = True
+        self.kernels_per_keyframe = getattr(self, "_kernels_a", 0) + getattr(self, "_kernels_b", 0)
+        self.t += 1
+        return self.t - 1
+
+    def depth_of(self, t):
+        return self.slots[t & 1]["depth"]
+
+    def synchronize(self):
+        self.stream_a.synchronize()
+        self.stream_b.synchronize()

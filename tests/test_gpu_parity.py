@@ -333,10 +333,12 @@ def test_pipeline_keyframe_and_cuda_graph_engine_match_script_sequence(oracle, s
     H, W, D, M = 64, 96, 64, 2
     w = helpers.oracle_weights(oracle, synth, 11, n_depth_levels=D)
     mods = helpers.build_product_modules(w, n_depth_levels=D)
-    clip = synth.make_clip(5, 4, H, W, M)
+    clip = synth.make_clip(5, 6, H, W, M)
     K = _cuda(clip["K"])[None]
     st_a, st_b = helpers.ProductState(), pipeline.KeyframeState()
     eng = pipeline.GraphedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
+    pipe = pipeline.PipelinedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
+    expected, piped = [], []
     with torch.no_grad():
         for ref_i, meas_i in clip["frames"]:
             args = (_cuda(clip["images"][ref_i])[None], _cuda(clip["poses"][ref_i])[None], [_cuda(clip["images"][j])[None] for j in meas_i],
@@ -346,6 +348,13 @@ def test_pipeline_keyframe_and_cuda_graph_engine_match_script_sequence(oracle, s
             c = eng.step(*args)
             assert oracle.rel_l1_inverse_depth(b.cpu().numpy(), a.cpu().numpy()) <= 1e-6
             assert oracle.rel_l1_inverse_depth(c.cpu().numpy(), a.cpu().numpy()) <= 1e-6
+            expected.append(a.cpu().numpy())
+            out = torch.empty((1, H, W), dtype=torch.float32, device=DEV)
+            pipe.submit(*args, out=out)          # asynchronous: keyframe t+1's feature stage overlaps this one's recurrent stage
+            piped.append(out)
+        pipe.synchronize()
+    for e, got in zip(expected, piped):
+        assert oracle.rel_l1_inverse_depth(got.cpu().numpy(), e) <= 1e-6
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 backend
