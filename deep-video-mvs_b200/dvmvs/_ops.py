@@ -20,8 +20,10 @@ WORKSPACE_BYTES = 32 << 20
 
 
 def workspace(device):
-    """Per-device scratch for the deterministic split-K reductions of small-map convolutions (allocated once)."""
-    key = (device.type, device.index)
+    """Scratch for the deterministic split-K reductions of small-map convolutions: one buffer per (device, stream) --
+    kernels on different streams (the two stages of PipelinedFusionnet, or a user's own streams) may run concurrently
+    and must not share partial-sum storage.  Allocated once per stream."""
+    key = (device.type, device.index, 0 if N.DRYRUN else torch.cuda.current_stream(device).cuda_stream)
     ws = _WORKSPACE.get(key)
     if ws is None:
         # zero-initialised: its first 16 KiB hold the split-K arrival counters of conv_tc_kernel (self-cleaning)

@@ -132,6 +132,7 @@ class GraphedFusionnet:
         self.meas_poses = [z(batch, 4, 4) for _ in range(n_measurement_frames)]
         self.state = KeyframeState()
         self._graphs = {}
+        self._capture_stream = None
         self.kernels_per_replay = {}
         self._static_state = None     # (h, c, prev_depth, prev_pose) buffers the steady-state graph reads and rewrites
         self._out = None
@@ -160,19 +161,22 @@ class GraphedFusionnet:
 
     def _capture(self, with_state):
         # warm-up on a side stream (allocations, weight packing, function attributes), then capture
-        s = torch.cuda.Stream(device=self.device)
+        if self._capture_stream is None:
+            self._capture_stream = torch.cuda.Stream(device=self.device)
+        s = self._capture_stream        # same stream for warm-up and capture: per-stream scratch is allocated outside the graph
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s), torch.no_grad():
             for _ in range(2):
                 pred, st = self._body(with_state)
         torch.cuda.current_stream(self.device).wait_stream(s)
+        s.synchronize()
         if self._static_state is None:
             self._static_state = (st.lstm_state[0].clone(), st.lstm_state[1].clone(), st.previous_depth.clone(), self.ref_pose.clone())
             self._out = torch.empty_like(pred)
         from . import _native
         g = torch.cuda.CUDAGraph()
         n0 = _native.launch_count()
-        with torch.no_grad(), torch.cuda.graph(g):
+        with torch.no_grad(), torch.cuda.graph(g, stream=s):
             pred, st = self._body(with_state)
             self.kernels_per_replay[with_state] = _native.launch_count() - n0   # our kernels captured in this graph
             h, c, pd, pp = self._static_state
