@@ -1,0 +1,361 @@
+// Stride-1 k x k convolution on tcgen05 WITHOUT im2col amplification: "halo" implicit GEMM.  sm_100a.
+//
+// conv_tc_kernel (conv_tc.cu) re-loads the activation tile once per filter tap (25x for 5x5), one TMA row per pixel;
+// on the big 32-channel layers (refine, decoder block 4, aggregator0, FPN outputs) it is bound by the TMA request rate.
+// Here the activations are stored in a channel-BLOCKED fp16 layout  [plane][B][C/8][H][W][8]  ("NC8HW8"), so that
+//   * one TMA box {(8+k-1) pixels x 8 ch = one contiguous row, 16+k-1 rows, KC/8 channel blocks} brings the whole halo
+//     of an 8-wide x 16-high output tile into shared memory ONCE per KC-channel group, in rows of (8+k-1)*16 bytes;
+//   * in shared memory [channel block][halo y][halo x][8 ch] IS the canonical no-swizzle K-major UMMA layout: a core
+//     matrix = 8 x-consecutive pixels x 16 bytes, the next 8 GEMM rows (= next tile row) lie one halo row further
+//     (SBO), the next 8 channels one channel block further (LBO);
+//   * a filter tap (ky,kx) is just a different START ADDRESS of the same halo tile: (ky*halo_w + kx)*16 bytes.
+// So per KC channels the tile issues k*k*(KC/16) MMAs per term from one resident halo, and only the (tiny) per-tap
+// weight blocks stream through a ring (one bulk copy per filter row: all kx taps are contiguous in the packed weights).
+// Weights are pre-packed in exactly their shared-memory image [n-tile][k-group][ky][kx][KC/8][BLOCK_N][8].
+// The epilogue writes fp32 channel-last and/or the blocked fp16 pair planes (16 bytes per pixel and channel block,
+// coalesced over the 8 pixels of a tile row).
+//
+// Warp roles as in conv_tc_kernel: warp 0 = TMA / bulk-copy producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2-5 = epilogue.  fp16 (hi, lo) pairs, 3 terms (hi*hi + lo*hi + hi*lo) or 1 term.
+#include <string.h>
+
+#include "tc_ptx.cuh"
+
+namespace dvmvs {
+
+constexpr int kHaloThreads = 192;
+constexpr int kHaloTileW = 8, kHaloTileH = 16;
+constexpr int kHaloWStages = 4;
+
+struct HaloParams {
+  CUtensorMap a_map[3][2];     // [source][hi/lo]: 4-D {W*8, H, C8, B} over the blocked planes
+  const __half* w_hi;          // packed weights, see header comment
+  const __half* w_lo;
+  int src_groups[3];           // KC-channel groups per source
+  int n_src, terms, ksize, pad, kc;           // kc: channels per group (16 or 32)
+  int B, Hout, Wout, Cout, c8_out, tiles_x, tiles_y, n_groups;
+  const float* bias;
+  const float* residual;       // fp32 channel-last, same size (DVMVS_RES_SAME) or null
+  float* out_f32;              // [B][H][W][Cout] or null
+  __half* out_blk;             // [2][B][Cout/8][H][W][8] or null
+  __half* out_nhwc;            // [2][B][H][W][Cout] or null
+  int act;
+  uint32_t a_bytes, w_bytes;   // per plane: halo tile bytes of one group, weight bytes of one (group, ky) stage
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 127u) & ~127u;
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+  const int planes = p.terms > 1 ? 2 : 1;
+  // layout: A[2 buffers][planes][a_bytes] | W[kHaloWStages][planes][w_bytes] | barriers
+  const uint32_t a_buf_bytes = planes * p.a_bytes, w_stage_bytes = planes * p.w_bytes;
+  const uint32_t a_base = base, w_base = base + 2 * a_buf_bytes;
+  const uint32_t bars = w_base + kHaloWStages * w_stage_bytes;
+  auto a_full = [&](int i) { return bars + 8u * i; };
+  auto a_empty = [&](int i) { return bars + 8u * (2 + i); };
+  auto w_full = [&](int i) { return bars + 8u * (4 + i); };
+  auto w_empty = [&](int i) { return bars + 8u * (4 + kHaloWStages + i); };
+  const uint32_t tmem_full_bar = bars + 8u * (4 + 2 * kHaloWStages);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + (bars - base) + 8 * (5 + 2 * kHaloWStages));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int b = blockIdx.x / tiles_per_img;
+  const int t_in = blockIdx.x - b * tiles_per_img;
+  const int oy0 = (t_in / p.tiles_x) * kHaloTileH, ox0 = (t_in % p.tiles_x) * kHaloTileW;
+  const int nt = blockIdx.y, n0 = nt * BLOCK_N;
+  const int halo_w = kHaloTileW + p.ksize - 1, halo_h = kHaloTileH + p.ksize - 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_src; ++s) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map[s][0]) : "memory");
+      if (p.terms > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map[s][1]) : "memory");
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a_full(i), 1);
+      mbar_init(a_empty(i), 1);
+    }
+    for (int i = 0; i < kHaloWStages; ++i) {
+      mbar_init(w_full(i), 1);
+      mbar_init(w_empty(i), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ============================== producer ==============================
+    if (lane == 0) {
+      int g = 0, wst = 0;
+      uint32_t wphase = 0;
+      for (int s = 0; s < p.n_src; ++s) {
+        for (int cg = 0; cg < p.src_groups[s]; ++cg, ++g) {
+          const int ab = g & 1;
+          mbar_wait(a_empty(ab), ((g >> 1) & 1) ^ 1u);
+          mbar_expect_tx(a_full(ab), planes * p.a_bytes);
+          const uint32_t adst = a_base + ab * a_buf_bytes;
+          // box {halo_w*8 elements, halo_h rows, kc/8 channel blocks, 1}; out-of-image rows / columns are zero-filled
+          tma_load_4d(adst, &p.a_map[s][0], a_full(ab), (ox0 - p.pad) * 8, oy0 - p.pad, cg * (p.kc / 8), b);
+          if (p.terms > 1) tma_load_4d(adst + p.a_bytes, &p.a_map[s][1], a_full(ab), (ox0 - p.pad) * 8, oy0 - p.pad, cg * (p.kc / 8), b);
+          for (int ky = 0; ky < p.ksize; ++ky) {
+            mbar_wait(w_empty(wst), wphase ^ 1u);
+            mbar_expect_tx(w_full(wst), planes * p.w_bytes);
+            const size_t woff = ((((size_t)nt * p.n_groups + g) * p.ksize + ky) * (size_t)p.w_bytes) / sizeof(__half);
+            const uint32_t wdst = w_base + wst * w_stage_bytes;
+            bulk_load(wdst, p.w_hi + woff, p.w_bytes, w_full(wst));
+            if (p.terms > 1) bulk_load(wdst + p.w_bytes, p.w_lo + woff, p.w_bytes, w_full(wst));
+            if (++wst == kHaloWStages) { wst = 0; wphase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t a_chunk = (uint32_t)halo_h * halo_w * 16;       // bytes of one 8-channel block of the halo tile
+      const uint32_t a_sbo = (uint32_t)halo_w * 16;                  // next tile row (next 8 GEMM rows)
+      const uint32_t w_chunk = BLOCK_N * 16;                         // bytes of one 8-channel block of a weight tap
+      const uint32_t w_tap = (uint32_t)(p.kc / 8) * w_chunk;         // bytes of one tap's [kc/8][BLOCK_N][8] block
+      int g = 0, wst = 0;
+      uint32_t wphase = 0, accumulate = 0;
+      for (int s = 0; s < p.n_src; ++s) {
+        for (int cg = 0; cg < p.src_groups[s]; ++cg, ++g) {
+          const int ab = g & 1;
+          mbar_wait(a_full(ab), (g >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = a_base + ab * a_buf_bytes, a_lo = a_hi + p.a_bytes;
+          for (int ky = 0; ky < p.ksize; ++ky) {
+            mbar_wait(w_full(wst), wphase);
+            tc_fence_after();
+            const uint32_t w_hi = w_base + wst * w_stage_bytes, w_lo = w_hi + p.w_bytes;
+            for (int kx = 0; kx < p.ksize; ++kx) {
+              const uint32_t a_tap = (uint32_t)(ky * halo_w + kx) * 16;
+              for (int term = 0; term < p.terms; ++term) {
+                const uint32_t a_s = ((term == 1) ? a_lo : a_hi) + a_tap;
+                const uint32_t w_s = ((term == 2) ? w_lo : w_hi) + kx * w_tap;
+                for (int k2 = 0; k2 < p.kc / 16; ++k2) {
+                  tc_mma_f16(tmem_base, umma_desc_noswizzle(a_s + 2 * k2 * a_chunk, a_chunk, a_sbo),
+                             umma_desc_noswizzle(w_s + 2 * k2 * w_chunk, w_chunk, 128), idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+            }
+            tc_commit(w_empty(wst));
+            if (++wst == kHaloWStages) { wst = 0; wphase ^= 1u; }
+          }
+          tc_commit(a_empty(ab));
+        }
+      }
+      tc_commit(tmem_full_bar);
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ty = row >> 3, tx = row & 7;
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    const bool valid = (oy < p.Hout) && (ox < p.Wout);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
+    const size_t hw = (size_t)p.Hout * p.Wout;
+    const size_t plane_elems = (size_t)p.B * p.c8_out * hw * 8;
+    const size_t nhwc_plane = (size_t)p.B * hw * p.Cout;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
+      float v[8];
+      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      const int cbase = n0 + c0;
+      if (!valid || cbase >= p.Cout) continue;
+      if (p.bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (p.residual) {
+        const float* rr = p.residual + pix * p.Cout + cbase;
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rr)), r1 = __ldg(reinterpret_cast<const float4*>(rr + 4));
+        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = tc_act(v[e], p.act);
+      if (p.out_f32) {
+        float* o = p.out_f32 + pix * p.Cout + cbase;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      if (p.out_blk || p.out_nhwc) {
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          hi[e] = __float2half_rn(v[e]);
+          lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+        }
+        if (p.out_blk) {
+          __half* o = p.out_blk + (((size_t)b * p.c8_out + (cbase >> 3)) * hw + (size_t)oy * p.Wout + ox) * 8;
+          *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(hi);
+          *reinterpret_cast<uint4*>(o + plane_elems) = *reinterpret_cast<const uint4*>(lo);
+        }
+        if (p.out_nhwc) {
+          __half* o = p.out_nhwc + pix * p.Cout + cbase;
+          *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(hi);
+          *reinterpret_cast<uint4*>(o + nhwc_plane) = *reinterpret_cast<const uint4*>(lo);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// fp32 channel-last -> channels [c_offset, c_offset + c_cover) of the blocked fp16 pair planes [2][B][C8][H'][W'][8]
+// (the C values of x, then zeros); optional x2 bilinear (align_corners) upsampling on the way.
+__global__ void split_blocked_kernel(const float* __restrict__ x, __half* __restrict__ planes, int B, int H, int W, int C, int C8,
+                                     int upsample, int c_offset, int c_cover) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
+  const size_t total = (size_t)B * C8 * Ho * Wo * 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * Ho * Wo * c_cover) return;
+  // thread order: channel fastest within a pixel so that the fp32 reads are coalesced
+  const int c = (int)(idx % c_cover);
+  const size_t pix = idx / c_cover;
+  const int ox = (int)(pix % Wo);
+  const int oy = (int)((pix / Wo) % Ho);
+  const int b = (int)(pix / ((size_t)Wo * Ho));
+  float v = 0.f;
+  if (c < C) {
+    if (!upsample) {
+      v = x[pix * C + c];
+    } else {
+      const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+      const float sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+      const float fy = sh * oy, fx = sw * ox;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+      const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+      const float* bp = x + (size_t)b * H * W * C + c;
+      v = ly0 * (lx0 * bp[((size_t)y0 * W + x0) * C] + lx1 * bp[((size_t)y0 * W + x1) * C]) +
+          ly1 * (lx0 * bp[((size_t)y1 * W + x0) * C] + lx1 * bp[((size_t)y1 * W + x1) * C]);
+    }
+  }
+  const int cc = c_offset + c;
+  const size_t o = ((((size_t)b * C8 + (cc >> 3)) * Ho + oy) * Wo + ox) * 8 + (cc & 7);
+  const __half h = __float2half_rn(v);
+  planes[o] = h;
+  planes[total + o] = __float2half_rn(v - __half2float(h));
+}
+
+static int make_halo_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C8, int halo_w, int halo_h, int kc8) {
+  cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)C8, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)C8 * H * W * 16};
+  cuuint32_t box[4] = {(cuuint32_t)halo_w * 8, (cuuint32_t)halo_h, (cuuint32_t)kc8, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = tensor_map_encoder()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(blocked activation B=%d H=%d W=%d C8=%d halo %dx%d) failed: %d", B, H, W, C8, halo_w, halo_h, (int)r);
+    return DVMVS_EINVAL;
+  }
+  return DVMVS_OK;
+}
+
+template <int BLOCK_N>
+static int launch_halo(const HaloParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("conv_halo smem attribute: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
+    attr_set = true;
+  }
+  launch_k(conv_halo_kernel<BLOCK_N>, grid, dim3(kHaloThreads), smem, s, p);
+  return check_launch("conv_halo_kernel");
+}
+
+}  // namespace dvmvs
+
+using namespace dvmvs;
+
+extern "C" int dvmvs_conv2d_halo(const dvmvs_conv_halo_desc* d, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(d != nullptr, "conv2d_halo: null descriptor");
+  DVMVS_REQUIRE(tensor_map_encoder() != nullptr, "conv2d_halo: cuTensorMapEncodeTiled entry point not available");
+  DVMVS_REQUIRE(d->n_src >= 1 && d->n_src <= 3, "conv2d_halo: n_src=%d", d->n_src);
+  DVMVS_REQUIRE(d->ksize == 1 || d->ksize == 3 || d->ksize == 5, "conv2d_halo: ksize=%d", d->ksize);
+  DVMVS_REQUIRE(d->terms == 1 || d->terms == 3, "conv2d_halo: terms=%d", d->terms);
+  DVMVS_REQUIRE(d->kc == 16 || d->kc == 32, "conv2d_halo: kc=%d", d->kc);
+  DVMVS_REQUIRE(d->block_n == 32 || d->block_n == 64, "conv2d_halo: block_n=%d", d->block_n);
+  DVMVS_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cout > 0 && d->Cout % 8 == 0 && d->w_hi && (d->terms == 1 || d->w_lo),
+                "conv2d_halo: bad shape / null weights (Cout must be a multiple of 8)");
+  DVMVS_REQUIRE(d->out_f32 || d->out_blk || d->out_nhwc, "conv2d_halo: no output");
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.ksize = d->ksize; p.pad = (d->ksize - 1) / 2; p.terms = d->terms; p.kc = d->kc; p.n_src = d->n_src;
+  p.B = d->B; p.Hout = d->H; p.Wout = d->W; p.Cout = d->Cout; p.c8_out = d->Cout / 8;
+  p.tiles_x = (d->W + kHaloTileW - 1) / kHaloTileW;
+  p.tiles_y = (d->H + kHaloTileH - 1) / kHaloTileH;
+  const int halo_w = kHaloTileW + d->ksize - 1, halo_h = kHaloTileH + d->ksize - 1;
+  int n_groups = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    const int C8 = d->src_c8[s];
+    DVMVS_REQUIRE(d->src_blk[s] && C8 > 0, "conv2d_halo: source %d null / empty", s);
+    DVMVS_REQUIRE((uintptr_t)d->src_blk[s] % 16 == 0, "conv2d_halo: source %d not 16-byte aligned", s);
+    p.src_groups[s] = (C8 * 8 + d->kc - 1) / d->kc;
+    n_groups += p.src_groups[s];
+    const size_t plane = (size_t)d->B * C8 * d->H * d->W * 8;
+    int rc = make_halo_map(&p.a_map[s][0], d->src_blk[s], d->B, d->H, d->W, C8, halo_w, halo_h, d->kc / 8);
+    if (rc != DVMVS_OK) return rc;
+    if (d->terms > 1) {
+      rc = make_halo_map(&p.a_map[s][1], (const __half*)d->src_blk[s] + plane, d->B, d->H, d->W, C8, halo_w, halo_h, d->kc / 8);
+      if (rc != DVMVS_OK) return rc;
+    }
+  }
+  p.n_groups = n_groups;
+  DVMVS_REQUIRE(d->n_groups == n_groups, "conv2d_halo: weights packed for %d channel groups, sources give %d", d->n_groups, n_groups);
+  p.a_bytes = (uint32_t)(d->kc / 8) * halo_h * halo_w * 16;
+  p.w_bytes = (uint32_t)d->ksize * (d->kc / 8) * d->block_n * 16;
+  p.w_hi = (const __half*)d->w_hi; p.w_lo = (const __half*)d->w_lo;
+  p.bias = d->bias; p.residual = d->residual; p.act = d->act;
+  p.out_f32 = d->out_f32; p.out_blk = (__half*)d->out_blk; p.out_nhwc = (__half*)d->out_nhwc;
+  const int planes = d->terms > 1 ? 2 : 1;
+  const size_t smem = 2 * (size_t)planes * p.a_bytes + kHaloWStages * (size_t)planes * p.w_bytes + 256 + 128;
+  DVMVS_REQUIRE(smem <= 227 * 1024, "conv2d_halo: shared memory %zu too large", smem);
+  const int n_tiles = (d->Cout + d->block_n - 1) / d->block_n;
+  dim3 grid(p.tiles_x * p.tiles_y * d->B, n_tiles, 1);
+  if (d->block_n == 32) return launch_halo<32>(p, grid, smem, (cudaStream_t)stream);
+  return launch_halo<64>(p, grid, smem, (cudaStream_t)stream);
+}
+
+extern "C" int dvmvs_split_blocked(const float* x, void* planes, int B, int H, int W, int C, int C8, int upsample2x, int c_offset,
+                                   int c_cover, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(x && planes && B > 0 && H > 0 && W > 0 && C > 0 && C8 > 0, "split_blocked: bad argument");
+  DVMVS_REQUIRE(c_offset >= 0 && c_cover >= C && c_offset + c_cover <= C8 * 8, "split_blocked: channel window [%d,+%d) outside %d",
+                c_offset, c_cover, C8 * 8);
+  const size_t total = (size_t)B * H * W * c_cover * (upsample2x ? 4 : 1);
+  launch_k(split_blocked_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, (__half*)planes, B, H, W, C,
+           C8, upsample2x, c_offset, c_cover);
+  return check_launch("split_blocked_kernel");
+}

@@ -17,7 +17,7 @@ SWEEP_DOT, SWEEP_SAD = 0, 1
 # every symbol include/dvmvs_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "dvmvs_abi_version", "dvmvs_last_error_string", "dvmvs_kernel_launch_count", "dvmvs_plane_sweep_fused",
-    "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_split_planes", "dvmvs_stem_conv", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
+    "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_conv2d_halo", "dvmvs_split_blocked", "dvmvs_split_planes", "dvmvs_stem_conv", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
     "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw",
 ]
 
@@ -70,6 +70,19 @@ class _DryRunLib:
         return lambda *a, **k: 0
 
 
+class ConvHaloDesc(ctypes.Structure):
+    """mirror of dvmvs_conv_halo_desc"""
+    _fields_ = [
+        ("src_blk", ctypes.c_void_p * 3), ("src_c8", ctypes.c_int * 3), ("n_src", ctypes.c_int),
+        ("w_hi", ctypes.c_void_p), ("w_lo", ctypes.c_void_p),
+        ("n_groups", ctypes.c_int), ("kc", ctypes.c_int), ("block_n", ctypes.c_int), ("terms", ctypes.c_int),
+        ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+        ("out_f32", ctypes.c_void_p), ("out_blk", ctypes.c_void_p), ("out_nhwc", ctypes.c_void_p),
+        ("B", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cout", ctypes.c_int),
+        ("ksize", ctypes.c_int), ("act", ctypes.c_int),
+    ]
+
+
 def lib():
     global _lib
     if _lib is None and DRYRUN:
@@ -87,6 +100,8 @@ def lib():
         L.dvmvs_depth_reproject.argtypes = [p, p, p, p, p, p, i, i, i, p]
         L.dvmvs_conv2d.argtypes = [ctypes.POINTER(ConvDesc), p]
         L.dvmvs_conv2d_tc.argtypes = [ctypes.POINTER(ConvTcDesc), p]
+        L.dvmvs_conv2d_halo.argtypes = [ctypes.POINTER(ConvHaloDesc), p]
+        L.dvmvs_split_blocked.argtypes = [p, p, i, i, i, i, i, i, i, i, p]
         L.dvmvs_split_planes.argtypes = [p, p, i, i, i, i, i, i, i, i, p]
         L.dvmvs_stem_conv.argtypes = [p, p, p, p, i, i, i, p]
         L.dvmvs_dwconv2d.argtypes = [p, p, p, p, p, i, i, i, i, i, i, i, p]

@@ -372,12 +372,103 @@ def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, w
     return out_f32, out_planes
 
 
+# ================================================================================================ halo (blocked-layout) path
+def split_blocked(sources):
+    """sources: [(fp32 nhwc tensor, upsample)] -> blocked fp16 pair planes (2, B, C8, H', W', 8) of their channel
+    concatenation (torch.cat staged straight into the operand layout of conv_halo_kernel)."""
+    shapes = [(t.shape[1] * (2 if up else 1), t.shape[2] * (2 if up else 1)) for t, up in sources]
+    B, (Ho, Wo) = sources[0][0].shape[0], shapes[0]
+    if any(sh != (Ho, Wo) for sh in shapes):
+        raise ValueError("split_blocked: spatial sizes differ: %s" % (shapes,))
+    c_total = sum(t.shape[3] for t, _ in sources)
+    C8 = (c_total + 7) // 8
+    planes = torch.empty((2, B, C8, Ho, Wo, 8), dtype=torch.float16, device=sources[0][0].device)
+    off = 0
+    for i, (t, up) in enumerate(sources):
+        C = t.shape[3]
+        cover = C if i + 1 < len(sources) else C8 * 8 - off
+        N.check(N.lib().dvmvs_split_blocked(t.data_ptr(), planes.data_ptr(), B, t.shape[1], t.shape[2], C, C8, 1 if up else 0, off, cover,
+                                            _stream()), "split_blocked")
+        off += C
+    return planes
+
+
+class PackedConvHalo:
+    """Weights for dvmvs_conv2d_halo in their shared-memory image [n-tile][group][ky][kx][kc/8][block_n][8] (fp16 hi / lo)."""
+
+    def __init__(self, pc, src_channels, device, kc=None, block_n=None):
+        k, cin, cout = pc.ksize, pc.cin, pc.cout
+        assert sum(src_channels) == cin and pc.stride == 1
+        self.kc = kc or (16 if k == 5 else 32)
+        self.block_n = block_n or (32 if cout <= 32 else 64)
+        kc, bn = self.kc, self.block_n
+        w = pc.weight.detach().to("cpu", torch.float32)                    # [k][k][cin][cout]
+        n_tiles = (cout + bn - 1) // bn
+        groups = []                                                          # (cin offset, valid channels) per kc-group
+        self.src_c8 = []
+        off = 0
+        for cr in src_channels:
+            c8 = (cr + 7) // 8
+            self.src_c8.append(c8)
+            for cg in range((c8 * 8 + kc - 1) // kc):
+                lo_c = cg * kc
+                groups.append((off + lo_c, max(0, min(kc, cr - lo_c))))
+            off += cr
+        self.n_groups = len(groups)
+        packed = torch.zeros(n_tiles, self.n_groups, k, k, kc // 8, bn, 8, dtype=torch.float32)
+        for gi, (c0, nvalid) in enumerate(groups):
+            if nvalid == 0:
+                continue
+            blk = torch.zeros(k, k, kc, n_tiles * bn, dtype=torch.float32)
+            blk[:, :, :nvalid, :cout] = w[:, :, c0:c0 + nvalid, :]
+            # [k][k][kc][ntile*bn] -> [ntile][k][k][kc/8][bn][8]
+            blk = blk.reshape(k, k, kc // 8, 8, n_tiles, bn).permute(4, 0, 1, 2, 5, 3)
+            packed[:, gi] = blk
+        hi = packed.to(torch.float16)
+        lo = (packed - hi.to(torch.float32)).to(torch.float16)
+        self.w_hi, self.w_lo = hi.contiguous().to(device), lo.contiguous().to(device)
+        self.ksize, self.cin, self.cout, self.act = k, cin, cout, pc.act
+        self.bias = pc.bias.to(device) if pc.bias is not None else None
+        self.src_channels = list(src_channels)
+
+
+def conv2d_halo(sources_blk, ph, residual=None, terms=3, want_f32=True, want_blk=False, want_nhwc=True):
+    """sources_blk: list of blocked plane tensors (2,B,C8_i,H,W,8).  Returns (f32 or None, blk or None, nhwc planes or None)."""
+    d = N.ConvHaloDesc()
+    first = sources_blk[0]
+    B, H, W = first.shape[1], first.shape[3], first.shape[4]
+    if len(sources_blk) != len(ph.src_c8):
+        raise ValueError("conv2d_halo: %d sources given, weights packed for %d" % (len(sources_blk), len(ph.src_c8)))
+    for i, t in enumerate(sources_blk):
+        if t.dtype != torch.float16 or tuple(t.shape) != (2, B, ph.src_c8[i], H, W, 8):
+            raise ValueError("conv2d_halo: source %d has shape %s, expected %s" % (i, tuple(t.shape), (2, B, ph.src_c8[i], H, W, 8)))
+        d.src_blk[i] = t.data_ptr()
+        d.src_c8[i] = ph.src_c8[i]
+    d.n_src = len(sources_blk)
+    dev = first.device
+    out_f32 = torch.empty((B, H, W, ph.cout), dtype=torch.float32, device=dev) if want_f32 else None
+    out_blk = torch.empty((2, B, ph.cout // 8, H, W, 8), dtype=torch.float16, device=dev) if want_blk else None
+    out_nhwc = torch.empty((2, B, H, W, ph.cout), dtype=torch.float16, device=dev) if want_nhwc else None
+    d.w_hi, d.w_lo = ph.w_hi.data_ptr(), ph.w_lo.data_ptr()
+    d.n_groups, d.kc, d.block_n, d.terms = ph.n_groups, ph.kc, ph.block_n, terms
+    d.bias = ph.bias.data_ptr() if ph.bias is not None else None
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.out_f32 = out_f32.data_ptr() if want_f32 else None
+    d.out_blk = out_blk.data_ptr() if want_blk else None
+    d.out_nhwc = out_nhwc.data_ptr() if want_nhwc else None
+    d.B, d.H, d.W, d.Cout, d.ksize, d.act = B, H, W, ph.cout, ph.ksize, ph.act
+    N.check(N.lib().dvmvs_conv2d_halo(ctypes.byref(d), _stream()), "conv2d_halo")
+    return out_f32, out_blk, out_nhwc
+
+
 # ================================================================================================ backend dispatch
 import os as _os
 
 _BACKEND = _os.environ.get("DVMVS_CONV_BACKEND", "fp32")     # "fp32": CUDA-core kernels; "tc": tcgen05 where eligible
 _TC_TERMS = int(_os.environ.get("DVMVS_TC_TERMS", "3"))
 _TC_STRIDE2 = _os.environ.get("DVMVS_TC_STRIDE2", "0") == "1"
+_HALO = _os.environ.get("DVMVS_HALO", "1") == "1"          # blocked-layout halo kernel for large stride-1 k>=3 convolutions
+_HALO_MIN_PIXELS = int(_os.environ.get("DVMVS_HALO_MIN_PIXELS", "1024"))
 
 
 def set_conv_backend(name, terms=None, stride2=None):
@@ -400,10 +491,10 @@ def conv_backend():
 class Act:
     """An activation inside a module: fp32 channel-last tensor and/or its fp16 (hi, lo) planes (created on demand,
     cached).  `up` planes = planes of the x2-bilinear-upsampled tensor (F.interpolate materialised for the TMA loader)."""
-    __slots__ = ("f32", "planes", "planes_up", "version")
+    __slots__ = ("f32", "planes", "planes_up", "blk", "version")
 
-    def __init__(self, f32=None, planes=None):
-        self.f32, self.planes, self.planes_up, self.version = f32, planes, None, None
+    def __init__(self, f32=None, planes=None, blk=None):
+        self.f32, self.planes, self.planes_up, self.blk, self.version = f32, planes, None, blk, None
 
     @property
     def channels(self):
@@ -448,6 +539,7 @@ class ConvLayer:
         self.src_channels = list(src_channels) if src_channels is not None else [pc.cin]
         self.pack_sources = pack_sources
         self._ptc = None
+        self._phalo = None
 
     def tc_eligible(self):
         pc = self.pc
@@ -456,10 +548,30 @@ class ConvLayer:
     def uses_tc(self):
         return _BACKEND == "tc" and self.tc_eligible()
 
+    def uses_halo(self, hout, wout, residual_mode, aux):
+        pc = self.pc
+        return (_HALO and self.uses_tc() and pc.stride == 1 and pc.ksize >= 3 and hout * wout >= _HALO_MIN_PIXELS and
+                residual_mode in (N.RES_NONE, N.RES_SAME) and aux is None)
+
     def run(self, sources, residual=None, residual_mode=N.RES_NONE, aux=None, want_f32=True, want_planes=True):
         """sources: list of (Act, mode).  Returns Act (or (Act, aux tensor)).  want_* only prune outputs of the
         tensor-core path (the fp32 path always produces fp32)."""
         pc = self.pc
+        a0, m0 = sources[0]
+        hin = (a0.f32 if a0.f32 is not None else a0.planes[0]).shape[1] * (2 if m0 == N.SRC_UPSAMPLE2X else 1)
+        win = (a0.f32 if a0.f32 is not None else a0.planes[0]).shape[2] * (2 if m0 == N.SRC_UPSAMPLE2X else 1)
+        if self.uses_halo(hin, win, residual_mode, aux):
+            if self._phalo is None:
+                self._phalo = PackedConvHalo(pc, [pc.cin], pc.weight.device)
+            # a single source that already carries blocked planes is used as is; anything else (concats, upsampled
+            # sources, fp32-only producers) is staged once into one blocked operand tensor
+            if len(sources) == 1 and m0 == N.SRC_DIRECT and a0.blk is not None:
+                blk = a0.blk
+            else:
+                blk = split_blocked([(a.f32, mode == N.SRC_UPSAMPLE2X) for a, mode in sources])
+            f32, oblk, onhwc = conv2d_halo([blk], self._phalo, residual=residual.f32 if residual is not None else None,
+                                           terms=_TC_TERMS, want_f32=True, want_blk=True, want_nhwc=want_planes)
+            return Act(f32, onhwc, oblk)
         if self.uses_tc():
             if self._ptc is None:
                 self._ptc = PackedConvTC(pc, [pc.cin] if self.pack_sources else self.src_channels, pc.weight.device)

@@ -138,6 +138,37 @@ typedef struct {
 
 int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* desc_host, dvmvs_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Stride-1 k x k convolution on tcgen05 without im2col amplification ("halo" implicit GEMM, csrc/conv_halo.cu): the
+ * activations live in the channel-BLOCKED fp16 pair layout [2][B][C/8][H][W][8]; one TMA box loads the halo of an
+ * 8 x 16 output tile once per kc-channel group and every filter tap is a start-address offset into it.
+ *   src_blk[i]  blocked planes of source i (C8_i = channel blocks; padded channels are zero); sources concatenate
+ *   w_hi/w_lo   fp16 weights in their shared-memory image: [n-tile][group][ky][kx][kc/8][block_n][8], BN folded; groups
+ *               enumerate the kc-channel groups of source 0, then source 1, ... (zero rows for padded channels)
+ *   outputs     any of: out_f32 [B][H][W][Cout], out_blk [2][B][Cout/8][H][W][8], out_nhwc [2][B][H][W][Cout]
+ *   residual    optional fp32 [B][H][W][Cout] added before the activation. */
+typedef struct {
+  const void* src_blk[3];
+  int src_c8[3];
+  int n_src;
+  const void* w_hi;
+  const void* w_lo;
+  int n_groups, kc, block_n, terms;
+  const float* bias;
+  const float* residual;
+  float* out_f32;
+  void* out_blk;
+  void* out_nhwc;
+  int B, H, W, Cout, ksize, act;
+} dvmvs_conv_halo_desc;
+
+int dvmvs_conv2d_halo(const dvmvs_conv_halo_desc* desc_host, dvmvs_stream_t stream);
+
+/* fp32 channel-last [B][H][W][C] -> channels [c_offset, c_offset + c_cover) of the BLOCKED fp16 pair planes
+ * [2][B][C8][H'][W'][8] (x, then zeros), optional x2 bilinear (align_corners) upsampling (H' = 2H). */
+int dvmvs_split_blocked(const float* x, void* planes, int B, int H, int W, int C, int C8, int upsample2x, int c_offset,
+                        int c_cover, dvmvs_stream_t stream);
+
 /* fp32 channel-last [B][H][W][C] -> channels [c_offset, c_offset + c_cover) of fp16 (hi, lo) planes
  * [2][B][H'][W'][Cs] (Cs a multiple of 8): the C values of x, then zeros up to c_cover.  Several calls with different
  * offsets stage a channel concatenation (torch.cat) into one operand tensor.  upsample2x != 0 applies the x2 bilinear

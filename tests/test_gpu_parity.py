@@ -452,3 +452,49 @@ def test_fusionnet_shipped_weights_tensor_core_backend_vs_shipped_golden():
         assert max(errs) <= 1e-3, errs
     finally:
         ops.set_conv_backend(old)
+
+
+HALO_CASES = [
+    # name, B, H, W, [(channels, upsampled)], Cout, k, residual, terms, tol
+    ("k3_c32", 1, 40, 48, [(32, False)], 32, 3, False, 3, 2e-5),
+    ("k5_c32", 1, 64, 64, [(32, False)], 32, 5, False, 3, 5e-5),
+    ("k5_concat_96", 1, 64, 64, [(32, False), (64, False)], 32, 5, False, 3, 5e-5),
+    ("k5_refine_like", 1, 64, 64, [(32, True), (1, True), (3, False)], 32, 5, False, 3, 5e-5),
+    ("k3_c64_n64", 2, 32, 32, [(64, False)], 64, 3, True, 3, 5e-5),
+    ("k3_ragged", 1, 20, 12, [(24, False)], 40, 3, False, 3, 5e-5),
+    ("k5_c64_n128", 1, 32, 40, [(64, False)], 128, 5, False, 3, 5e-5),
+    ("k3_plain_fp16", 1, 32, 32, [(32, False)], 32, 3, False, 1, 2e-3),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=[c[0] for c in HALO_CASES])
+def test_conv2d_halo_vs_torch_fp32(synth, case):
+    """Blocked-layout halo implicit GEMM (one TMA halo load per channel group, taps = descriptor offsets) vs torch fp32."""
+    import torch.nn.functional as F
+    from dvmvs import _native as N
+    from dvmvs import _ops as ops
+    name, B, H, W, srcs, Cout, k, use_res, terms, tol = case
+    xs, full = [], []
+    for i, (c, up) in enumerate(srcs):
+        f = 2 if up else 1
+        x = T(synth.tensor("halo/%s/x%d" % (name, i), (B, c, H // f, W // f), seed=1))
+        xs.append(x)
+        full.append(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True) if up else x)
+    cin = sum(c for c, _ in srcs)
+    w = T(synth.tensor("halo/%s/w" % name, (Cout, cin, k, k), seed=2, scale=(2.0 / (cin * k * k)) ** 0.5))
+    bias = T(synth.tensor("halo/%s/b" % name, (Cout,), seed=3, scale=0.1))
+    ref = F.conv2d(torch.cat(full, 1), w, bias, 1, (k - 1) // 2)
+    res = T(synth.tensor("halo/%s/r" % name, (B, Cout, H, W), seed=4)) if use_res else None
+    if res is not None:
+        ref = ref + res
+    ref = F.relu(ref)
+    pc = ops.PackedConv(w, bias, None, stride=1, act=N.ACT_RELU)
+    ph = ops.PackedConvHalo(pc, [cin], DEV)
+    blk = ops.split_blocked([(ops.to_nhwc(x.to(DEV)), up) for x, (c, up) in zip(xs, srcs)])
+    f32, oblk, onhwc = ops.conv2d_halo([blk], ph, residual=None if res is None else ops.to_nhwc(res.to(DEV)), terms=terms,
+                                       want_f32=True, want_blk=True, want_nhwc=True)
+    assert rel_err(ops.to_api(f32).cpu().numpy(), ref.numpy()) <= tol, name
+    nh = onhwc[0].float() + onhwc[1].float()
+    assert rel_err(ops.to_api(nh).cpu().numpy(), ref.numpy()) <= max(tol, 1e-5), name
+    bl = (oblk[0].float() + oblk[1].float()).permute(0, 1, 4, 2, 3).reshape(B, Cout, H, W)     # (B,C8,H,W,8) -> (B,C,H,W)
+    assert rel_err(bl.cpu().numpy(), ref.numpy()) <= max(tol, 1e-5), name

@@ -62,6 +62,15 @@ def main():
                 t = timeit(lambda: ops.conv2d_tc(planes, ptc, terms=terms, block_n=bn, allow_split=split))
                 res.append("N%d%s %.1f" % (bn, "+splitK" if split else "", t))
         t1 = timeit(lambda: ops.conv2d_tc(planes, ptc, terms=1, allow_split=True))
+        if stride == 1 and k >= 3 and Cout <= 64 * 8:
+            for kc in (16, 32):
+                try:
+                    ph = ops.PackedConvHalo(pc, [cin], DEV, kc=kc)
+                    blk = ops.split_blocked([(x, False) for x in xs])
+                    th = timeit(lambda: ops.conv2d_halo([blk], ph, terms=terms, want_f32=True, want_blk=True, want_nhwc=False))
+                    res.append("HALO kc%d %.1f" % (kc, th))
+                except Exception as e:  # noqa: BLE001
+                    res.append("HALO kc%d FAILED %s" % (kc, str(e)[:60]))
         macs = B * (H // stride) * (W // stride) * Cout * cin * k * k
         print("%-38s %7.1f MMAC | fp32 %7.1f us | tc x%d: %s | tc x1 auto %.1f us" % (name, macs / 1e6, t_fp32, terms, "  ".join(res), t1), flush=True)
 
