@@ -32,6 +32,9 @@ import torch  # noqa: E402
 H, W, D, M = 256, 256, 64, 2
 WORKLOAD = "fusionnet inference 256x256, 64 planes, 2 measurement frames, batch=%d clip(s)/GPU (BASELINE.json configs[1])"
 SWEEP_BYTES_PER_CLIP = ((1 + M) * 32 + D) * (H // 2) * (W // 2) * 4        # 10,485,760 B at c2
+# dram__bytes_read.sum + dram__bytes_write.sum of plane_sweep_c32_kernel at c2, B=1, from the committed ncu --set full
+# capture profiles/r01_plane_sweep_v3_ncu.md (6.6 MB read, 0 B written: the 4 MiB cost volume stays in L2)
+SWEEP_DRAM_TRAFFIC_PER_CLIP = 6616320
 
 
 def measured_peaks():
@@ -268,6 +271,50 @@ def run_ours(args, rank, world, local_rank):
     sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in sw_ev]))
     log("roofline arm done: plane sweep %.3f ms" % sweep_ms)
 
+    # ---------------- extra operating points (reported next to the headline): strictly sequential latency
+    # of one keyframe (CUDA graph, no inter-keyframe overlap) and batched throughput (EXTRA_B clips per GPU)
+    extras = {}
+    if args.extras:
+        with torch.no_grad():
+            eng = pipeline.GraphedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
+            for t in range(4):
+                eng.step(*frames_dev[t])
+            lat = []
+            for t in range(4, min(n_frames, 16)):
+                flush.zero_()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                eng.step(*frames_dev[t])
+                b_.record()
+                torch.cuda.synchronize()
+                lat.append(a.elapsed_time(b_))
+            extras["sequential_latency_ms_per_keyframe"] = float(np.median(lat)) if lat else None
+            del eng
+            EB = args.extra_clips
+            if EB > B:
+                clips_b = make_inputs(EB, 12, rank)
+                fb = []
+                for t in range(12):
+                    ref, rpose, meas, mpose, K = stack_frame(clips_b, t)
+                    fb.append((torch.from_numpy(ref).to(dev), torch.from_numpy(rpose).to(dev), [torch.from_numpy(x).to(dev) for x in meas],
+                               [torch.from_numpy(p_).to(dev) for p_ in mpose], torch.from_numpy(K).to(dev)))
+                pb = pipeline.PipelinedFusionnet(mods, batch=EB, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
+                outb = torch.empty((EB, H, W), dtype=torch.float32, device=dev)
+                for t in range(4):
+                    pb.submit(*fb[t], out=outb)
+                pb.synchronize()
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record(pb.stream_a)
+                for t in range(4, 12):
+                    pb.submit(*fb[t], out=outb)
+                q1.record(pb.stream_b)
+                pb.synchronize()
+                torch.cuda.synchronize()
+                ms = q0.elapsed_time(q1)
+                extras["batched"] = {"clips_per_gpu": EB, "frames_per_s_per_gpu": EB * 8 / (ms * 1e-3), "ms_per_step": ms / 8}
+                del pb, fb
+        log("extra operating points done")
+
     # ---------------- max over ranks
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
     lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
@@ -290,10 +337,11 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": int(lt[0]),
+        "operating_points": extras,
         "roofline": {"kernel": "plane_sweep_c32_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src, "ms_per_launch": sweep_ms,
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": SWEEP_DRAM_TRAFFIC_PER_CLIP * B, "peak_source": peak_src, "ms_per_launch": sweep_ms,
                      "algorithmic_bytes_per_launch": SWEEP_BYTES_PER_CLIP * B,
-                     "note": "52 FLOP/B of fp32 FMA work per algorithmic byte: CUDA-core/L1-gather bound before HBM (DESIGN.md)"},
+                     "note": "64 FLOP per algorithmic byte and 512 B of L1 gather traffic per sample: bound by the L1 gather path / FFMA issue, not HBM (DESIGN.md section 6)"},
     }
     return result
 
@@ -363,6 +411,8 @@ def main():
                          "launch per kernel")
     ap.add_argument("--backend", default=os.environ.get("DVMVS_CONV_BACKEND", "tc"), choices=["tc", "fp32"])
     ap.add_argument("--tc-terms", type=int, default=3)
+    ap.add_argument("--extras", type=int, default=1, help="also measure sequential latency and batched throughput (0 to skip)")
+    ap.add_argument("--extra-clips", type=int, default=8)
     ap.add_argument("--cpu-frames", type=int, default=6, help="frames of the bounded CPU-baseline sample")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

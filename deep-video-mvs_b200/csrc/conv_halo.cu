@@ -41,11 +41,20 @@ struct HaloParams {
   __half* out_nhwc;            // [2][B][H][W][Cout] or null
   int act;
   uint32_t a_bytes, w_bytes;   // per plane: halo tile bytes of one group, weight bytes of one (group, ky) stage
+  unsigned long long* dbg;     // optional timeline dump: [cta][8] globaltimer ns at phase boundaries (profiling aid)
 };
 
-template <int BLOCK_N>
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define HALO_MARK(i) do { if (p.dbg) p.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = gtimer(); } while (0)
+
+template <int BLOCK_N, int KSIZE, int KC, int TERMS>
 __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   pdl_launch_dependents();
+  if (threadIdx.x == 0) HALO_MARK(0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 127u) & ~127u;
@@ -97,7 +106,9 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) HALO_MARK(1);
   pdl_wait();
+  if (threadIdx.x == 0) HALO_MARK(2);
 
   if (warp == 0) {
     // ============================== producer ==============================
@@ -129,10 +140,13 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t a_chunk = (uint32_t)halo_h * halo_w * 16;       // bytes of one 8-channel block of the halo tile
-      const uint32_t a_sbo = (uint32_t)halo_w * 16;                  // next tile row (next 8 GEMM rows)
-      const uint32_t w_chunk = BLOCK_N * 16;                         // bytes of one 8-channel block of a weight tap
-      const uint32_t w_tap = (uint32_t)(p.kc / 8) * w_chunk;         // bytes of one tap's [kc/8][BLOCK_N][8] block
+      // all offsets below are in 16-byte units (the granularity of the descriptor's address field)
+      const uint32_t a_chunk16 = (uint32_t)halo_h * halo_w;          // one 8-channel block of the halo tile
+      constexpr uint32_t w_chunk16 = BLOCK_N;                        // one 8-channel block of a weight tap: [BLOCK_N][8]
+      constexpr uint32_t w_tap16 = (KC / 8) * BLOCK_N;               // one tap: [KC/8][BLOCK_N][8]
+      const uint32_t a_hi_word = umma_hi_word((uint32_t)halo_w * 16, 0);     // SBO = next tile row (next 8 GEMM rows)
+      const uint32_t w_hi_word = umma_hi_word(128, 0);                        // SBO = next 8 output channels
+      const uint32_t a_lbo = ((a_chunk16 & 0x3FFF) << 16), w_lbo = ((w_chunk16 & 0x3FFF) << 16);
       int g = 0, wst = 0;
       uint32_t wphase = 0, accumulate = 0;
       for (int s = 0; s < p.n_src; ++s) {
@@ -140,19 +154,23 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
           const int ab = g & 1;
           mbar_wait(a_full(ab), (g >> 1) & 1);
           tc_fence_after();
-          const uint32_t a_hi = a_base + ab * a_buf_bytes, a_lo = a_hi + p.a_bytes;
-          for (int ky = 0; ky < p.ksize; ++ky) {
+          if (g == 0) HALO_MARK(3);
+          const uint32_t a_plane0 = ((a_base + ab * a_buf_bytes) >> 4) | a_lbo, a_plane1 = a_plane0 + (p.a_bytes >> 4);
+#pragma unroll 1
+          for (int ky = 0; ky < KSIZE; ++ky) {
             mbar_wait(w_full(wst), wphase);
             tc_fence_after();
-            const uint32_t w_hi = w_base + wst * w_stage_bytes, w_lo = w_hi + p.w_bytes;
-            for (int kx = 0; kx < p.ksize; ++kx) {
-              const uint32_t a_tap = (uint32_t)(ky * halo_w + kx) * 16;
-              for (int term = 0; term < p.terms; ++term) {
-                const uint32_t a_s = ((term == 1) ? a_lo : a_hi) + a_tap;
-                const uint32_t w_s = ((term == 2) ? w_lo : w_hi) + kx * w_tap;
-                for (int k2 = 0; k2 < p.kc / 16; ++k2) {
-                  tc_mma_f16(tmem_base, umma_desc_noswizzle(a_s + 2 * k2 * a_chunk, a_chunk, a_sbo),
-                             umma_desc_noswizzle(w_s + 2 * k2 * w_chunk, w_chunk, 128), idesc, accumulate);
+            const uint32_t w_plane0 = ((w_base + wst * w_stage_bytes) >> 4) | w_lbo, w_plane1 = w_plane0 + (p.w_bytes >> 4);
+            const uint32_t a_row = (uint32_t)ky * halo_w;
+#pragma unroll
+            for (int kx = 0; kx < KSIZE; ++kx) {
+#pragma unroll
+              for (int term = 0; term < TERMS; ++term) {
+#pragma unroll
+                for (int k2 = 0; k2 < KC / 16; ++k2) {
+                  const uint32_t a_lo = ((term == 1) ? a_plane1 : a_plane0) + a_row + kx + 2 * k2 * a_chunk16;
+                  const uint32_t w_lo = ((term == 2) ? w_plane1 : w_plane0) + kx * w_tap16 + 2 * k2 * w_chunk16;
+                  tc_mma_f16_words(tmem_base, a_lo, a_hi_word, w_lo, w_hi_word, idesc, accumulate);
                   accumulate = 1;
                 }
               }
@@ -164,6 +182,7 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
         }
       }
       tc_commit(tmem_full_bar);
+      HALO_MARK(4);
     }
   } else {
     // ============================== epilogue ==============================
@@ -174,6 +193,7 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
     const bool valid = (oy < p.Hout) && (ox < p.Wout);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) HALO_MARK(5);
     const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
     const size_t hw = (size_t)p.Hout * p.Wout;
     const size_t plane_elems = (size_t)p.B * p.c8_out * hw * 8;
@@ -220,6 +240,7 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
         }
       }
     }
+    if (threadIdx.x == 64) HALO_MARK(6);
     tc_fence_before();
   }
   __syncthreads();
@@ -228,6 +249,7 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
+  if (threadIdx.x == 0) HALO_MARK(7);
 }
 
 // fp32 channel-last -> channels [c_offset, c_offset + c_cover) of the blocked fp16 pair planes [2][B][C8][H'][W'][8]
@@ -284,27 +306,43 @@ static int make_halo_map(CUtensorMap* map, const void* ptr, int B, int H, int W,
   return DVMVS_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int KSIZE, int KC, int TERMS>
 static int launch_halo(const HaloParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, KSIZE, KC, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("conv_halo smem attribute: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
     attr_set = true;
   }
-  launch_k(conv_halo_kernel<BLOCK_N>, grid, dim3(kHaloThreads), smem, s, p);
+  launch_k(conv_halo_kernel<BLOCK_N, KSIZE, KC, TERMS>, grid, dim3(kHaloThreads), smem, s, p);
   return check_launch("conv_halo_kernel");
 }
+
+template <int BLOCK_N, int KSIZE>
+static int launch_halo_kt(const HaloParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+  if (p.kc == 16) return p.terms == 3 ? launch_halo<BLOCK_N, KSIZE, 16, 3>(p, grid, smem, s) : launch_halo<BLOCK_N, KSIZE, 16, 1>(p, grid, smem, s);
+  return p.terms == 3 ? launch_halo<BLOCK_N, KSIZE, 32, 3>(p, grid, smem, s) : launch_halo<BLOCK_N, KSIZE, 32, 1>(p, grid, smem, s);
+}
+
+static void* g_halo_dbg = nullptr;
 
 }  // namespace dvmvs
 
 using namespace dvmvs;
 
+// profiling aid: device buffer of (#CTAs x 8) uint64 receiving %globaltimer at the phase boundaries of conv_halo_kernel
+// (0 start, 1 setup done, 2 dependencies resolved, 3 first halo landed, 4 last MMA issued, 5 accumulator ready,
+// 6 epilogue stores issued, 7 exit); NULL switches it off.
+extern "C" int dvmvs_debug_set_halo_timeline(void* device_buffer) {
+  g_halo_dbg = device_buffer;
+  return DVMVS_OK;
+}
+
 extern "C" int dvmvs_conv2d_halo(const dvmvs_conv_halo_desc* d, dvmvs_stream_t stream) {
   DVMVS_REQUIRE(d != nullptr, "conv2d_halo: null descriptor");
   DVMVS_REQUIRE(tensor_map_encoder() != nullptr, "conv2d_halo: cuTensorMapEncodeTiled entry point not available");
   DVMVS_REQUIRE(d->n_src >= 1 && d->n_src <= 3, "conv2d_halo: n_src=%d", d->n_src);
-  DVMVS_REQUIRE(d->ksize == 1 || d->ksize == 3 || d->ksize == 5, "conv2d_halo: ksize=%d", d->ksize);
+  DVMVS_REQUIRE(d->ksize == 3 || d->ksize == 5, "conv2d_halo: ksize=%d (3 or 5)", d->ksize);
   DVMVS_REQUIRE(d->terms == 1 || d->terms == 3, "conv2d_halo: terms=%d", d->terms);
   DVMVS_REQUIRE(d->kc == 16 || d->kc == 32, "conv2d_halo: kc=%d", d->kc);
   DVMVS_REQUIRE(d->block_n == 32 || d->block_n == 64, "conv2d_halo: block_n=%d", d->block_n);
@@ -340,13 +378,15 @@ extern "C" int dvmvs_conv2d_halo(const dvmvs_conv_halo_desc* d, dvmvs_stream_t s
   p.w_hi = (const __half*)d->w_hi; p.w_lo = (const __half*)d->w_lo;
   p.bias = d->bias; p.residual = d->residual; p.act = d->act;
   p.out_f32 = d->out_f32; p.out_blk = (__half*)d->out_blk; p.out_nhwc = (__half*)d->out_nhwc;
+  p.dbg = (unsigned long long*)g_halo_dbg;
   const int planes = d->terms > 1 ? 2 : 1;
   const size_t smem = 2 * (size_t)planes * p.a_bytes + kHaloWStages * (size_t)planes * p.w_bytes + 256 + 128;
   DVMVS_REQUIRE(smem <= 227 * 1024, "conv2d_halo: shared memory %zu too large", smem);
   const int n_tiles = (d->Cout + d->block_n - 1) / d->block_n;
   dim3 grid(p.tiles_x * p.tiles_y * d->B, n_tiles, 1);
-  if (d->block_n == 32) return launch_halo<32>(p, grid, smem, (cudaStream_t)stream);
-  return launch_halo<64>(p, grid, smem, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->block_n == 32) return d->ksize == 3 ? launch_halo_kt<32, 3>(p, grid, smem, st) : launch_halo_kt<32, 5>(p, grid, smem, st);
+  return d->ksize == 3 ? launch_halo_kt<64, 3>(p, grid, smem, st) : launch_halo_kt<64, 5>(p, grid, smem, st);
 }
 
 extern "C" int dvmvs_split_blocked(const float* x, void* planes, int B, int H, int W, int C, int C8, int upsample2x, int c_offset,

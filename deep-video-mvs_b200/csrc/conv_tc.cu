@@ -151,18 +151,27 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
           const int kc = p.src_kchunk[s];
           const uint32_t layout = (kc == 64) ? 2u : 4u;           // SWIZZLE_128B : SWIZZLE_64B
           const uint32_t sbo = (kc == 64) ? 1024u : 512u;         // 8 rows x row bytes
+          const uint32_t hi_word = umma_hi_word(sbo, layout);
+          const int ksteps = kc >> 4;
           for (int ch = 0; ch < p.src_chunks[s]; ++ch) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t sb = base + stage * p.stage_bytes;
-            const uint32_t a_hi = sb, a_lo = sb + off_a_lo;
-            const uint32_t w_hi = sb + off_w_hi, w_lo = sb + off_w_lo;
-            for (int term = 0; term < p.terms; ++term) {
-              const uint32_t a_s = (term == 1) ? a_lo : a_hi;
-              const uint32_t w_s = (term == 2) ? w_lo : w_hi;
-              for (int k = 0; k < kc / 16; ++k) {
-                tc_mma_f16(tmem_base, umma_desc(a_s + k * 32, sbo, layout), umma_desc(w_s + k * 32, sbo, layout), idesc, accumulate);
-                accumulate = 1;
+            // lo words: (address >> 4) | LBO(=1) << 16; a K step of 16 fp16 = 32 bytes = +2
+            const uint32_t a_hi = umma_lo_word(sb, 16), a_lo = umma_lo_word(sb + off_a_lo, 16);
+            const uint32_t w_hi = umma_lo_word(sb + off_w_hi, 16), w_lo = umma_lo_word(sb + off_w_lo, 16);
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              if (term < p.terms) {
+                const uint32_t a_s = (term == 1) ? a_lo : a_hi;
+                const uint32_t w_s = (term == 2) ? w_lo : w_hi;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < ksteps) {
+                    tc_mma_f16_words(tmem_base, a_s + 2 * k, hi_word, w_s + 2 * k, hi_word, idesc, accumulate);
+                    accumulate = 1;
+                  }
+                }
               }
             }
             tc_commit(empty_bar(stage));     // stage reusable once these MMAs have consumed it

@@ -79,6 +79,25 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 }
 
 
+// Lean MMA issue: the descriptors are passed as (lo, hi) 32-bit words.  The hi word (stride byte offset, version, layout
+// type) is constant per operand; the lo word is (smem address >> 4) | (leading byte offset >> 4) << 16, so stepping to
+// another tile / K step / filter tap is ONE 32-bit add.  The single issuing thread's instruction count per MMA is what
+// bounds narrow-N (Cout = 32) layers, so this path must stay at a handful of instructions per MMA.
+__device__ __forceinline__ void tc_mma_f16_words(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t umma_hi_word(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint32_t umma_lo_word(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+
 // bulk (non-tensor) global -> shared copy completing on an mbarrier
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
