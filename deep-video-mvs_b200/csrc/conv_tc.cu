@@ -43,6 +43,7 @@ struct TcParams {
   int residual_mode, Hr, Wr;
   float* out_f32;             // [B][Hout][Wout][Cout] or null
   __half* out_planes;         // [2][B][Hout][Wout][Cout] or null
+  __half* out_blk;            // blocked planes [2][B][Cout/8][Hout][Wout][8] or null (operand layout of conv_halo_kernel)
   float* aux_out;
   float aux_mult, aux_base;
   int act;
@@ -247,6 +248,11 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
           __half* oh = p.out_planes + pix * p.Cout + cbase;
           *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(hi);
           *reinterpret_cast<uint4*>(oh + plane_stride) = *reinterpret_cast<const uint4*>(lo);
+          if (p.out_blk) {
+            __half* ob = p.out_blk + ((((size_t)b * (p.Cout >> 3) + (cbase >> 3)) * p.Hout + oy) * p.Wout + ox) * 8;
+            *reinterpret_cast<uint4*>(ob) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(ob + plane_stride) = *reinterpret_cast<const uint4*>(lo);
+          }
         }
       } else {        // generic tail (Cout not a multiple of 8): scalar, rolled
 #pragma unroll 1
@@ -305,8 +311,14 @@ __global__ void conv_tc_finish_kernel(TcParams p) {
   if (p.aux_out) p.aux_out[idx] = 1.f / (p.aux_mult * x + p.aux_base);
   if (p.out_planes) {
     const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
     p.out_planes[idx] = h;
-    p.out_planes[total + idx] = __float2half_rn(x - __half2float(h));
+    p.out_planes[total + idx] = l;
+    if (p.out_blk) {
+      const size_t o = ((((size_t)b * (p.Cout >> 3) + (c >> 3)) * p.Hout + oy) * p.Wout + ox) * 8 + (c & 7);
+      p.out_blk[o] = h;
+      p.out_blk[total + o] = l;
+    }
   }
 }
 
@@ -479,6 +491,8 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   p.bias = d->bias; p.residual = d->residual; p.residual_mode = d->residual_mode; p.Hr = d->Hr; p.Wr = d->Wr;
   DVMVS_REQUIRE(d->residual_mode == DVMVS_RES_NONE || d->residual, "conv2d_tc: residual pointer missing");
   p.out_f32 = d->out_f32; p.out_planes = (__half*)d->out_planes; p.aux_out = d->aux_out;
+  p.out_blk = (__half*)d->out_blk;
+  DVMVS_REQUIRE(!d->out_blk || (d->out_planes && d->Cout % 8 == 0), "conv2d_tc: out_blk needs out_planes and Cout %% 8 == 0");
   p.aux_mult = d->aux_mult; p.aux_base = d->aux_base; p.act = d->act;
   cudaStream_t s = (cudaStream_t)stream;
   const int n_tiles = (d->Cout + d->block_n - 1) / d->block_n;

@@ -316,7 +316,7 @@ class PackedConvTC:
 
 
 def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, want_f32=True, want_planes=True, terms=3,
-              block_n=None, allow_split=True):
+              block_n=None, allow_split=True, blk_out=None):
     """sources: list of fp16-pair plane tensors (2,B,Hin,Win,Cs_i) matching ptc.src_stored.  Returns
     (out_f32 or None, out_planes or None[, aux_out])."""
     d = N.ConvTcDesc()
@@ -356,6 +356,8 @@ def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, w
         d.Hr, d.Wr = residual.shape[1], residual.shape[2]
     d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
     d.out_planes = out_planes.data_ptr() if out_planes is not None else None
+    if blk_out is not None:            # caller-provided (2,B,Cout/8,Hout,Wout,8) tensor, filled alongside out_planes
+        d.out_blk = blk_out.data_ptr()
     aux_out = None
     if aux is not None:
         aux_out = torch.empty((B, Hout, Wout, ptc.cout), dtype=torch.float32, device=dev)
@@ -562,14 +564,15 @@ class ConvLayer:
         win = (a0.f32 if a0.f32 is not None else a0.planes[0]).shape[2] * (2 if m0 == N.SRC_UPSAMPLE2X else 1)
         if self.uses_halo(hin, win, residual_mode, aux):
             if self._phalo is None:
-                self._phalo = PackedConvHalo(pc, [pc.cin], pc.weight.device)
-            # a single source that already carries blocked planes is used as is; anything else (concats, upsampled
-            # sources, fp32-only producers) is staged once into one blocked operand tensor
-            if len(sources) == 1 and m0 == N.SRC_DIRECT and a0.blk is not None:
-                blk = a0.blk
+                self._phalo = PackedConvHalo(pc, [pc.cin] if self.pack_sources else self.src_channels, pc.weight.device)
+            # sources that already carry blocked planes (outputs of tensor-core layers on large maps) are used as they
+            # are -- the kernel concatenates up to three sources along K; upsampled / fp32-only sources are staged
+            if self.pack_sources:
+                blks = [split_blocked([(a.f32, mode == N.SRC_UPSAMPLE2X) for a, mode in sources])]
             else:
-                blk = split_blocked([(a.f32, mode == N.SRC_UPSAMPLE2X) for a, mode in sources])
-            f32, oblk, onhwc = conv2d_halo([blk], self._phalo, residual=residual.f32 if residual is not None else None,
+                blks = [a.blk if (mode == N.SRC_DIRECT and a.blk is not None) else split_blocked([(a.f32, mode == N.SRC_UPSAMPLE2X)])
+                        for a, mode in sources]
+            f32, oblk, onhwc = conv2d_halo(blks, self._phalo, residual=residual.f32 if residual is not None else None,
                                            terms=_TC_TERMS, want_f32=True, want_blk=True, want_nhwc=want_planes)
             return Act(f32, onhwc, oblk)
         if self.uses_tc():
@@ -580,9 +583,15 @@ class ConvLayer:
             else:
                 planes = [a.get_planes(upsample=(mode == N.SRC_UPSAMPLE2X)) for a, mode in sources]
             res = residual.f32 if residual is not None else None
+            hout = (hin + 2 * ((pc.ksize - 1) // 2) - pc.ksize) // pc.stride + 1
+            wout = (win + 2 * ((pc.ksize - 1) // 2) - pc.ksize) // pc.stride + 1
+            blk_out = None
+            if _HALO and want_planes and hout * wout >= _HALO_MIN_PIXELS and pc.cout % 8 == 0:
+                # large map: its consumers are halo convolutions -> emit their operand layout from this epilogue too
+                blk_out = torch.empty((2, planes[0].shape[1], pc.cout // 8, hout, wout, 8), dtype=torch.float16, device=planes[0].device)
             r = conv2d_tc(planes, self._ptc, residual=res, residual_mode=residual_mode, aux=aux, terms=_TC_TERMS,
-                          want_f32=want_f32, want_planes=want_planes)
-            out = Act(r[0], r[1])
+                          want_f32=want_f32, want_planes=want_planes, blk_out=blk_out)
+            out = Act(r[0], r[1], blk_out)
             return (out, r[2]) if aux is not None else out
         r = conv2d([(a.f32, mode) for a, mode in sources], pc, residual=residual.f32 if residual is not None else None,
                    residual_mode=residual_mode, aux=aux)

@@ -134,6 +134,8 @@ typedef struct {
   int B, Hin, Win, Cout, ksize, stride, act;
   float* workspace;      /* as in dvmvs_conv_desc (split over filter taps) */
   long long workspace_bytes;
+  void* out_blk;         /* optional: the same output also in the blocked layout [2][B][Cout/8][Hout][Wout][8] that
+                            dvmvs_conv2d_halo consumes (needs out_planes) */
 } dvmvs_conv_tc_desc;
 
 int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* desc_host, dvmvs_stream_t stream);
