@@ -51,6 +51,7 @@ class ConvTcDesc(ctypes.Structure):
         ("B", ctypes.c_int), ("Hin", ctypes.c_int), ("Win", ctypes.c_int), ("Cout", ctypes.c_int),
         ("ksize", ctypes.c_int), ("stride", ctypes.c_int), ("act", ctypes.c_int),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_longlong),
+        ("out_blk", ctypes.c_void_p),
     ]
 
 

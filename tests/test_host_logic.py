@@ -27,13 +27,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.dvmvs_abi_version() == 2
 
 
-def test_conv_desc_struct_matches_header_field_order():
+def test_desc_structs_match_header_field_order():
+    """The ctypes mirrors must list exactly the fields of the C structs, in order (a mismatch corrupts memory)."""
     from dvmvs import _native as N
     header = open(os.path.join(REPO, "include", "dvmvs_b200.h")).read()
-    body = header[header.index("typedef struct {"):header.index("} dvmvs_conv_desc;")]
-    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    names = re.findall(r"[\s\*]([A-Za-z_][A-Za-z0-9_]*)(?:\[3\])?\s*[;,]", body)
-    assert names == [f[0] for f in N.ConvDesc._fields_], names
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    for cname, mirror in (("dvmvs_conv_desc", N.ConvDesc), ("dvmvs_conv_tc_desc", N.ConvTcDesc), ("dvmvs_conv_halo_desc", N.ConvHaloDesc)):
+        end = header.index("} %s;" % cname)
+        start = header.rindex("typedef struct {", 0, end)
+        body = header[start + len("typedef struct {"):end]
+        names = re.findall(r"[\s\*]([A-Za-z_][A-Za-z0-9_]*)(?:\[3\])?\s*[;,]", body)
+        assert names == [f[0] for f in mirror._fields_], (cname, names, [f[0] for f in mirror._fields_])
+        # ctypes silently accepts assignments to unknown attributes: make sure every mirror forbids them in tests
+        obj = mirror()
+        for f in names:
+            getattr(obj, f)
 
 
 def test_argument_validation_without_gpu():
