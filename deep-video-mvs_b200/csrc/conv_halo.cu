@@ -252,43 +252,65 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
   if (threadIdx.x == 0) HALO_MARK(7);
 }
 
-// fp32 channel-last -> channels [c_offset, c_offset + c_cover) of the blocked fp16 pair planes [2][B][C8][H'][W'][8]
-// (the C values of x, then zeros); optional x2 bilinear (align_corners) upsampling on the way.
+// fp32 channel-last -> channel blocks [c_offset/8, (c_offset + c_cover)/8) of the blocked fp16 pair planes
+// [2][B][C8][H'][W'][8] (the C values of x, then zeros); optional x2 bilinear (align_corners) upsampling on the way.
+// One thread per (pixel, 8-channel block): 32-byte reads, one 16-byte store per plane, consecutive threads = consecutive
+// pixels of one channel block (coalesced 512-byte stores per warp).  c_offset must be a multiple of 8.
 __global__ void split_blocked_kernel(const float* __restrict__ x, __half* __restrict__ planes, int B, int H, int W, int C, int C8,
                                      int upsample, int c_offset, int c_cover) {
   pdl_launch_dependents();
   pdl_wait();
   const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
-  const size_t total = (size_t)B * C8 * Ho * Wo * 8;
+  const size_t hw = (size_t)Ho * Wo;
+  const size_t total = (size_t)B * C8 * hw * 8;
+  const int nblk = (c_cover + 7) >> 3;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * Ho * Wo * c_cover) return;
-  // thread order: channel fastest within a pixel so that the fp32 reads are coalesced
-  const int c = (int)(idx % c_cover);
-  const size_t pix = idx / c_cover;
-  const int ox = (int)(pix % Wo);
-  const int oy = (int)((pix / Wo) % Ho);
-  const int b = (int)(pix / ((size_t)Wo * Ho));
-  float v = 0.f;
-  if (c < C) {
-    if (!upsample) {
-      v = x[pix * C + c];
+  if (idx >= (size_t)B * nblk * hw) return;
+  const size_t p_in = idx % hw;
+  const int cb = (int)((idx / hw) % nblk);
+  const int b = (int)(idx / (hw * nblk));
+  const int ox = (int)(p_in % Wo), oy = (int)(p_in / Wo);
+  const int c0 = cb * 8;                       // first source channel of this block
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  const bool vec = ((C & 3) == 0) && (c0 + 8 <= C);
+  if (!upsample) {
+    const float* src = x + ((size_t)b * hw + p_in) * C + c0;
+    if (vec) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(src)), a1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
     } else {
-      const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
-      const float sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
-      const float fy = sh * oy, fx = sw * ox;
-      const int y0 = (int)fy, x0 = (int)fx;
-      const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
-      const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-      const float* bp = x + (size_t)b * H * W * C + c;
-      v = ly0 * (lx0 * bp[((size_t)y0 * W + x0) * C] + lx1 * bp[((size_t)y0 * W + x1) * C]) +
-          ly1 * (lx0 * bp[((size_t)y1 * W + x0) * C] + lx1 * bp[((size_t)y1 * W + x1) * C]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (c0 + e < C) v[e] = __ldg(src + e);
     }
+  } else {
+    const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+    const float sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+    const float fy = sh * oy, fx = sw * ox;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+    const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float* bp = x + (size_t)b * H * W * C + c0;
+    const float* p00 = bp + ((size_t)y0 * W + x0) * C;
+    const float* p01 = bp + ((size_t)y0 * W + x1) * C;
+    const float* p10 = bp + ((size_t)y1 * W + x0) * C;
+    const float* p11 = bp + ((size_t)y1 * W + x1) * C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (c0 + e < C) v[e] = ly0 * (lx0 * __ldg(p00 + e) + lx1 * __ldg(p01 + e)) + ly1 * (lx0 * __ldg(p10 + e) + lx1 * __ldg(p11 + e));
   }
-  const int cc = c_offset + c;
-  const size_t o = ((((size_t)b * C8 + (cc >> 3)) * Ho + oy) * Wo + ox) * 8 + (cc & 7);
-  const __half h = __float2half_rn(v);
-  planes[o] = h;
-  planes[total + o] = __float2half_rn(v - __half2float(h));
+  __align__(16) __half hi[8];
+  __align__(16) __half lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    hi[e] = __float2half_rn(v[e]);
+    lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+  }
+  const size_t o = (((size_t)b * C8 + (c_offset >> 3) + cb) * hw + p_in) * 8;
+  *reinterpret_cast<uint4*>(planes + o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(planes + total + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
 static int make_halo_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C8, int halo_w, int halo_h, int kc8) {
@@ -394,7 +416,8 @@ extern "C" int dvmvs_split_blocked(const float* x, void* planes, int B, int H, i
   DVMVS_REQUIRE(x && planes && B > 0 && H > 0 && W > 0 && C > 0 && C8 > 0, "split_blocked: bad argument");
   DVMVS_REQUIRE(c_offset >= 0 && c_cover >= C && c_offset + c_cover <= C8 * 8, "split_blocked: channel window [%d,+%d) outside %d",
                 c_offset, c_cover, C8 * 8);
-  const size_t total = (size_t)B * H * W * c_cover * (upsample2x ? 4 : 1);
+  DVMVS_REQUIRE(c_offset % 8 == 0, "split_blocked: c_offset must be a multiple of 8 (got %d)", c_offset);
+  const size_t total = (size_t)B * H * W * ((c_cover + 7) / 8) * (upsample2x ? 4 : 1);
   launch_k(split_blocked_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, (__half*)planes, B, H, W, C,
            C8, upsample2x, c_offset, c_cover);
   return check_launch("split_blocked_kernel");

@@ -336,7 +336,10 @@ def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, w
     Wout = (Win + 2 * pad - ptc.ksize) // ptc.stride + 1
     if block_n is None:
         tiles = B * ((Hout + 7) // 8) * ((Wout + 15) // 16)
-        if ptc.cout <= 32 or tiles < 16:
+        if ptc.cout >= 1024 and tiles < 16:
+            block_n = 128          # e.g. the ConvLSTM gate conv (Cout 2048 on an 8x8 map): amortise the activation tile over
+                                   # 128 output channels and let split-K over the taps provide the CTAs
+        elif ptc.cout <= 32 or tiles < 16:
             block_n = 32
         elif ptc.cout <= 64 or tiles < 64:
             block_n = 64
@@ -377,28 +380,32 @@ def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, w
 # ================================================================================================ halo (blocked-layout) path
 def split_blocked(sources):
     """sources: [(fp32 nhwc tensor, upsample)] -> blocked fp16 pair planes (2, B, C8, H', W', 8) of their channel
-    concatenation (torch.cat staged straight into the operand layout of conv_halo_kernel)."""
+    concatenation (torch.cat staged straight into the operand layout of conv_halo_kernel).  Every source starts on an
+    8-channel block boundary: narrow sources (the 1-channel depth, the RGB image) are padded to 8 with zero channels --
+    PackedConvHalo(pad_sources_to_8=True) lays the weights out the same way."""
     shapes = [(t.shape[1] * (2 if up else 1), t.shape[2] * (2 if up else 1)) for t, up in sources]
     B, (Ho, Wo) = sources[0][0].shape[0], shapes[0]
     if any(sh != (Ho, Wo) for sh in shapes):
         raise ValueError("split_blocked: spatial sizes differ: %s" % (shapes,))
-    c_total = sum(t.shape[3] for t, _ in sources)
-    C8 = (c_total + 7) // 8
+    C8 = sum((t.shape[3] + 7) // 8 for t, _ in sources)
     planes = torch.empty((2, B, C8, Ho, Wo, 8), dtype=torch.float16, device=sources[0][0].device)
     off = 0
-    for i, (t, up) in enumerate(sources):
+    for t, up in sources:
         C = t.shape[3]
-        cover = C if i + 1 < len(sources) else C8 * 8 - off
+        cover = (C + 7) // 8 * 8
         N.check(N.lib().dvmvs_split_blocked(t.data_ptr(), planes.data_ptr(), B, t.shape[1], t.shape[2], C, C8, 1 if up else 0, off, cover,
                                             _stream()), "split_blocked")
-        off += C
+        off += cover
     return planes
 
 
 class PackedConvHalo:
     """Weights for dvmvs_conv2d_halo in their shared-memory image [n-tile][group][ky][kx][kc/8][block_n][8] (fp16 hi / lo)."""
 
-    def __init__(self, pc, src_channels, device, kc=None, block_n=None):
+    def __init__(self, pc, src_channels, device, kc=None, block_n=None, concat_padded=False):
+        """src_channels: real channels of each source.  concat_padded=False: every source is its own blocked tensor
+        (kernel-level K-split).  concat_padded=True: the sources are staged by split_blocked() into ONE blocked tensor
+        in which each source starts on an 8-channel boundary."""
         k, cin, cout = pc.ksize, pc.cin, pc.cout
         assert sum(src_channels) == cin and pc.stride == 1
         self.kc = kc or (16 if k == 5 else 32)
@@ -406,6 +413,13 @@ class PackedConvHalo:
         kc, bn = self.kc, self.block_n
         w = pc.weight.detach().to("cpu", torch.float32)                    # [k][k][cin][cout]
         n_tiles = (cout + bn - 1) // bn
+        if concat_padded:                                                    # one operand tensor, sources padded to 8 channels
+            padded = torch.zeros(k, k, sum((c + 7) // 8 * 8 for c in src_channels), cout, dtype=torch.float32)
+            src_off, dst_off = 0, 0
+            for cr in src_channels:
+                padded[:, :, dst_off:dst_off + cr, :] = w[:, :, src_off:src_off + cr, :]
+                src_off, dst_off = src_off + cr, dst_off + (cr + 7) // 8 * 8
+            w, src_channels = padded, [padded.shape[2]]
         groups = []                                                          # (cin offset, valid channels) per kc-group
         self.src_c8 = []
         off = 0
@@ -470,7 +484,7 @@ _BACKEND = _os.environ.get("DVMVS_CONV_BACKEND", "fp32")     # "fp32": CUDA-core
 _TC_TERMS = int(_os.environ.get("DVMVS_TC_TERMS", "3"))
 _TC_STRIDE2 = _os.environ.get("DVMVS_TC_STRIDE2", "0") == "1"
 _HALO = _os.environ.get("DVMVS_HALO", "1") == "1"          # blocked-layout halo kernel for large stride-1 k>=3 convolutions
-_HALO_MIN_PIXELS = int(_os.environ.get("DVMVS_HALO_MIN_PIXELS", "1024"))
+_HALO_MIN_PIXELS = int(_os.environ.get("DVMVS_HALO_MIN_PIXELS", "4096"))   # >= 64x64 maps; smaller maps: split-K conv_tc
 
 
 def set_conv_backend(name, terms=None, stride2=None):
@@ -564,7 +578,7 @@ class ConvLayer:
         win = (a0.f32 if a0.f32 is not None else a0.planes[0]).shape[2] * (2 if m0 == N.SRC_UPSAMPLE2X else 1)
         if self.uses_halo(hin, win, residual_mode, aux):
             if self._phalo is None:
-                self._phalo = PackedConvHalo(pc, [pc.cin] if self.pack_sources else self.src_channels, pc.weight.device)
+                self._phalo = PackedConvHalo(pc, self.src_channels, pc.weight.device, concat_padded=self.pack_sources)
             # sources that already carry blocked planes (outputs of tensor-core layers on large maps) are used as they
             # are -- the kernel concatenates up to three sources along K; upsampled / fp32-only sources are staged
             if self.pack_sources:

@@ -489,7 +489,7 @@ def test_conv2d_halo_vs_torch_fp32(synth, case):
         ref = ref + res
     ref = F.relu(ref)
     pc = ops.PackedConv(w, bias, None, stride=1, act=N.ACT_RELU)
-    ph = ops.PackedConvHalo(pc, [cin], DEV)
+    ph = ops.PackedConvHalo(pc, [c for c, _ in srcs], DEV, concat_padded=True)
     blk = ops.split_blocked([(ops.to_nhwc(x.to(DEV)), up) for x, (c, up) in zip(xs, srcs)])
     f32, oblk, onhwc = ops.conv2d_halo([blk], ph, residual=None if res is None else ops.to_nhwc(res.to(DEV)), terms=terms,
                                        want_f32=True, want_blk=True, want_nhwc=True)

@@ -10,7 +10,7 @@ for (name, B, H, W, cin, Cout, k, kc) in [("refine.1", 1, 256, 256, 32, 32, 5, 1
     x = torch.from_numpy(synth.tensor("tl/x", (B, H, W, cin), seed=1)).to(DEV)
     w = torch.from_numpy(synth.tensor("tl/w", (Cout, cin, k, k), seed=2, scale=0.05))
     pc = ops.PackedConv(w, None, None, stride=1, act=N.ACT_RELU)
-    ph = ops.PackedConvHalo(pc, [cin], DEV, kc=kc)
+    ph = ops.PackedConvHalo(pc, [cin], DEV, kc=kc, concat_padded=True)
     blk = ops.split_blocked([(x, False)])
     n_cta = ((W + 7) // 8) * ((H + 15) // 16) * B
     for _ in range(3):

@@ -65,7 +65,7 @@ def main():
         if stride == 1 and k >= 3 and Cout <= 64 * 8:
             for kc in (16, 32):
                 try:
-                    ph = ops.PackedConvHalo(pc, [cin], DEV, kc=kc)
+                    ph = ops.PackedConvHalo(pc, chans, DEV, kc=kc, concat_padded=True)
                     blk = ops.split_blocked([(x, False) for x in xs])
                     th = timeit(lambda: ops.conv2d_halo([blk], ph, terms=terms, want_f32=True, want_blk=True, want_nhwc=False))
                     res.append("HALO kc%d %.1f" % (kc, th))
