@@ -149,7 +149,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     pipe = None
     if args.mode == "pipeline":
-        pipe = pipeline.PipelinedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
+        pipe = pipeline.PipelinedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=args.stages)
         pred = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         with torch.no_grad():
             for t in range(args.warmup):
@@ -298,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
                     ref, rpose, meas, mpose, K = stack_frame(clips_b, t)
                     fb.append((torch.from_numpy(ref).to(dev), torch.from_numpy(rpose).to(dev), [torch.from_numpy(x).to(dev) for x in meas],
                                [torch.from_numpy(p_).to(dev) for p_ in mpose], torch.from_numpy(K).to(dev)))
-                pb = pipeline.PipelinedFusionnet(mods, batch=EB, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
+                pb = pipeline.PipelinedFusionnet(mods, batch=EB, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=args.stages)
                 outb = torch.empty((EB, H, W), dtype=torch.float32, device=dev)
                 for t in range(4):
                     pb.submit(*fb[t], out=outb)
@@ -330,7 +330,7 @@ def run_ours(args, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.backend == "fp32" else "f16x2+f32acc", "data": "synthetic",
         "config": {"workload": WORKLOAD % B, "clips_per_gpu": B, "height": H, "width": W, "planes": D, "measurement_frames": M,
-                   "weights": "random-init (seeded) reference architecture", "mode": args.mode,
+                   "weights": "random-init (seeded) reference architecture", "mode": args.mode + (" (%d stages)" % args.stages if args.mode == "pipeline" else ""),
                    "conv_backend": args.backend + ("" if args.backend == "fp32" else " (tcgen05, fp16-pair operands x%d terms, fp32 accumulate)" % args.tc_terms), "l2": ("per-step working set (weights 138 MB + activations) exceeds the 126 MB L2; steps run back to back (pipelined)"
                           if args.mode == "pipeline" else "flushed (256 MiB write) between timed steps"),
                    "parallelism": "clip-sharded x%d, no data-path collective" % world, "host_loop_wall_ms_per_step": (wall1 - wall0) * 1e3 / args.steps},
@@ -411,6 +411,7 @@ def main():
                          "launch per kernel")
     ap.add_argument("--backend", default=os.environ.get("DVMVS_CONV_BACKEND", "tc"), choices=["tc", "fp32"])
     ap.add_argument("--tc-terms", type=int, default=3)
+    ap.add_argument("--stages", type=int, default=3, choices=[2, 3], help="pipeline depth of --mode pipeline")
     ap.add_argument("--extras", type=int, default=1, help="also measure sequential latency and batched throughput (0 to skip)")
     ap.add_argument("--extra-clips", type=int, default=8)
     ap.add_argument("--cpu-frames", type=int, default=6, help="frames of the bounded CPU-baseline sample")

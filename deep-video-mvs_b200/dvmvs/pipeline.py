@@ -209,12 +209,57 @@ class GraphedFusionnet:
         return self._out
 
 
+def _stage_fe(mods, slot):
+    """Stage 1 of 3: MnasNet trunk on the reference + measurement images stacked on the batch axis."""
+    stacked = torch.cat([slot["ref_image"]] + list(slot["meas_images"]), dim=0)
+    return mods["fe"](stacked)
+
+
+def _stage_mid(mods, slot, fe_out, min_depth, max_depth, n_depth_levels):
+    """Stage 2 of 3: feature pyramid, fused plane sweep, cost-volume encoder (still independent of the recurrent state)."""
+    B = slot["ref_image"].shape[0]
+    M = len(slot["meas_images"])
+    a2, a4, a8, a16 = mods["fpn"](*fe_out)
+    f2, f4, f8, f16 = a2[:B], a4[:B], a8[:B], a16[:B]
+    meas_half = [a2[(m + 1) * B:(m + 2) * B] for m in range(M)]
+    half_K = slot["full_K"].clone()
+    half_K[:, 0:2, :] = half_K[:, 0:2, :] / 2.0
+    cv = cost_volume_fusion(image1=f2, image2s=meas_half, pose1=slot["ref_pose"], pose2s=slot["meas_poses"], K=half_K, warp_grid=None,
+                            min_depth=min_depth, max_depth=max_depth, n_depth_levels=n_depth_levels, device=f2.device, dot_product=True)
+    enc = mods["cve"](features_half=f2, features_quarter=f4, features_one_eight=f8, features_one_sixteen=f16, cost_volume=cv)
+    return enc, half_K
+
+
+def _stage_rec(mods, state, slot, enc, half_K):
+    """Last stage: depth re-projection + ConvLSTM fusion + decoder -- the only part with a loop-carried dependence."""
+    s0, s1, s2, s3, bottom = enc
+    reference_image, reference_pose, full_K = slot["ref_image"], slot["ref_pose"], slot["full_K"]
+    B, _, H, W = reference_image.shape
+    lstm_K = full_K.clone()
+    lstm_K[:, 0:2, :] = lstm_K[:, 0:2, :] / 32.0
+    if state.previous_depth is not None:
+        de = get_non_differentiable_rectangle_depth_estimation(reference_pose_torch=reference_pose, measurement_pose_torch=state.previous_pose,
+                                                               previous_depth_torch=state.previous_depth, full_K_torch=full_K,
+                                                               half_K_torch=half_K, original_height=H, original_width=W)
+        de = de[:, :, ::16, ::16].contiguous()
+    else:
+        de = torch.zeros(size=(B, 1, H // 32, W // 32), device=reference_image.device)
+    state.lstm_state = mods["lstm"](current_encoding=bottom, current_state=state.lstm_state, previous_pose=state.previous_pose,
+                                    current_pose=reference_pose, estimated_current_depth=de, camera_matrix=lstm_K)
+    pred = mods["cvd"](reference_image, s0, s1, s2, s3, state.lstm_state[0])[0]
+    state.previous_depth = pred.view(B, 1, H, W)
+    state.previous_pose = reference_pose
+    return pred, state
+
+
 class PipelinedFusionnet:
-    """Throughput engine for ONE clip (or B clips batched): consecutive keyframes are software-pipelined over two CUDA
-    streams.  Stage A(t) = feature_stage (features + plane sweep: no dependence on the recurrent state) of keyframe t runs
-    concurrently with stage B(t-1) = recurrent_stage (encoder, ConvLSTM, decoder) of the previous keyframe; each stage is
-    a captured CUDA graph over double-buffered static tensors.  Results are identical to GraphedFusionnet / keyframe():
-    the per-keyframe dataflow is unchanged, only independent work of neighbouring keyframes overlaps.
+    """Throughput engine for ONE clip (or B clips batched): consecutive keyframes are software-pipelined over CUDA streams.
+    Only the last stage (depth re-projection, ConvLSTM, decoder) depends on the previous keyframe; everything before it
+    -- n_stages=2: [FE + FPN + plane sweep | encoder + ConvLSTM + decoder]; n_stages=3 (default):
+    [FE | FPN + plane sweep + encoder | ConvLSTM + decoder] -- runs ahead for the following keyframes on its own stream.
+    Each (stage, slot) is a captured CUDA graph over n_stages-buffered static tensors.  Results are identical to
+    GraphedFusionnet / keyframe(): the per-keyframe dataflow is unchanged, only independent work of neighbouring
+    keyframes overlaps (tests/test_gpu_parity.py).
 
         eng = PipelinedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M)
         for frame in stream:  eng.submit(*frame, out=pinned_host_tensor_or_None)
@@ -222,75 +267,84 @@ class PipelinedFusionnet:
     """
 
     def __init__(self, mods, batch, height, width, n_measurement_frames, min_depth=0.25, max_depth=20.0, n_depth_levels=64,
-                 device=None):
+                 device=None, n_stages=3):
+        if n_stages not in (2, 3):
+            raise ValueError("n_stages must be 2 or 3")
         self.mods, self.B, self.H, self.W, self.M = mods, batch, height, width, n_measurement_frames
         self.min_depth, self.max_depth, self.D = min_depth, max_depth, n_depth_levels
         dev = device or next(mods["fe"].parameters()).device
         self.device = dev
+        self.n_stages = n_stages
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
         self.slots = []
-        for _ in range(2):
+        for _ in range(n_stages):
             self.slots.append({"ref_image": z(batch, 3, height, width), "ref_pose": z(batch, 4, 4), "full_K": z(batch, 3, 3),
                                "meas_images": [z(batch, 3, height, width) for _ in range(n_measurement_frames)],
                                "meas_poses": [z(batch, 4, 4) for _ in range(n_measurement_frames)],
-                               "features": None, "depth": z(batch, height, width), "graph_a": None, "graph_b": {},
-                               "a_done": torch.cuda.Event(), "b_done": torch.cuda.Event()})
-        self.stream_a, self.stream_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+                               "out": [None] * n_stages, "depth": z(batch, height, width),
+                               "graph": [dict() for _ in range(n_stages)],
+                               "done": [torch.cuda.Event() for _ in range(n_stages)]})
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_stages)]
+        self.stream_a, self.stream_b = self.streams[0], self.streams[-1]      # first / last stage (timing hooks)
         self._static_state = None
         self._has_state = False
         self.t = 0
+        self._kernels = [0] * n_stages
         self.kernels_per_keyframe = 0
 
     def reset(self):
         self._has_state = False
 
-    # -- capture helpers ------------------------------------------------------------------------------------------
-    def _run_a(self, slot):
-        return feature_stage(self.mods, slot["ref_image"], slot["ref_pose"], slot["meas_images"], slot["meas_poses"], slot["full_K"],
-                             self.min_depth, self.max_depth, self.D)
-
-    def _run_b(self, slot, with_state):
+    # -- stage bodies -----------------------------------------------------------------------------------------------
+    def _run_stage(self, i, slot, with_state):
+        last = self.n_stages - 1
+        if self.n_stages == 2:
+            if i == 0:
+                return feature_stage(self.mods, slot["ref_image"], slot["ref_pose"], slot["meas_images"], slot["meas_poses"],
+                                     slot["full_K"], self.min_depth, self.max_depth, self.D)
+        else:
+            if i == 0:
+                return _stage_fe(self.mods, slot)
+            if i == 1:
+                return _stage_mid(self.mods, slot, slot["out"][0], self.min_depth, self.max_depth, self.D)
         st = KeyframeState()
         if with_state:
             h, c, pd, pp = self._static_state
             st.lstm_state, st.previous_depth, st.previous_pose = (h, c), pd, pp
-        return recurrent_stage(self.mods, st, slot["features"], slot["ref_image"], slot["ref_pose"], slot["full_K"])
+        if self.n_stages == 2:
+            return recurrent_stage(self.mods, st, slot["out"][0], slot["ref_image"], slot["ref_pose"], slot["full_K"])
+        enc, half_K = slot["out"][last - 1]
+        return _stage_rec(self.mods, st, slot, enc, half_K)
 
-    def _capture_a(self, slot):
+    def _capture(self, i, slot, with_state):
         from . import _native
-        with torch.cuda.stream(self.stream_a), torch.no_grad():
+        last = self.n_stages - 1
+        stream = self.streams[i]
+        torch.cuda.synchronize(self.device)
+        saved = [t.clone() for t in self._static_state] if (i == last and self._static_state is not None) else None
+        with torch.cuda.stream(stream), torch.no_grad():
             for _ in range(2):
-                self._run_a(slot)
-        self.stream_a.synchronize()
+                res = self._run_stage(i, slot, with_state)
+        stream.synchronize()
+        if i == last and self._static_state is None:
+            pred, st = res
+            self._static_state = (st.lstm_state[0].clone(), st.lstm_state[1].clone(), st.previous_depth.clone(), slot["ref_pose"].clone())
         g = torch.cuda.CUDAGraph()
         n0 = _native.launch_count()
-        with torch.no_grad(), torch.cuda.graph(g, stream=self.stream_a):
-            slot["features"] = self._run_a(slot)
-        self._kernels_a = _native.launch_count() - n0
-        slot["graph_a"] = g
-
-    def _capture_b(self, slot, with_state):
-        from . import _native
-        saved = [t.clone() for t in self._static_state] if self._static_state is not None else None
-        with torch.cuda.stream(self.stream_b), torch.no_grad():
-            for _ in range(2):
-                pred, st = self._run_b(slot, with_state)
-        self.stream_b.synchronize()
-        if self._static_state is None:
-            self._static_state = (st.lstm_state[0].clone(), st.lstm_state[1].clone(), st.previous_depth.clone(),
-                                  slot["ref_pose"].clone())
-        g = torch.cuda.CUDAGraph()
-        n0 = _native.launch_count()
-        with torch.no_grad(), torch.cuda.graph(g, stream=self.stream_b):
-            pred, st = self._run_b(slot, with_state)
-            h, c, pd, pp = self._static_state
-            slot["depth"].copy_(pred)
-            h.copy_(st.lstm_state[0])
-            c.copy_(st.lstm_state[1])
-            pd.copy_(st.previous_depth)
-            pp.copy_(slot["ref_pose"])
-        self._kernels_b = _native.launch_count() - n0
-        slot["graph_b"][with_state] = g
+        with torch.no_grad(), torch.cuda.graph(g, stream=stream):
+            res = self._run_stage(i, slot, with_state)
+            if i == last:
+                pred, st = res
+                h, c, pd, pp = self._static_state
+                slot["depth"].copy_(pred)
+                h.copy_(st.lstm_state[0])
+                c.copy_(st.lstm_state[1])
+                pd.copy_(st.previous_depth)
+                pp.copy_(slot["ref_pose"])
+            else:
+                slot["out"][i] = res
+        self._kernels[i] = _native.launch_count() - n0
+        slot["graph"][i][with_state if i == last else False] = g
         if saved is not None:
             for dst, src in zip(self._static_state, saved):
                 dst.copy_(src)
@@ -299,40 +353,39 @@ class PipelinedFusionnet:
     # -- steady state ----------------------------------------------------------------------------------------------
     def submit(self, reference_image, reference_pose, measurement_images, measurement_poses, full_K, out=None):
         """Enqueue keyframe t (inputs CPU-pinned or CUDA).  If `out` (pinned host or CUDA tensor (B,H,W)) is given the
-        depth is copied into it on the recurrent stream; otherwise read eng.depth_of(t) after synchronisation."""
-        slot = self.slots[self.t & 1]
-        with torch.cuda.stream(self.stream_a):
-            self.stream_a.wait_event(slot["b_done"])            # slot reuse: keyframe t-2's recurrent stage has consumed it
-            slot["ref_image"].copy_(reference_image, non_blocking=True)
-            slot["ref_pose"].copy_(reference_pose, non_blocking=True)
-            slot["full_K"].copy_(full_K, non_blocking=True)
-            for dst, src in zip(slot["meas_images"], measurement_images):
-                dst.copy_(src, non_blocking=True)
-            for dst, src in zip(slot["meas_poses"], measurement_poses):
-                dst.copy_(src, non_blocking=True)
-            if slot["graph_a"] is None:
-                self.stream_a.synchronize()
-                self._capture_a(slot)
-            slot["graph_a"].replay()
-            slot["a_done"].record(self.stream_a)
+        depth is copied into it on the last stage's stream; otherwise read eng.depth_of(t) after synchronisation."""
+        n, last = self.n_stages, self.n_stages - 1
+        slot = self.slots[self.t % n]
         with_state = self._has_state
-        with torch.cuda.stream(self.stream_b):
-            self.stream_b.wait_event(slot["a_done"])
-            if with_state not in slot["graph_b"]:
-                torch.cuda.synchronize(self.device)
-                self._capture_b(slot, with_state)
-            slot["graph_b"][with_state].replay()
-            if out is not None:
-                out.copy_(slot["depth"], non_blocking=True)
-            slot["b_done"].record(self.stream_b)
+        for i in range(n):
+            stream = self.streams[i]
+            key = with_state if i == last else False
+            with torch.cuda.stream(stream):
+                if i == 0:
+                    stream.wait_event(slot["done"][last])         # slot reuse: keyframe t-n has left the pipeline
+                    slot["ref_image"].copy_(reference_image, non_blocking=True)
+                    slot["ref_pose"].copy_(reference_pose, non_blocking=True)
+                    slot["full_K"].copy_(full_K, non_blocking=True)
+                    for dst, src in zip(slot["meas_images"], measurement_images):
+                        dst.copy_(src, non_blocking=True)
+                    for dst, src in zip(slot["meas_poses"], measurement_poses):
+                        dst.copy_(src, non_blocking=True)
+                else:
+                    stream.wait_event(slot["done"][i - 1])
+                if key not in slot["graph"][i]:
+                    self._capture(i, slot, with_state)
+                slot["graph"][i][key].replay()
+                if i == last and out is not None:
+                    out.copy_(slot["depth"], non_blocking=True)
+                slot["done"][i].record(stream)
         self._has_state = True
-        self.kernels_per_keyframe = getattr(self, "_kernels_a", 0) + getattr(self, "_kernels_b", 0)
+        self.kernels_per_keyframe = sum(self._kernels)
         self.t += 1
         return self.t - 1
 
     def depth_of(self, t):
-        return self.slots[t & 1]["depth"]
+        return self.slots[t % self.n_stages]["depth"]
 
     def synchronize(self):
-        self.stream_a.synchronize()
-        self.stream_b.synchronize()
+        for s in self.streams:
+            s.synchronize()

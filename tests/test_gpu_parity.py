@@ -337,8 +337,9 @@ def test_pipeline_keyframe_and_cuda_graph_engine_match_script_sequence(oracle, s
     K = _cuda(clip["K"])[None]
     st_a, st_b = helpers.ProductState(), pipeline.KeyframeState()
     eng = pipeline.GraphedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
-    pipe = pipeline.PipelinedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
-    expected, piped = [], []
+    pipes = [pipeline.PipelinedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=ns)
+             for ns in (2, 3)]
+    expected, piped = [], [[], []]
     with torch.no_grad():
         for ref_i, meas_i in clip["frames"]:
             args = (_cuda(clip["images"][ref_i])[None], _cuda(clip["poses"][ref_i])[None], [_cuda(clip["images"][j])[None] for j in meas_i],
@@ -349,12 +350,15 @@ def test_pipeline_keyframe_and_cuda_graph_engine_match_script_sequence(oracle, s
             assert oracle.rel_l1_inverse_depth(b.cpu().numpy(), a.cpu().numpy()) <= 1e-6
             assert oracle.rel_l1_inverse_depth(c.cpu().numpy(), a.cpu().numpy()) <= 1e-6
             expected.append(a.cpu().numpy())
-            out = torch.empty((1, H, W), dtype=torch.float32, device=DEV)
-            pipe.submit(*args, out=out)          # asynchronous: keyframe t+1's feature stage overlaps this one's recurrent stage
-            piped.append(out)
-        pipe.synchronize()
-    for e, got in zip(expected, piped):
-        assert oracle.rel_l1_inverse_depth(got.cpu().numpy(), e) <= 1e-6
+            for pi, pipe in enumerate(pipes):    # asynchronous: later keyframes' early stages overlap this one's recurrent stage
+                out = torch.empty((1, H, W), dtype=torch.float32, device=DEV)
+                pipe.submit(*args, out=out)
+                piped[pi].append(out)
+        for pipe in pipes:
+            pipe.synchronize()
+    for pi in range(2):
+        for e, got in zip(expected, piped[pi]):
+            assert oracle.rel_l1_inverse_depth(got.cpu().numpy(), e) <= 1e-6, "pipeline with %d stages" % (pi + 2)
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 backend
