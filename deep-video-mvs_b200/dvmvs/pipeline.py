@@ -285,6 +285,9 @@ class PipelinedFusionnet:
                                "graph": [dict() for _ in range(n_stages)],
                                "done": [torch.cuda.Event() for _ in range(n_stages)]})
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_stages)]
+        import os as _os
+        if _os.environ.get("DVMVS_PIPE_SERIAL") == "1":        # debugging aid: all stages on one stream (no overlap)
+            self.streams = [self.streams[0]] * n_stages
         self.stream_a, self.stream_b = self.streams[0], self.streams[-1]      # first / last stage (timing hooks)
         self._static_state = None
         self._has_state = False
@@ -357,6 +360,15 @@ class PipelinedFusionnet:
         n, last = self.n_stages, self.n_stages - 1
         slot = self.slots[self.t % n]
         with_state = self._has_state
+        # the inputs were produced on the caller's stream: order the first stage after it and keep CUDA inputs alive
+        # (caching-allocator wise) until our copies on the stage stream have run
+        caller = torch.cuda.current_stream(self.device)
+        self.streams[0].wait_stream(caller)
+        for t_in in [reference_image, reference_pose, full_K] + list(measurement_images) + list(measurement_poses):
+            if t_in.is_cuda:
+                t_in.record_stream(self.streams[0])
+        if out is not None and out.is_cuda:
+            out.record_stream(self.streams[last])
         for i in range(n):
             stream = self.streams[i]
             key = with_state if i == last else False
