@@ -411,7 +411,7 @@ def main():
                          "launch per kernel")
     ap.add_argument("--backend", default=os.environ.get("DVMVS_CONV_BACKEND", "tc"), choices=["tc", "fp32"])
     ap.add_argument("--tc-terms", type=int, default=3)
-    ap.add_argument("--stages", type=int, default=3, choices=[2, 3], help="pipeline depth of --mode pipeline")
+    ap.add_argument("--stages", type=int, default=3, choices=[2, 3, 4, 5], help="pipeline depth of --mode pipeline")
     ap.add_argument("--extras", type=int, default=1, help="also measure sequential latency and batched throughput (0 to skip)")
     ap.add_argument("--extra-clips", type=int, default=8)
     ap.add_argument("--cpu-frames", type=int, default=6, help="frames of the bounded CPU-baseline sample")

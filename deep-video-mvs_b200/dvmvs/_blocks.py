@@ -164,7 +164,8 @@ class FeatureExtractor(NativeModule):
             levels.append(blocks)
         return stem, levels
 
-    def run(self, x, image_nchw=None):
+    def run(self, x, image_nchw=None, part="all"):
+        """part: "all" -> [layer1..layer5]; "head" -> [layer1, layer2, layer3]; "tail" (x = layer3 Act) -> [layer4, layer5]."""
         stem, levels = self.packed()
         def depthwise(t, dw, consumer):
             # the depthwise output feeds exactly one pointwise conv: hand it the operand format that conv reads
@@ -172,14 +173,16 @@ class FeatureExtractor(NativeModule):
                 return ops.Act(None, ops.dwconv2d(t.f32, dw, want_f32=False, want_planes=True)[1])
             return ops.Act(ops.dwconv2d(t.f32, dw))
 
-        if image_nchw is not None:        # dedicated stem kernel reads the NCHW image directly (no layout pass)
-            x = ops.Act(ops.stem_conv(image_nchw, stem[0].pc))
-        else:
-            x = stem[0].run([(x, D)])
-        x = depthwise(x, stem[1], stem[2])
-        x = stem[2].run([(x, D)])
-        outs = [x]
-        for blocks in levels:
+        outs = []
+        if part != "tail":
+            if image_nchw is not None:        # dedicated stem kernel reads the NCHW image directly (no layout pass)
+                x = ops.Act(ops.stem_conv(image_nchw, stem[0].pc))
+            else:
+                x = stem[0].run([(x, D)])
+            x = depthwise(x, stem[1], stem[2])
+            x = stem[2].run([(x, D)])
+            outs = [x]
+        for blocks in {"all": levels, "head": levels[:2], "tail": levels[2:]}[part]:
             for expand, dw, project, residual in blocks:
                 y = depthwise(expand.run([(x, D)], want_planes=False), dw, project)
                 x = project.run([(y, D)], residual=x if residual else None,
@@ -195,6 +198,16 @@ class FeatureExtractor(NativeModule):
         if image.is_contiguous():
             return tuple(ops.act_to_api(t) for t in self.run(None, image_nchw=image))
         return tuple(ops.act_to_api(t) for t in self.run(ops.to_act(image, "image")))
+
+    def forward_head(self, image):
+        """layer1..layer3 only (pipeline engines split the trunk here); forward_tail(head) completes it."""
+        ops.require_cuda_f32(image, "image")
+        return tuple(ops.act_to_api(t) for t in self.run(None, image_nchw=image.contiguous(), part="head"))
+
+    def forward_tail(self, head):
+        l1, l2, l3 = head
+        tail = self.run(ops.to_act(l3, "layer3"), part="tail")
+        return (l1, l2, l3) + tuple(ops.act_to_api(t) for t in tail)
 
 
 class _FPNHolder(torch.nn.Module):

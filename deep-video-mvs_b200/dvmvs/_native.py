@@ -18,7 +18,7 @@ SWEEP_DOT, SWEEP_SAD = 0, 1
 EXPORTED_SYMBOLS = [
     "dvmvs_abi_version", "dvmvs_last_error_string", "dvmvs_kernel_launch_count", "dvmvs_plane_sweep_fused",
     "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_conv2d_halo", "dvmvs_split_blocked", "dvmvs_split_planes", "dvmvs_stem_conv", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
-    "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw",
+    "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw", "dvmvs_preprocess_rgb",
 ]
 
 
@@ -108,6 +108,7 @@ def lib():
         L.dvmvs_dwconv2d.argtypes = [p, p, p, p, p, i, i, i, i, i, i, i, p]
         L.dvmvs_lstm_gates.argtypes = [p, p, p, p, i, i, i, i, p]
         L.dvmvs_upsample2x.argtypes = [p, p, i, i, i, i, p]
+        L.dvmvs_preprocess_rgb.argtypes = [p, i, i, i, i, i, i, p, i, i, i, f, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), p]
         L.dvmvs_nchw_to_nhwc.argtypes = [p, p, i, i, i, i, p]
         L.dvmvs_nhwc_to_nchw.argtypes = [p, p, i, i, i, i, p]
         _lib = L

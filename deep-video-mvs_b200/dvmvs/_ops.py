@@ -197,6 +197,31 @@ def plane_sweep(ref_nhwc, meas_nhwc_list, pose1, pose2_list, K, min_depth, max_d
     return out
 
 
+def preprocess_rgb(image_hwc, crop_x, crop_y, out_h, out_w, scale, mean, std, normalize=True, bgr=None, out=None):
+    """Device pre-processing of one decoded frame (dataset_loader.py:260-263,322-334 + run-testing.py:127): image_hwc is a
+    CUDA tensor (H,W,3), uint8 (as cv2.imread returns it: BGR unless bgr=False) or float32 (as load_image returns it: RGB
+    unless bgr=True).  Returns / fills a (1,3,out_h,out_w) fp32 tensor."""
+    if not image_hwc.is_cuda:
+        raise RuntimeError("preprocess_rgb: image must be a CUDA tensor (no CPU fallback; use PreprocessImage.apply_rgb on the host)")
+    if image_hwc.dim() != 3 or image_hwc.shape[2] != 3 or image_hwc.dtype not in (torch.uint8, torch.float32):
+        raise RuntimeError("preprocess_rgb: expected an (H,W,3) uint8 or float32 tensor, got %s %s" % (tuple(image_hwc.shape), image_hwc.dtype))
+    is_u8 = image_hwc.dtype == torch.uint8
+    if bgr is None:
+        bgr = is_u8
+    image_hwc = image_hwc.contiguous()
+    in_h, in_w = int(image_hwc.shape[0]), int(image_hwc.shape[1])
+    if out is None:
+        out = torch.empty((1, 3, int(out_h), int(out_w)), dtype=torch.float32, device=image_hwc.device)
+    elif tuple(out.shape) != (1, 3, int(out_h), int(out_w)) or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
+        raise RuntimeError("preprocess_rgb: out must be a contiguous CUDA fp32 (1,3,%d,%d) tensor" % (out_h, out_w))
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    N.check(N.lib().dvmvs_preprocess_rgb(image_hwc.data_ptr(), 1 if is_u8 else 0, 1 if bgr else 0, in_h, in_w, int(crop_x), int(crop_y),
+                                         out.data_ptr(), int(out_h), int(out_w), 1 if normalize else 0, float(scale), m3, s3, _stream()),
+            "preprocess_rgb")
+    return out
+
+
 def hidden_warp(h_nhwc, depth_b1hw, prev_pose, cur_pose, K, invalid_thresh):
     B, h, w, C = h_nhwc.shape
     depth = require_cuda_f32(depth_b1hw, "depth").contiguous()

@@ -1,12 +1,19 @@
 """Image loading / pre-processing names the reference's test drivers import (dvmvs/dataset_loader.py:260-346):
-load_image and PreprocessImage (crop, INTER_LINEAR resize, mean/std normalisation, intrinsics rescale).  Host-side,
-adjacent to the hot path; MVSDataset (training crawler) is out of scope."""
+load_image and PreprocessImage (crop, INTER_LINEAR resize, mean/std normalisation, intrinsics rescale).  The reference's
+methods stay host-side (same results as the reference: they call the same cv2 functions); `load_image_u8` +
+`PreprocessImage.apply_rgb_cuda` are the device path: upload the decoded uint8 frame once and
+do crop + resize + colour order + normalisation + CHW in one kernel.  MVSDataset (training crawler) is out of scope."""
 import cv2
 import numpy as np
 
 
 def load_image(path):
     return cv2.cvtColor(cv2.imread(str(path), cv2.IMREAD_COLOR).astype(np.float32), cv2.COLOR_BGR2RGB)
+
+
+def load_image_u8(path):
+    """The decoded frame as cv2 returns it ((H,W,3) uint8, BGR) -- input of PreprocessImage.apply_rgb_cuda."""
+    return cv2.imread(str(path), cv2.IMREAD_COLOR)
 
 
 class PreprocessImage:
@@ -44,6 +51,14 @@ class PreprocessImage:
             for c in range(3):
                 out[:, :, c] = (out[:, :, c] - mean_rgb[c]) / std_rgb[c]
         return out
+
+    def apply_rgb_cuda(self, image, scale_rgb, mean_rgb, std_rgb, normalize_colors=True, out=None):
+        """Device version of apply_rgb + the script's transpose / float / upload (fusionnet/run-testing.py:122-127).
+        image: CUDA tensor (H,W,3) -- uint8 BGR (cv2.imread / load_image_u8) or float32 RGB (load_image).  Returns the
+        (1,3,new_height,new_width) fp32 CUDA tensor the modules take.  Work is enqueued on the current stream."""
+        from . import _ops
+        return _ops.preprocess_rgb(image, self.crop_x, self.crop_y, self.new_height, self.new_width, scale_rgb, mean_rgb, std_rgb,
+                                   normalize=normalize_colors, out=out)
 
     def get_updated_intrinsics(self):
         return np.array([[self.fx, 0, self.cx], [0, self.fy, self.cy], [0, 0, 1]])

@@ -215,8 +215,19 @@ def _stage_fe(mods, slot):
     return mods["fe"](stacked)
 
 
-def _stage_mid(mods, slot, fe_out, min_depth, max_depth, n_depth_levels):
-    """Stage 2 of 3: feature pyramid, fused plane sweep, cost-volume encoder (still independent of the recurrent state)."""
+def _stage_fe_head(mods, slot):
+    """MnasNet trunk up to layer3 (1/8 resolution) on the stacked images."""
+    stacked = torch.cat([slot["ref_image"]] + list(slot["meas_images"]), dim=0)
+    return mods["fe"].forward_head(stacked)
+
+
+def _stage_fe_tail(mods, slot, head):
+    """MnasNet layers 4-5 (1/16, 1/32 resolution) from the head's outputs."""
+    return mods["fe"].forward_tail(head)
+
+
+def _stage_sweep(mods, slot, fe_out, min_depth, max_depth, n_depth_levels):
+    """Feature pyramid + fused plane sweep."""
     B = slot["ref_image"].shape[0]
     M = len(slot["meas_images"])
     a2, a4, a8, a16 = mods["fpn"](*fe_out)
@@ -226,8 +237,19 @@ def _stage_mid(mods, slot, fe_out, min_depth, max_depth, n_depth_levels):
     half_K[:, 0:2, :] = half_K[:, 0:2, :] / 2.0
     cv = cost_volume_fusion(image1=f2, image2s=meas_half, pose1=slot["ref_pose"], pose2s=slot["meas_poses"], K=half_K, warp_grid=None,
                             min_depth=min_depth, max_depth=max_depth, n_depth_levels=n_depth_levels, device=f2.device, dot_product=True)
+    return (f2, f4, f8, f16, cv), half_K
+
+
+def _stage_enc(mods, slot, swept):
+    """Cost-volume encoder (still independent of the recurrent state)."""
+    (f2, f4, f8, f16, cv), half_K = swept
     enc = mods["cve"](features_half=f2, features_quarter=f4, features_one_eight=f8, features_one_sixteen=f16, cost_volume=cv)
     return enc, half_K
+
+
+def _stage_mid(mods, slot, fe_out, min_depth, max_depth, n_depth_levels):
+    """Feature pyramid, fused plane sweep, cost-volume encoder."""
+    return _stage_enc(mods, slot, _stage_sweep(mods, slot, fe_out, min_depth, max_depth, n_depth_levels))
 
 
 def _stage_rec(mods, state, slot, enc, half_K):
@@ -256,7 +278,8 @@ class PipelinedFusionnet:
     """Throughput engine for ONE clip (or B clips batched): consecutive keyframes are software-pipelined over CUDA streams.
     Only the last stage (depth re-projection, ConvLSTM, decoder) depends on the previous keyframe; everything before it
     -- n_stages=2: [FE + FPN + plane sweep | encoder + ConvLSTM + decoder]; n_stages=3 (default):
-    [FE | FPN + plane sweep + encoder | ConvLSTM + decoder] -- runs ahead for the following keyframes on its own stream.
+    [FE | FPN + plane sweep + encoder | ConvLSTM + decoder]; 4 and 5 split the MnasNet trunk at layer3 and (5) the
+    encoder off the plane sweep -- runs ahead for the following keyframes on its own stream.
     Each (stage, slot) is a captured CUDA graph over n_stages-buffered static tensors.  Results are identical to
     GraphedFusionnet / keyframe(): the per-keyframe dataflow is unchanged, only independent work of neighbouring
     keyframes overlaps (tests/test_gpu_parity.py).
@@ -268,8 +291,8 @@ class PipelinedFusionnet:
 
     def __init__(self, mods, batch, height, width, n_measurement_frames, min_depth=0.25, max_depth=20.0, n_depth_levels=64,
                  device=None, n_stages=3):
-        if n_stages not in (2, 3):
-            raise ValueError("n_stages must be 2 or 3")
+        if n_stages not in (2, 3, 4, 5):
+            raise ValueError("n_stages must be 2, 3, 4 or 5")
         self.mods, self.B, self.H, self.W, self.M = mods, batch, height, width, n_measurement_frames
         self.min_depth, self.max_depth, self.D = min_depth, max_depth, n_depth_levels
         dev = device or next(mods["fe"].parameters()).device
@@ -284,8 +307,11 @@ class PipelinedFusionnet:
                                "out": [None] * n_stages, "depth": z(batch, height, width),
                                "graph": [dict() for _ in range(n_stages)],
                                "done": [torch.cuda.Event() for _ in range(n_stages)]})
-        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_stages)]
         import os as _os
+        # the last stage carries the loop dependence (keyframe t+1's ConvLSTM needs keyframe t's state and depth), so its
+        # kernels go first when several stages compete for SMs
+        prio = _os.environ.get("DVMVS_PIPE_PRIO", "1") == "1"
+        self.streams = [torch.cuda.Stream(device=dev, priority=(-1 if (prio and i == n_stages - 1) else 0)) for i in range(n_stages)]
         if _os.environ.get("DVMVS_PIPE_SERIAL") == "1":        # debugging aid: all stages on one stream (no overlap)
             self.streams = [self.streams[0]] * n_stages
         self.stream_a, self.stream_b = self.streams[0], self.streams[-1]      # first / last stage (timing hooks)
@@ -301,15 +327,29 @@ class PipelinedFusionnet:
     # -- stage bodies -----------------------------------------------------------------------------------------------
     def _run_stage(self, i, slot, with_state):
         last = self.n_stages - 1
+        prev = slot["out"][i - 1] if i > 0 else None
+        depth_args = (self.min_depth, self.max_depth, self.D)
         if self.n_stages == 2:
             if i == 0:
                 return feature_stage(self.mods, slot["ref_image"], slot["ref_pose"], slot["meas_images"], slot["meas_poses"],
                                      slot["full_K"], self.min_depth, self.max_depth, self.D)
-        else:
-            if i == 0:
+        elif i < last:
+            # stage plans (all stages before the last are independent of the recurrent state):
+            #   3: FE | FPN + sweep + encoder | rec        4: FE head | FE tail | FPN + sweep + encoder | rec
+            #   5: FE head | FE tail | FPN + sweep | encoder | rec
+            plan = {3: ("fe", "mid"), 4: ("head", "tail", "mid"), 5: ("head", "tail", "sweep", "enc")}[self.n_stages]
+            kind = plan[i]
+            if kind == "fe":
                 return _stage_fe(self.mods, slot)
-            if i == 1:
-                return _stage_mid(self.mods, slot, slot["out"][0], self.min_depth, self.max_depth, self.D)
+            if kind == "head":
+                return _stage_fe_head(self.mods, slot)
+            if kind == "tail":
+                return _stage_fe_tail(self.mods, slot, prev)
+            if kind == "mid":
+                return _stage_mid(self.mods, slot, prev, *depth_args)
+            if kind == "sweep":
+                return _stage_sweep(self.mods, slot, prev, *depth_args)
+            return _stage_enc(self.mods, slot, prev)
         st = KeyframeState()
         if with_state:
             h, c, pd, pp = self._static_state

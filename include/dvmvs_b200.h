@@ -199,6 +199,17 @@ int dvmvs_lstm_gates(const float* gates, const float* c_in, float* h_out, float*
 /* x2 bilinear upsampling, align_corners=True (F.interpolate at dvmvs/fusionnet/model.py:59,114,293-294). */
 int dvmvs_upsample2x(const float* x, float* y, int B, int H, int W, int C, dvmvs_stream_t stream);
 
+/* Image pre-processing on the device: replaces the per-image host work of the test drivers -- load_image's float
+ * conversion + BGR->RGB (dvmvs/dataset_loader.py:260-263), PreprocessImage.apply_rgb's crop + cv2.INTER_LINEAR
+ * resize + /scale + (x-mean)/std (dvmvs/dataset_loader.py:322-334) and the HWC->CHW transpose + upload of
+ * fusionnet/run-testing.py:127.
+ * image: DEVICE pointer, [in_h][in_w][3] interleaved, uint8 (is_u8 = 1, what cv2.imread returns) or fp32;
+ * swap_rb = 1 when the input is BGR.  crop_x / crop_y are removed on both sides before resizing to out_h x out_w.
+ * out: DEVICE fp32 [3][out_h][out_w] (RGB planes).  mean3 / std3: HOST arrays of 3 floats (copied into the launch). */
+int dvmvs_preprocess_rgb(const void* image, int is_u8, int swap_rb, int in_h, int in_w, int crop_x, int crop_y, float* out,
+                         int out_h, int out_w, int normalize, float scale, const float* mean3, const float* std3,
+                         dvmvs_stream_t stream);
+
 /* Layout helpers: NCHW <-> NHWC fp32 copies. */
 int dvmvs_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, dvmvs_stream_t stream);
 int dvmvs_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, dvmvs_stream_t stream);

@@ -30,6 +30,16 @@ for backend in ("fp32", "tc"):
                                          T(clip["K"])[None], n_depth_levels=D, batch_features=batch_features)
             assert tuple(pred.shape) == (1, H, W), pred.shape
             assert tuple(st.lstm_state[0].shape) == (1, 512, H // 32, W // 32)
+    # the pipeline engine's stage functions (split MnasNet trunk, sweep / encoder split) compose to a keyframe
+    T = torch.from_numpy
+    ref_i, meas_i = clip["frames"][0]
+    slot = {"ref_image": T(clip["images"][ref_i])[None], "ref_pose": T(clip["poses"][ref_i])[None], "full_K": T(clip["K"])[None],
+            "meas_images": [T(clip["images"][j])[None] for j in meas_i], "meas_poses": [T(clip["poses"][j])[None] for j in meas_i]}
+    fe = pipeline._stage_fe_tail(mods, slot, pipeline._stage_fe_head(mods, slot))
+    assert [tuple(t.shape[1:]) for t in fe] == [(16, H // 2, W // 2), (24, H // 4, W // 4), (40, H // 8, W // 8), (96, H // 16, W // 16), (320, H // 32, W // 32)]
+    enc, half_K = pipeline._stage_enc(mods, slot, pipeline._stage_sweep(mods, slot, fe, 0.25, 20.0, D))
+    pred, _ = pipeline._stage_rec(mods, pipeline.KeyframeState(), slot, enc, half_K)
+    assert tuple(pred.shape) == (1, H, W)
 print("dryrun ok")
 """
 

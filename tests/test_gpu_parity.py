@@ -338,8 +338,8 @@ def test_pipeline_keyframe_and_cuda_graph_engine_match_script_sequence(oracle, s
     st_a, st_b = helpers.ProductState(), pipeline.KeyframeState()
     eng = pipeline.GraphedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
     pipes = [pipeline.PipelinedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=ns)
-             for ns in (2, 3)]
-    expected, piped = [], [[], []]
+             for ns in (2, 3, 4, 5)]
+    expected, piped = [], [[] for _ in pipes]
     with torch.no_grad():
         for ref_i, meas_i in clip["frames"]:
             args = (_cuda(clip["images"][ref_i])[None], _cuda(clip["poses"][ref_i])[None], [_cuda(clip["images"][j])[None] for j in meas_i],
@@ -356,7 +356,7 @@ def test_pipeline_keyframe_and_cuda_graph_engine_match_script_sequence(oracle, s
                 piped[pi].append(out)
         for pipe in pipes:
             pipe.synchronize()
-    for pi in range(2):
+    for pi in range(len(pipes)):
         for e, got in zip(expected, piped[pi]):
             assert oracle.rel_l1_inverse_depth(got.cpu().numpy(), e) <= 1e-6, "pipeline with %d stages" % (pi + 2)
 
@@ -502,3 +502,67 @@ def test_conv2d_halo_vs_torch_fp32(synth, case):
     assert rel_err(ops.to_api(nh).cpu().numpy(), ref.numpy()) <= max(tol, 1e-5), name
     bl = (oblk[0].float() + oblk[1].float()).permute(0, 1, 4, 2, 3).reshape(B, Cout, H, W)     # (B,C8,H,W,8) -> (B,C,H,W)
     assert rel_err(bl.cpu().numpy(), ref.numpy()) <= max(tol, 1e-5), name
+
+
+# ------------------------------------------------------------------------------------------------ device pre-processing (f2)
+PREP_CASES = [  # name, in_h, in_w, out_h, out_w, distortion_crop, perform_crop
+    ("hololens_480x640_to_256x256_crop", 480, 640, 256, 256, 0, True),
+    ("fixture_540x960_to_256x320_crop", 540, 960, 256, 320, 0, True),
+    ("tall_640x480_to_256x320_crop10", 640, 480, 256, 320, 10, True),
+    ("no_crop_downscale", 480, 640, 256, 320, 0, False),
+    ("upscale_96x128_to_256x320", 96, 128, 256, 320, 0, False),
+    ("identity_64x96", 64, 96, 64, 96, 0, False),
+    ("odd_ratio_231x317_to_64x96", 231, 317, 64, 96, 3, True),
+]
+
+
+@pytest.mark.parametrize("case", PREP_CASES, ids=[c[0] for c in PREP_CASES])
+def test_device_preprocessing_vs_cv2_host_path(case):
+    """PreprocessImage.apply_rgb_cuda (one kernel on the decoded uint8 frame) against the reference's host sequence
+    load_image -> PreprocessImage.apply_rgb -> transpose (dataset_loader.py:260-263,322-334, run-testing.py:122-127), which
+    this package's host methods reproduce with the same cv2 calls.  fp32 both sides; OpenCV's SIMD path may fuse one
+    multiply-add, so the bound is a few ulp of a 0..255 value after normalisation."""
+    import cv2
+    from dvmvs.dataset_loader import PreprocessImage
+    _, in_h, in_w, out_h, out_w, dcrop, crop = case
+    rng = np.random.default_rng(in_h * 1000 + in_w)
+    bgr = rng.integers(0, 256, size=(in_h, in_w, 3), dtype=np.uint8)
+    bgr[: in_h // 2] = cv2.GaussianBlur(bgr[: in_h // 2], (9, 9), 3.0)          # smooth half + noise half
+    K = np.array([[0.9 * in_w, 0, in_w / 2], [0, 0.9 * in_w, in_h / 2], [0, 0, 1]])
+    pre = PreprocessImage(K=K, old_width=in_w, old_height=in_h, new_width=out_w, new_height=out_h, distortion_crop=dcrop, perform_crop=crop)
+    scale, mean, std = 255.0, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    rgb_f32 = cv2.cvtColor(bgr.astype(np.float32), cv2.COLOR_BGR2RGB)           # == load_image
+    want = np.transpose(pre.apply_rgb(image=rgb_f32, scale_rgb=scale, mean_rgb=mean, std_rgb=std), (2, 0, 1))[None]
+    got_u8 = pre.apply_rgb_cuda(torch.from_numpy(bgr).to(DEV), scale, mean, std)
+    got_f32 = pre.apply_rgb_cuda(torch.from_numpy(rgb_f32).to(DEV), scale, mean, std)
+    assert tuple(got_u8.shape) == (1, 3, out_h, out_w) and got_u8.dtype == torch.float32
+    for got in (got_u8, got_f32):
+        assert np.abs(got.cpu().numpy() - want).max() <= 2e-6 * 4.5            # |normalised value| <= ~2.7
+    raw = pre.apply_rgb_cuda(torch.from_numpy(bgr).to(DEV), scale, mean, std, normalize_colors=False)
+    want_raw = np.transpose(pre.apply_rgb(image=rgb_f32, scale_rgb=scale, mean_rgb=mean, std_rgb=std, normalize_colors=False), (2, 0, 1))[None]
+    assert np.abs(raw.cpu().numpy() - want_raw).max() <= 6.2e-5                 # 2 ulp at 255
+
+
+def test_device_preprocessing_feeds_the_network_like_the_host_path(oracle, synth):
+    """End to end: a keyframe computed from device-preprocessed frames equals the one from host-preprocessed frames."""
+    import cv2
+    from dvmvs import pipeline
+    from dvmvs.dataset_loader import PreprocessImage
+    H, W, D, M = 64, 96, 64, 2
+    w = helpers.oracle_weights(oracle, synth, 3, n_depth_levels=D)
+    mods = helpers.build_product_modules(w, n_depth_levels=D)
+    clip = synth.make_clip(2, 1, H, W, M)
+    rng = np.random.default_rng(5)
+    frames = [cv2.GaussianBlur(rng.integers(0, 256, size=(240, 320, 3), dtype=np.uint8), (7, 7), 2.0) for _ in range(M + 1)]
+    K0 = np.array([[290.0, 0, 160], [0, 290.0, 120], [0, 0, 1]])
+    pre = PreprocessImage(K=K0, old_width=320, old_height=240, new_width=W, new_height=H, distortion_crop=0, perform_crop=True)
+    scale, mean, std = 255.0, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    host = [_cuda(np.transpose(pre.apply_rgb(cv2.cvtColor(f.astype(np.float32), cv2.COLOR_BGR2RGB), scale, mean, std), (2, 0, 1)))[None] for f in frames]
+    dev = [pre.apply_rgb_cuda(torch.from_numpy(f).to(DEV), scale, mean, std) for f in frames]
+    K = _cuda(pre.get_updated_intrinsics().astype(np.float32))[None]
+    ref_i, meas_i = clip["frames"][0]
+    poses = [_cuda(clip["poses"][i])[None] for i in [ref_i] + list(meas_i)]
+    with torch.no_grad():
+        a, _ = pipeline.keyframe(mods, pipeline.KeyframeState(), host[0], poses[0], host[1:], poses[1:], K, n_depth_levels=D)
+        b, _ = pipeline.keyframe(mods, pipeline.KeyframeState(), dev[0], poses[0], dev[1:], poses[1:], K, n_depth_levels=D)
+    assert oracle.rel_l1_inverse_depth(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5

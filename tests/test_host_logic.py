@@ -131,3 +131,14 @@ def test_geometry_prologue_on_host_matches_numpy(synth):
         assert np.abs(out[:9].reshape(3, 3) - G).max() < 1e-4 and np.abs(out[9:] - Kt).max() < 1e-4
         q = G @ np.array([u, v, 1.0]) + Kt * (1 / 20.0 + d * (1 / 0.25 - 1 / 20.0) / 63)
         assert abs(xy[0] - q[0] / (q[2] + 1e-8) * 127 / 128) < 2e-3 and abs(xy[1] - q[1] / (q[2] + 1e-8) * 127 / 128) < 2e-3
+
+
+def test_device_preprocessing_refuses_host_tensors_and_bad_shapes():
+    """apply_rgb_cuda is the device path only: CPU tensors / wrong shapes raise instead of silently falling back."""
+    import numpy as np
+    import torch
+    from dvmvs.dataset_loader import PreprocessImage
+    pre = PreprocessImage(K=np.eye(3), old_width=64, old_height=48, new_width=32, new_height=32, distortion_crop=0, perform_crop=True)
+    assert (pre.crop_x, pre.crop_y) == (8, 0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pre.apply_rgb_cuda(torch.zeros(48, 64, 3, dtype=torch.uint8), 255.0, [0, 0, 0], [1, 1, 1])
