@@ -208,47 +208,50 @@ __global__ void conv_epilogue_kernel(ConvParams p) {
   if (d.aux_out) d.aux_out[idx] = 1.f / (d.aux_mult * v + d.aux_base);
 }
 
-// Single-output-channel 3x3 head (depth_layer_3x3): a quarter warp per output pixel, 128-byte channel reads.
+// Single-output-channel 3x3 head (depth_layer_3x3): LPP lanes per output pixel (a quarter warp on large maps, a whole
+// warp on the small ones, where the grid would otherwise be a handful of CTAs on the decoder's critical path), 16-byte
+// channel reads, the nine taps' loads issued back to back with three independent accumulators.
+template <int LPP>
 __global__ void __launch_bounds__(256) conv_head_kernel(ConvParams p) {
   pdl_launch_dependents();
   pdl_wait();
   const dvmvs_conv_desc& d = p.d;
+  constexpr int PPW = 32 / LPP;                 // pixels per warp
   const int lane = threadIdx.x & 31;
-  const int sub = lane & 7, quad = lane >> 3;
+  const int sub = lane % LPP, quad = lane / LPP;
   const size_t npix = (size_t)d.B * p.Hout * p.Wout;
-  const size_t pix = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + quad;
+  const size_t pix = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PPW + quad;
   const bool active = pix < npix;
   const size_t pc = active ? pix : 0;
   const int ox = (int)(pc % p.Wout);
   const int oy = (int)((pc / p.Wout) % p.Hout);
   const int b = (int)(pc / ((size_t)p.Wout * p.Hout));
   const int C = p.Cin;
-  float acc = 0.f;
+  float acc[3] = {0.f, 0.f, 0.f};
   if (active) {
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy + ky - 1;
-      if (iy < 0 || iy >= d.Hin) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox + kx - 1;
-        if (ix < 0 || ix >= d.Win) continue;
-        const float* xp = d.src[0] + (((size_t)b * d.Hin + iy) * d.Win + ix) * C;
-        const float* wp = d.weight + (size_t)(ky * 3 + kx) * C;
-        for (int c = sub * 4; c < C; c += 32) {
-          const float4 xv = __ldg(reinterpret_cast<const float4*>(xp + c));
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(wp + c));
-          acc = fmaf(xv.x, wv.x, acc);
-          acc = fmaf(xv.y, wv.y, acc);
-          acc = fmaf(xv.z, wv.z, acc);
-          acc = fmaf(xv.w, wv.w, acc);
+    unsigned mask = 0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int iy = oy + t / 3 - 1, ix = ox + t % 3 - 1;
+      if (iy >= 0 && iy < d.Hin && ix >= 0 && ix < d.Win) mask |= 1u << t;
+    }
+    const float* x0 = d.src[0] + (((size_t)b * d.Hin + oy) * d.Win + ox) * C;
+    for (int c = sub * 4; c < C; c += LPP * 4) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (mask & (1u << t)) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x0 + ((long long)(t / 3 - 1) * d.Win + (t % 3 - 1)) * C + c));
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(d.weight + (size_t)t * C + c));
+          acc[t % 3] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[t % 3]))));
         }
       }
     }
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  float a = acc[0] + acc[1] + acc[2];
+#pragma unroll
+  for (int o = 1; o < LPP; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
   if (active && sub == 0) {
-    float v = acc + (d.bias ? __ldg(d.bias) : 0.f);
+    float v = a + (d.bias ? __ldg(d.bias) : 0.f);
     v = apply_act(v, d.act);
     d.out[pix] = v;
     if (d.aux_out) d.aux_out[pix] = 1.f / (d.aux_mult * v + d.aux_base);
@@ -520,8 +523,11 @@ extern "C" int dvmvs_conv2d(const dvmvs_conv_desc* desc, dvmvs_stream_t stream) 
       d.residual_mode == DVMVS_RES_NONE && ((uintptr_t)d.src[0] % 16 == 0) && ((uintptr_t)d.weight % 16 == 0)) {
     p.ksplit = 1;
     const size_t npix = (size_t)d.B * p.Hout * p.Wout;
-    const unsigned blocks = (unsigned)((npix + 31) / 32);   // 8 warps x 4 pixels
-    launch_k(conv_head_kernel, dim3(blocks), dim3(256), 0, s, p);
+    if (npix <= 4096 && p.Cin >= 128) {                      // small map, many channels: a warp per pixel
+      launch_k(conv_head_kernel<32>, dim3((unsigned)((npix + 7) / 8)), dim3(256), 0, s, p);
+    } else {                                                 // 8 warps x 4 pixels
+      launch_k(conv_head_kernel<8>, dim3((unsigned)((npix + 31) / 32)), dim3(256), 0, s, p);
+    }
     return check_launch("conv_head_kernel");
   }
 

@@ -31,6 +31,7 @@ struct HaloParams {
   CUtensorMap a_map[3][2];     // [source][hi/lo]: 4-D {W*8, H, C8, B} over the blocked planes
   const __half* w_hi;          // packed weights, see header comment
   const __half* w_lo;
+  const __half* w_cat;         // TERMS == 2: hi and lo interleaved per 8-channel block, [..][kc/8][2][block_n][8]
   int src_groups[3];           // KC-channel groups per source
   int n_src, terms, ksize, pad, kc;           // kc: channels per group (16 or 32)
   int B, Hout, Wout, Cout, c8_out, tiles_x, tiles_y, n_groups;
@@ -95,7 +96,13 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  // TERMS == 2 ("concatenated" three-term product): the weight operand of a K step is the 2*BLOCK_N-row matrix
+  // [W_hi ; W_lo], so ONE MMA with the hi activations yields x_hi*w_hi (columns [0, BLOCK_N)) and x_hi*w_lo (columns
+  // [BLOCK_N, 2*BLOCK_N)); a second, BLOCK_N-wide MMA adds x_lo*w_hi to the first half; the epilogue sums the halves.
+  // Same three products as TERMS == 3 with two instead of three passes over the activation tile (the shared-memory read
+  // of the 128-row A operand is what bounds these small-N tiles) and two instead of three MMA issues.
+  constexpr bool CAT = (TERMS == 2);
+  constexpr int kTmemCols = CAT ? 2 * BLOCK_N : (BLOCK_N < 32 ? 32 : BLOCK_N);
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                  "n"(kTmemCols)
@@ -129,8 +136,12 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
             mbar_expect_tx(w_full(wst), planes * p.w_bytes);
             const size_t woff = ((((size_t)nt * p.n_groups + g) * p.ksize + ky) * (size_t)p.w_bytes) / sizeof(__half);
             const uint32_t wdst = w_base + wst * w_stage_bytes;
-            bulk_load(wdst, p.w_hi + woff, p.w_bytes, w_full(wst));
-            if (p.terms > 1) bulk_load(wdst + p.w_bytes, p.w_lo + woff, p.w_bytes, w_full(wst));
+            if (CAT) {
+              bulk_load(wdst, p.w_cat + 2 * woff, 2 * p.w_bytes, w_full(wst));
+            } else {
+              bulk_load(wdst, p.w_hi + woff, p.w_bytes, w_full(wst));
+              if (p.terms > 1) bulk_load(wdst + p.w_bytes, p.w_lo + woff, p.w_bytes, w_full(wst));
+            }
             if (++wst == kHaloWStages) { wst = 0; wphase ^= 1u; }
           }
         }
@@ -142,8 +153,10 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // all offsets below are in 16-byte units (the granularity of the descriptor's address field)
       const uint32_t a_chunk16 = (uint32_t)halo_h * halo_w;          // one 8-channel block of the halo tile
-      constexpr uint32_t w_chunk16 = BLOCK_N;                        // one 8-channel block of a weight tap: [BLOCK_N][8]
-      constexpr uint32_t w_tap16 = (KC / 8) * BLOCK_N;               // one tap: [KC/8][BLOCK_N][8]
+      constexpr uint32_t w_rows = CAT ? 2 * BLOCK_N : BLOCK_N;       // rows of the weight operand of one 8-channel block
+      constexpr uint32_t w_chunk16 = w_rows;                         // one 8-channel block of a weight tap: [w_rows][8]
+      constexpr uint32_t w_tap16 = (KC / 8) * w_rows;                // one tap: [KC/8][w_rows][8]
+      const uint32_t idesc_cat = (1u << 4) | ((uint32_t)((2 * BLOCK_N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t a_hi_word = umma_hi_word((uint32_t)halo_w * 16, 0);     // SBO = next tile row (next 8 GEMM rows)
       const uint32_t w_hi_word = umma_hi_word(128, 0);                        // SBO = next 8 output channels
       const uint32_t a_lbo = ((a_chunk16 & 0x3FFF) << 16), w_lbo = ((w_chunk16 & 0x3FFF) << 16);
@@ -164,14 +177,25 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
             const uint32_t a_row = (uint32_t)ky * halo_w;
 #pragma unroll
             for (int kx = 0; kx < KSIZE; ++kx) {
-#pragma unroll
-              for (int term = 0; term < TERMS; ++term) {
+              if constexpr (CAT) {
 #pragma unroll
                 for (int k2 = 0; k2 < KC / 16; ++k2) {
-                  const uint32_t a_lo = ((term == 1) ? a_plane1 : a_plane0) + a_row + kx + 2 * k2 * a_chunk16;
-                  const uint32_t w_lo = ((term == 2) ? w_plane1 : w_plane0) + kx * w_tap16 + 2 * k2 * w_chunk16;
-                  tc_mma_f16_words(tmem_base, a_lo, a_hi_word, w_lo, w_hi_word, idesc, accumulate);
+                  const uint32_t a_off = a_row + kx + 2 * k2 * a_chunk16;
+                  const uint32_t w_lo = w_plane0 + kx * w_tap16 + 2 * k2 * w_chunk16;
+                  tc_mma_f16_words(tmem_base, a_plane0 + a_off, a_hi_word, w_lo, w_hi_word, idesc_cat, accumulate);   // x_hi * [w_hi ; w_lo]
+                  tc_mma_f16_words(tmem_base, a_plane1 + a_off, a_hi_word, w_lo, w_hi_word, idesc, 1u);               // x_lo * w_hi
                   accumulate = 1;
+                }
+              } else {
+#pragma unroll
+                for (int term = 0; term < TERMS; ++term) {
+#pragma unroll
+                  for (int k2 = 0; k2 < KC / 16; ++k2) {
+                    const uint32_t a_lo = ((term == 1) ? a_plane1 : a_plane0) + a_row + kx + 2 * k2 * a_chunk16;
+                    const uint32_t w_lo = ((term == 2) ? w_plane1 : w_plane0) + kx * w_tap16 + 2 * k2 * w_chunk16;
+                    tc_mma_f16_words(tmem_base, a_lo, a_hi_word, w_lo, w_hi_word, idesc, accumulate);
+                    accumulate = 1;
+                  }
                 }
               }
             }
@@ -202,6 +226,12 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
     for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
       float v[8];
       tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if constexpr (CAT) {
+        float u[8];
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c0), u);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += u[e];
+      }
       const int cbase = n0 + c0;
       if (!valid || cbase >= p.Cout) continue;
       if (p.bias) {
@@ -342,6 +372,9 @@ static int launch_halo(const HaloParams& p, dim3 grid, size_t smem, cudaStream_t
 
 template <int BLOCK_N, int KSIZE>
 static int launch_halo_kt(const HaloParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+  if (p.terms == 3 && p.w_cat) {      // concatenated-weights form of the three-term product
+    return p.kc == 16 ? launch_halo<BLOCK_N, KSIZE, 16, 2>(p, grid, smem, s) : launch_halo<BLOCK_N, KSIZE, 32, 2>(p, grid, smem, s);
+  }
   if (p.kc == 16) return p.terms == 3 ? launch_halo<BLOCK_N, KSIZE, 16, 3>(p, grid, smem, s) : launch_halo<BLOCK_N, KSIZE, 16, 1>(p, grid, smem, s);
   return p.terms == 3 ? launch_halo<BLOCK_N, KSIZE, 32, 3>(p, grid, smem, s) : launch_halo<BLOCK_N, KSIZE, 32, 1>(p, grid, smem, s);
 }
@@ -398,6 +431,8 @@ extern "C" int dvmvs_conv2d_halo(const dvmvs_conv_halo_desc* d, dvmvs_stream_t s
   p.a_bytes = (uint32_t)(d->kc / 8) * halo_h * halo_w * 16;
   p.w_bytes = (uint32_t)d->ksize * (d->kc / 8) * d->block_n * 16;
   p.w_hi = (const __half*)d->w_hi; p.w_lo = (const __half*)d->w_lo;
+  p.w_cat = (d->terms == 3) ? (const __half*)d->w_cat : nullptr;
+  DVMVS_REQUIRE(!p.w_cat || (uintptr_t)p.w_cat % 16 == 0, "conv2d_halo: w_cat not 16-byte aligned");
   p.bias = d->bias; p.residual = d->residual; p.act = d->act;
   p.out_f32 = d->out_f32; p.out_blk = (__half*)d->out_blk; p.out_nhwc = (__half*)d->out_nhwc;
   p.dbg = (unsigned long long*)g_halo_dbg;

@@ -18,6 +18,7 @@
 //   smem ring of kStages stages, full/empty mbarriers, tcgen05.commit releases stages and signals the epilogue.
 // * Small-M layers (8x8 .. 16x16 maps) split K (filter taps) over blockIdx.z: every split publishes fp32 partial sums,
 //   a finishing kernel reduces them in split order (deterministic) and applies the epilogue.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_ptx.cuh"
@@ -48,6 +49,8 @@ struct TcParams {
   float aux_mult, aux_base;
   int act;
   float* workspace;           // split-K partial sums [ksplit][out elements]
+  int cluster_reduce;         // split-K splits form one thread-block cluster and reduce through distributed shared memory
+  int cat;                    // terms == 3 as two MMAs per K step: x_hi * [w_hi ; w_lo] (2*BLOCK_N columns) + x_lo * w_hi
   int num_stages, stage_bytes, a_bytes, w_bytes;   // smem ring geometry (runtime: sized by the widest K chunk in use)
 };
 
@@ -57,8 +60,58 @@ constexpr int kMaxSmemBytes = 227 * 1024;
 
 template <int BLOCK_N>
 struct TcCfg {
-  static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int kTmemCols = 2 * BLOCK_N;      // second half: the x_hi * w_lo product of the concatenated form
 };
+
+// bias / residual / activation and all requested output formats for 8 consecutive output channels of one pixel
+__device__ __forceinline__ void tc_emit8(const TcParams& p, float (&v)[8], int b, int oy, int ox, int cbase) {
+  const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
+  const size_t plane_stride = (size_t)p.B * p.Hout * p.Wout * p.Cout;
+  if (p.bias) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  const float* res_row = nullptr;
+  if (p.residual_mode == DVMVS_RES_SAME) {
+    res_row = p.residual + pix * p.Cout;
+  } else if (p.residual_mode == DVMVS_RES_NEAREST_UP) {
+    const int ry = (int)(((long long)oy * p.Hr) / p.Hout), rx = (int)(((long long)ox * p.Wr) / p.Wout);
+    res_row = p.residual + (((size_t)b * p.Hr + ry) * p.Wr + rx) * p.Cout;
+  }
+  if (res_row) {
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(res_row + cbase)), r1 = __ldg(reinterpret_cast<const float4*>(res_row + cbase + 4));
+    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = tc_act(v[e], p.act);
+  if (p.out_f32) {
+    float* o = p.out_f32 + pix * p.Cout + cbase;
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (p.aux_out) {
+    float* o = p.aux_out + pix * p.Cout + cbase;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 1.f / (p.aux_mult * v[e] + p.aux_base);
+  }
+  if (p.out_planes) {
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      hi[e] = __float2half_rn(v[e]);
+      lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+    }
+    __half* oh = p.out_planes + pix * p.Cout + cbase;
+    *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(oh + plane_stride) = *reinterpret_cast<const uint4*>(lo);
+    if (p.out_blk) {
+      __half* ob = p.out_blk + ((((size_t)b * (p.Cout >> 3) + (cbase >> 3)) * p.Hout + oy) * p.Wout + ox) * 8;
+      *reinterpret_cast<uint4*>(ob) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(ob + plane_stride) = *reinterpret_cast<const uint4*>(lo);
+    }
+  }
+}
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_constant__ TcParams p) {
@@ -132,7 +185,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             tma_load_2d(sb + off_w_hi, &p.w_map[kind][0], full_bar(stage), wk, n0);
             if (p.terms > 1) {
               tma_load_4d(sb + off_a_lo, &p.a_map[s][1], full_bar(stage), ch * kc, ix, iy, b);
-              tma_load_2d(sb + off_w_lo, &p.w_map[kind][1], full_bar(stage), wk, n0);
+              // concatenated form: the lo tile directly follows the hi tile, so both read as ONE 2*BLOCK_N-row operand
+              tma_load_2d(sb + (p.cat ? off_w_hi + w_bytes : off_w_lo), &p.w_map[kind][1], full_bar(stage), wk, n0);
             }
             if (++stage == n_stages) { stage = 0; phase ^= 1u; }
           }
@@ -144,6 +198,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     if (lane == 0) {
       // instruction descriptor: D=F32, A=B=F16, both K-major, N = BLOCK_N, M = 128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idesc_cat = (1u << 4) | ((uint32_t)((2 * BLOCK_N) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t accumulate = 0;
@@ -161,6 +216,16 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             // lo words: (address >> 4) | LBO(=1) << 16; a K step of 16 fp16 = 32 bytes = +2
             const uint32_t a_hi = umma_lo_word(sb, 16), a_lo = umma_lo_word(sb + off_a_lo, 16);
             const uint32_t w_hi = umma_lo_word(sb + off_w_hi, 16), w_lo = umma_lo_word(sb + off_w_lo, 16);
+            if (p.cat) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                  tc_mma_f16_words(tmem_base, a_hi + 2 * k, hi_word, w_hi + 2 * k, hi_word, idesc_cat, accumulate);   // x_hi * [w_hi ; w_lo]
+                  tc_mma_f16_words(tmem_base, a_lo + 2 * k, hi_word, w_hi + 2 * k, hi_word, idesc, 1u);               // x_lo * w_hi
+                  accumulate = 1;
+                }
+              }
+            } else
 #pragma unroll
             for (int term = 0; term < 3; ++term) {
               if (term < p.terms) {
@@ -209,51 +274,28 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
       float v[8];
       tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (p.cat) {
+        float u[8];
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c0), u);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += u[e];
+      }
       const int cbase = n0 + c0;
       if (!valid || cbase >= p.Cout) continue;
       if (vec8) {
-        if (split) {   // partial sums of this tap range; conv_tc_finish_kernel reduces the splits in fixed order
+        if (split) {
+          if (p.cluster_reduce) {   // partial tile -> own shared memory ([8-column group][row][8]); reduced across the cluster below
+            float4* st = reinterpret_cast<float4*>(base_ptr + ((size_t)(c0 >> 3) * kTileM + row) * 32);
+            st[0] = make_float4(v[0], v[1], v[2], v[3]);
+            st[1] = make_float4(v[4], v[5], v[6], v[7]);
+            continue;
+          }
+          // partial sums of this tap range; conv_tc_finish_kernel reduces the splits in fixed order
           *reinterpret_cast<float4*>(wsp_row + cbase) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(wsp_row + cbase + 4) = make_float4(v[4], v[5], v[6], v[7]);
           continue;
         }
-        if (p.bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + 4));
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        if (res_row) {
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(res_row + cbase)), r1 = __ldg(reinterpret_cast<const float4*>(res_row + cbase + 4));
-          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = tc_act(v[e], p.act);
-        if (p.out_f32) {
-          float* o = p.out_f32 + pix * p.Cout + cbase;
-          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (p.aux_out) {
-          float* o = p.aux_out + pix * p.Cout + cbase;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = 1.f / (p.aux_mult * v[e] + p.aux_base);
-        }
-        if (p.out_planes) {
-          __align__(16) __half hi[8];
-          __align__(16) __half lo[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            hi[e] = __float2half_rn(v[e]);
-            lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
-          }
-          __half* oh = p.out_planes + pix * p.Cout + cbase;
-          *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(hi);
-          *reinterpret_cast<uint4*>(oh + plane_stride) = *reinterpret_cast<const uint4*>(lo);
-          if (p.out_blk) {
-            __half* ob = p.out_blk + ((((size_t)b * (p.Cout >> 3) + (cbase >> 3)) * p.Hout + oy) * p.Wout + ox) * 8;
-            *reinterpret_cast<uint4*>(ob) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(ob + plane_stride) = *reinterpret_cast<const uint4*>(lo);
-          }
-        }
+        tc_emit8(p, v, b, oy, ox, cbase);
       } else {        // generic tail (Cout not a multiple of 8): scalar, rolled
 #pragma unroll 1
         for (int e = 0; e < 8; ++e) {
@@ -275,6 +317,31 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
       }
     }
     tc_fence_before();
+  }
+  if (p.cluster_reduce) {
+    // split-K over the CTAs of this cluster (blockIdx.z): every CTA has parked its fp32 partial tile in its own shared
+    // memory; CTA `rank` now sums (row, 8-column) units rank, rank + z, ... over all peers in rank order (deterministic,
+    // same order as conv_tc_finish_kernel) through distributed shared memory and runs the epilogue on them.
+    cluster_sync_all();
+    if (warp >= 2) {
+      const uint32_t z = (uint32_t)p.ksplit, rank = cluster_ctarank();
+      const int units = kTileM * (BLOCK_N >> 3);
+      for (int u = (int)rank + (int)z * (int)(threadIdx.x - 64); u < units; u += (int)z * 128) {
+        const int g = u >> 7, r = u & (kTileM - 1);
+        const int ty = r / p.tile_w, tx = r - ty * p.tile_w;
+        const int oy = oy0 + ty, ox = ox0 + tx, cbase = n0 + g * 8;
+        if (oy >= p.Hout || ox >= p.Wout || cbase >= p.Cout) continue;
+        const uint32_t local = base + (uint32_t)(g * kTileM + r) * 32u;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (uint32_t k = 0; k < z; ++k) {
+          const uint32_t remote = cluster_map_shared(local, k);
+          const float4 a0 = ld_cluster_f4(remote), a1 = ld_cluster_f4(remote + 16);
+          v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+        }
+        tc_emit8(p, v, b, oy, ox, cbase);
+      }
+    }
+    cluster_sync_all();      // no CTA may exit (and release its shared memory) while a peer still reads it
   }
   __syncthreads();
   if (warp == 1) {
@@ -424,6 +491,36 @@ static int launch_tc(TcParams& p, dim3 grid, int kc_max, cudaStream_t s) {
   stages = max(2, min(kMaxStages, stages));
   p.num_stages = stages;
   const int smem = stages * p.stage_bytes + overhead;
+  if (p.cluster_reduce) {
+    // the splits of one output tile (gridDim.z) form a cluster and reduce through distributed shared memory; needs the
+    // partial tile to fit in the (by then idle) stage ring and the cluster to be schedulable -- else the workspace path
+    static int cluster_ok[17] = {0};       // per cluster size: 0 unknown, 1 usable, -1 not
+    const int z = (int)grid.z;
+    bool ok = z <= 16 && kTileM * BLOCK_N * 4 <= stages * p.stage_bytes;
+    if (ok && cluster_ok[z] == 0) {
+      static bool np_set = false;
+      if (!np_set) {
+        cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        np_set = true;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kMaxSmemBytes;   // worst case: 1 CTA per SM
+      cudaLaunchAttribute a[1];
+      a[0].id = cudaLaunchAttributeClusterDimension;
+      a[0].val.clusterDim.x = 1; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = (unsigned)z;
+      cfg.attrs = a; cfg.numAttrs = 1;
+      int n_clusters = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, conv_tc_kernel<BLOCK_N>, &cfg);
+      cluster_ok[z] = (e == cudaSuccess && n_clusters > 0) ? 1 : -1;
+      if (e != cudaSuccess) cudaGetLastError();
+    }
+    ok = ok && cluster_ok[z] == 1;
+    if (ok) {
+      launch_k_cluster(conv_tc_kernel<BLOCK_N>, grid, dim3(kTcThreads), (size_t)smem, s, (unsigned)z, p);
+      return check_launch("conv_tc_kernel(cluster)");
+    }
+    p.cluster_reduce = 0;
+  }
   launch_k(conv_tc_kernel<BLOCK_N>, grid, dim3(kTcThreads), (size_t)smem, s, p);
   return check_launch("conv_tc_kernel");
 }
@@ -508,12 +605,16 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
     p.ksplit = (n_taps + per - 1) / per;              // no empty splits
   }
   dim3 grid(p.tiles_x * p.tiles_y * d->B, n_tiles, p.ksplit);
+  static const bool cat_env = []() { const char* e = getenv("DVMVS_TC_CAT"); return !(e && e[0] == '0'); }();
+  p.cat = (d->terms == 3 && cat_env) ? 1 : 0;
+  static const bool cluster_env = []() { const char* e = getenv("DVMVS_CLUSTER_SPLITK"); return !(e && e[0] == '0'); }();
+  p.cluster_reduce = (p.ksplit > 1 && cluster_env && d->Cout % 8 == 0) ? 1 : 0;
   int rc;
   if (d->block_n == 32) rc = launch_tc<32>(p, grid, kc_max, s);
   else if (d->block_n == 64) rc = launch_tc<64>(p, grid, kc_max, s);
   else rc = launch_tc<128>(p, grid, kc_max, s);
   if (rc != DVMVS_OK) return rc;
-  if (p.ksplit > 1) {
+  if (p.ksplit > 1 && !p.cluster_reduce) {     // launch_tc clears cluster_reduce when it had to fall back to the workspace path
     launch_k(conv_tc_finish_kernel, dim3((unsigned)((out_elems + 255) / 256)), dim3(256), 0, s, p);
     return check_launch("conv_tc_finish_kernel");
   }

@@ -439,7 +439,7 @@ __global__ void depth_reproject_kernel(const float* __restrict__ cur_pose, const
 
 using namespace dvmvs;
 
-extern "C" int dvmvs_abi_version(void) { return 2; }
+extern "C" int dvmvs_abi_version(void) { return 3; }
 
 // Host-side evaluation of the geometry prologue (same code the kernels run); lets the CPU test-suite check the
 // pose algebra without a GPU.  All pointers are HOST pointers here.

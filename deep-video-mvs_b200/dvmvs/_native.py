@@ -81,6 +81,7 @@ class ConvHaloDesc(ctypes.Structure):
         ("out_f32", ctypes.c_void_p), ("out_blk", ctypes.c_void_p), ("out_nhwc", ctypes.c_void_p),
         ("B", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cout", ctypes.c_int),
         ("ksize", ctypes.c_int), ("act", ctypes.c_int),
+        ("w_cat", ctypes.c_void_p),
     ]
 
 

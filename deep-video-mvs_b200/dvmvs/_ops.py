@@ -468,6 +468,8 @@ class PackedConvHalo:
         hi = packed.to(torch.float16)
         lo = (packed - hi.to(torch.float32)).to(torch.float16)
         self.w_hi, self.w_lo = hi.contiguous().to(device), lo.contiguous().to(device)
+        # [..][kc/8][2 (hi, lo)][bn][8]: weight operand of the two-MMA form (x_hi * [w_hi ; w_lo] + x_lo * w_hi)
+        self.w_cat = torch.stack([hi, lo], dim=5).contiguous().to(device) if _HALO_CAT else None
         self.ksize, self.cin, self.cout, self.act = k, cin, cout, pc.act
         self.bias = pc.bias.to(device) if pc.bias is not None else None
         self.src_channels = list(src_channels)
@@ -491,6 +493,7 @@ def conv2d_halo(sources_blk, ph, residual=None, terms=3, want_f32=True, want_blk
     out_blk = torch.empty((2, B, ph.cout // 8, H, W, 8), dtype=torch.float16, device=dev) if want_blk else None
     out_nhwc = torch.empty((2, B, H, W, ph.cout), dtype=torch.float16, device=dev) if want_nhwc else None
     d.w_hi, d.w_lo = ph.w_hi.data_ptr(), ph.w_lo.data_ptr()
+    d.w_cat = ph.w_cat.data_ptr() if (ph.w_cat is not None and terms == 3) else None
     d.n_groups, d.kc, d.block_n, d.terms = ph.n_groups, ph.kc, ph.block_n, terms
     d.bias = ph.bias.data_ptr() if ph.bias is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
@@ -509,6 +512,7 @@ _BACKEND = _os.environ.get("DVMVS_CONV_BACKEND", "fp32")     # "fp32": CUDA-core
 _TC_TERMS = int(_os.environ.get("DVMVS_TC_TERMS", "3"))
 _TC_STRIDE2 = _os.environ.get("DVMVS_TC_STRIDE2", "0") == "1"
 _HALO = _os.environ.get("DVMVS_HALO", "1") == "1"          # blocked-layout halo kernel for large stride-1 k>=3 convolutions
+_HALO_CAT = _os.environ.get("DVMVS_HALO_CAT", "1") == "1"  # two-MMA (concatenated hi/lo weights) form of the three-term product
 _HALO_MIN_PIXELS = int(_os.environ.get("DVMVS_HALO_MIN_PIXELS", "4096"))   # >= 64x64 maps; smaller maps: split-K conv_tc
 
 

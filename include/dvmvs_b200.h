@@ -147,6 +147,8 @@ int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* desc_host, dvmvs_stream_t stream);
  *   src_blk[i]  blocked planes of source i (C8_i = channel blocks; padded channels are zero); sources concatenate
  *   w_hi/w_lo   fp16 weights in their shared-memory image: [n-tile][group][ky][kx][kc/8][block_n][8], BN folded; groups
  *               enumerate the kc-channel groups of source 0, then source 1, ... (zero rows for padded channels)
+ *   w_cat       optional (terms == 3): the same weights with hi and lo interleaved per 8-channel block,
+ *               [n-tile][group][ky][kx][kc/8][2][block_n][8]; selects the two-MMA form x_hi*[w_hi;w_lo] + x_lo*w_hi
  *   outputs     any of: out_f32 [B][H][W][Cout], out_blk [2][B][Cout/8][H][W][8], out_nhwc [2][B][H][W][Cout]
  *   residual    optional fp32 [B][H][W][Cout] added before the activation. */
 typedef struct {
@@ -162,6 +164,7 @@ typedef struct {
   void* out_blk;
   void* out_nhwc;
   int B, H, W, Cout, ksize, act;
+  const void* w_cat;
 } dvmvs_conv_halo_desc;
 
 int dvmvs_conv2d_halo(const dvmvs_conv_halo_desc* desc_host, dvmvs_stream_t stream);
