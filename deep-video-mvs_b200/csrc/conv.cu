@@ -322,9 +322,13 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 // =====================================================================================================
 // Depthwise convolution
 // =====================================================================================================
-__global__ void dwconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                              float* __restrict__ y, __half* __restrict__ planes, int B, int H, int W, int C, int Hout, int Wout,
-                              int ks, int stride, int act) {
+// KS is a template parameter so that the tap loops unroll completely: all k*k (predicated) 16-byte loads of a thread are
+// in flight together instead of one load -> FMA round trip per tap (these launches are latency-bound, not bandwidth-bound).
+template <int KS>
+__global__ void __launch_bounds__(128) dwconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                     float* __restrict__ y, __half* __restrict__ planes, int B, int H, int W, int C, int Hout,
+                                                     int Wout, int stride, int act) {
+  constexpr int ks = KS;
   pdl_launch_dependents();
   pdl_wait();
   const int c4n = C >> 2;
@@ -338,12 +342,14 @@ __global__ void dwconv_kernel(const float* __restrict__ x, const float* __restri
   const int b = (int)(pix / ((size_t)Wout * Hout));
   const int pad = ks >> 1;
   float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
   for (int ky = 0; ky < ks; ++ky) {
     const int iy = oy * stride - pad + ky;
-    if (iy < 0 || iy >= H) continue;
+    const bool yok = iy >= 0 && iy < H;
+#pragma unroll
     for (int kx = 0; kx < ks; ++kx) {
       const int ix = ox * stride - pad + kx;
-      if (ix < 0 || ix >= W) continue;
+      if (!(yok && ix >= 0 && ix < W)) continue;      // predicated after unrolling; skipped taps contribute exactly 0
       const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + iy) * W + ix) * C) + cg);
       const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ky * ks + kx) * C) + cg);
       acc.x = fmaf(xv.x, wv.x, acc.x);
@@ -583,8 +589,12 @@ extern "C" int dvmvs_dwconv2d(const float* x, const float* weight, const float* 
   const int pad = ksize / 2;
   const int Hout = (H + 2 * pad - ksize) / stride + 1, Wout = (W + 2 * pad - ksize) / stride + 1;
   const size_t total = (size_t)B * Hout * Wout * (C / 4);
-  launch_k(dwconv_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, x, weight, bias, y, (__half*)y_planes,
-           B, H, W, C, Hout, Wout, ksize, stride, act);
+  if (ksize == 3)
+    launch_k(dwconv_kernel<3>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, x, weight, bias, y, (__half*)y_planes,
+             B, H, W, C, Hout, Wout, stride, act);
+  else
+    launch_k(dwconv_kernel<5>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, x, weight, bias, y, (__half*)y_planes,
+             B, H, W, C, Hout, Wout, stride, act);
   return check_launch("dwconv_kernel");
 }
 

@@ -327,9 +327,23 @@ __global__ void split_blocked_kernel(const float* __restrict__ x, __half* __rest
     const float* p01 = bp + ((size_t)y0 * W + x1) * C;
     const float* p10 = bp + ((size_t)y1 * W + x0) * C;
     const float* p11 = bp + ((size_t)y1 * W + x1) * C;
+    if (vec) {       // 8 x 16-byte loads instead of 32 scalar ones (this kernel is LSU-issue bound, not bandwidth bound)
+      float t00[8], t01[8], t10[8], t11[8];
+      *reinterpret_cast<float4*>(t00) = __ldg(reinterpret_cast<const float4*>(p00));
+      *reinterpret_cast<float4*>(t00 + 4) = __ldg(reinterpret_cast<const float4*>(p00 + 4));
+      *reinterpret_cast<float4*>(t01) = __ldg(reinterpret_cast<const float4*>(p01));
+      *reinterpret_cast<float4*>(t01 + 4) = __ldg(reinterpret_cast<const float4*>(p01 + 4));
+      *reinterpret_cast<float4*>(t10) = __ldg(reinterpret_cast<const float4*>(p10));
+      *reinterpret_cast<float4*>(t10 + 4) = __ldg(reinterpret_cast<const float4*>(p10 + 4));
+      *reinterpret_cast<float4*>(t11) = __ldg(reinterpret_cast<const float4*>(p11));
+      *reinterpret_cast<float4*>(t11 + 4) = __ldg(reinterpret_cast<const float4*>(p11 + 4));
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (c0 + e < C) v[e] = ly0 * (lx0 * __ldg(p00 + e) + lx1 * __ldg(p01 + e)) + ly1 * (lx0 * __ldg(p10 + e) + lx1 * __ldg(p11 + e));
+      for (int e = 0; e < 8; ++e) v[e] = ly0 * (lx0 * t00[e] + lx1 * t01[e]) + ly1 * (lx0 * t10[e] + lx1 * t11[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (c0 + e < C) v[e] = ly0 * (lx0 * __ldg(p00 + e) + lx1 * __ldg(p01 + e)) + ly1 * (lx0 * __ldg(p10 + e) + lx1 * __ldg(p11 + e));
+    }
   }
   __align__(16) __half hi[8];
   __align__(16) __half lo[8];

@@ -427,6 +427,63 @@ __global__ void split_planes_kernel(const float* __restrict__ x, __half* __restr
   planes[total + o] = __float2half_rn(v - __half2float(h));
 }
 
+// same for channel counts / windows that are multiples of 8: one thread per (pixel, 8 channels), 16-byte loads and stores
+__global__ void split_planes8_kernel(const float* __restrict__ x, __half* __restrict__ planes, int B, int H, int W, int C, int Cs,
+                                     int upsample, int c_offset, int c_cover) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
+  const size_t total = (size_t)B * Ho * Wo * Cs;
+  const int nblk = c_cover >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * Ho * Wo * nblk) return;
+  const int c = (int)(idx % nblk) * 8;
+  const size_t pix = idx / nblk;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (c < C) {
+    if (!upsample) {
+      const float* src = x + pix * C + c;
+      *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(src));
+      *reinterpret_cast<float4*>(v + 4) = __ldg(reinterpret_cast<const float4*>(src + 4));
+    } else {
+      const int ox = (int)(pix % Wo);
+      const int oy = (int)((pix / Wo) % Ho);
+      const int b = (int)(pix / ((size_t)Wo * Ho));
+      const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+      const float sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+      const float fy = sh * oy, fx = sw * ox;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+      const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+      const float* bp = x + (size_t)b * H * W * C + c;
+      float t00[8], t01[8], t10[8], t11[8];
+      const float* q;
+      q = bp + ((size_t)y0 * W + x0) * C;
+      *reinterpret_cast<float4*>(t00) = __ldg(reinterpret_cast<const float4*>(q)); *reinterpret_cast<float4*>(t00 + 4) = __ldg(reinterpret_cast<const float4*>(q + 4));
+      q = bp + ((size_t)y0 * W + x1) * C;
+      *reinterpret_cast<float4*>(t01) = __ldg(reinterpret_cast<const float4*>(q)); *reinterpret_cast<float4*>(t01 + 4) = __ldg(reinterpret_cast<const float4*>(q + 4));
+      q = bp + ((size_t)y1 * W + x0) * C;
+      *reinterpret_cast<float4*>(t10) = __ldg(reinterpret_cast<const float4*>(q)); *reinterpret_cast<float4*>(t10 + 4) = __ldg(reinterpret_cast<const float4*>(q + 4));
+      q = bp + ((size_t)y1 * W + x1) * C;
+      *reinterpret_cast<float4*>(t11) = __ldg(reinterpret_cast<const float4*>(q)); *reinterpret_cast<float4*>(t11 + 4) = __ldg(reinterpret_cast<const float4*>(q + 4));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = ly0 * (lx0 * t00[e] + lx1 * t01[e]) + ly1 * (lx0 * t10[e] + lx1 * t11[e]);
+    }
+  }
+  __align__(16) __half hi[8];
+  __align__(16) __half lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    hi[e] = __float2half_rn(v[e]);
+    lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+  }
+  const size_t o = pix * Cs + c_offset + c;
+  *reinterpret_cast<uint4*>(planes + o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(planes + total + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
 // ----------------------------------------------------------------------------------------------- host side
 EncodeTiledFn tensor_map_encoder() {
   static EncodeTiledFn fn = nullptr;
@@ -607,7 +664,10 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   dim3 grid(p.tiles_x * p.tiles_y * d->B, n_tiles, p.ksplit);
   static const bool cat_env = []() { const char* e = getenv("DVMVS_TC_CAT"); return !(e && e[0] == '0'); }();
   p.cat = (d->terms == 3 && cat_env) ? 1 : 0;
-  static const bool cluster_env = []() { const char* e = getenv("DVMVS_CLUSTER_SPLITK"); return !(e && e[0] == '0'); }();
+  // opt-in (DVMVS_CLUSTER_SPLITK=1): measured SLOWER than partials + finish kernel on B200 (c2 keyframe 1.52 vs 1.33 ms):
+  // clusters of 5 / 9 one-CTA-per-SM blocks must be co-scheduled inside a GPC, which costs more (extra waves, two
+  // cluster barriers) than the 21 short finish launches it removes.  Kept for the record and for larger split counts.
+  static const bool cluster_env = []() { const char* e = getenv("DVMVS_CLUSTER_SPLITK"); return e && e[0] == '1'; }();
   p.cluster_reduce = (p.ksplit > 1 && cluster_env && d->Cout % 8 == 0) ? 1 : 0;
   int rc;
   if (d->block_n == 32) rc = launch_tc<32>(p, grid, kc_max, s);
@@ -626,6 +686,12 @@ extern "C" int dvmvs_split_planes(const float* x, void* planes, int B, int H, in
   DVMVS_REQUIRE(x && planes && B > 0 && H > 0 && W > 0 && C > 0 && Cs % 8 == 0, "split_planes: bad argument");
   DVMVS_REQUIRE(c_offset >= 0 && c_cover >= C && c_offset + c_cover <= Cs, "split_planes: channel window [%d,+%d) outside %d", c_offset,
                 c_cover, Cs);
+  if (C % 8 == 0 && c_offset % 8 == 0 && c_cover % 8 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)planes % 16 == 0) {
+    const size_t n8 = (size_t)B * H * W * (c_cover / 8) * (upsample2x ? 4 : 1);
+    launch_k(split_planes8_kernel, dim3((unsigned)((n8 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, (__half*)planes, B, H, W, C, Cs,
+             upsample2x, c_offset, c_cover);
+    return check_launch("split_planes8_kernel");
+  }
   const size_t total = (size_t)B * H * W * c_cover * (upsample2x ? 4 : 1);
   launch_k(split_planes_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, (__half*)planes, B, H, W, C, Cs,
            upsample2x, c_offset, c_cover);

@@ -9,6 +9,9 @@
 //   fx = (float)((dx + 0.5) * (double)src_w / dst_w - 0.5);  sx = floor(fx);  fx -= sx;
 //   sx < 0 -> (sx, fx) = (0, 0);   sx >= src_w - 1 -> (sx, fx) = (src_w - 1, 0)        (same for y, rows clamped)
 //   horizontal pass  t = S[sx] * (1 - fx) + S[sx + 1] * fx   then vertical pass  t0 * (1 - fy) + t1 * fy, all fp32.
+// This is bit-for-bit OpenCV's native path (cv2.ipp.setUseIPP(False)) up to one fused multiply-add in its SIMD vertical
+// pass; OpenCV builds that dispatch float resizes to Intel IPP round the interpolation coefficients differently
+// (<= 0.009 on the 0..255 scale for white noise) -- tests/test_gpu_parity.py checks both.
 // HBM-bound: reads <= 4 source texels per output texel (mostly L2 hits), writes 12 B per output pixel.
 #include "common.cuh"
 

@@ -209,14 +209,26 @@ class GraphedFusionnet:
         return self._out
 
 
+def _stage_side_inputs(slot):
+    """Small state-independent preparations the last stage would otherwise do on the loop-carried critical path: the
+    channel-last copy of the reference image the decoder's refinement convolutions read, and the 1/32 intrinsics."""
+    from . import _ops as ops
+    slot["ref_cl"] = ops.to_api(ops.to_nhwc(slot["ref_image"], "image"))      # (B,3,H,W) view with channels_last strides
+    lstm_K = slot["full_K"].clone()
+    lstm_K[:, 0:2, :] = lstm_K[:, 0:2, :] / 32.0
+    slot["lstm_K"] = lstm_K
+
+
 def _stage_fe(mods, slot):
     """Stage 1 of 3: MnasNet trunk on the reference + measurement images stacked on the batch axis."""
+    _stage_side_inputs(slot)
     stacked = torch.cat([slot["ref_image"]] + list(slot["meas_images"]), dim=0)
     return mods["fe"](stacked)
 
 
 def _stage_fe_head(mods, slot):
     """MnasNet trunk up to layer3 (1/8 resolution) on the stacked images."""
+    _stage_side_inputs(slot)
     stacked = torch.cat([slot["ref_image"]] + list(slot["meas_images"]), dim=0)
     return mods["fe"].forward_head(stacked)
 
@@ -255,10 +267,12 @@ def _stage_mid(mods, slot, fe_out, min_depth, max_depth, n_depth_levels):
 def _stage_rec(mods, state, slot, enc, half_K):
     """Last stage: depth re-projection + ConvLSTM fusion + decoder -- the only part with a loop-carried dependence."""
     s0, s1, s2, s3, bottom = enc
-    reference_image, reference_pose, full_K = slot["ref_image"], slot["ref_pose"], slot["full_K"]
+    reference_image, reference_pose, full_K = slot.get("ref_cl", slot["ref_image"]), slot["ref_pose"], slot["full_K"]
     B, _, H, W = reference_image.shape
-    lstm_K = full_K.clone()
-    lstm_K[:, 0:2, :] = lstm_K[:, 0:2, :] / 32.0
+    lstm_K = slot.get("lstm_K")
+    if lstm_K is None:
+        lstm_K = full_K.clone()
+        lstm_K[:, 0:2, :] = lstm_K[:, 0:2, :] / 32.0
     if state.previous_depth is not None:
         de = get_non_differentiable_rectangle_depth_estimation(reference_pose_torch=reference_pose, measurement_pose_torch=state.previous_pose,
                                                                previous_depth_torch=state.previous_depth, full_K_torch=full_K,

@@ -532,15 +532,28 @@ def test_device_preprocessing_vs_cv2_host_path(case):
     pre = PreprocessImage(K=K, old_width=in_w, old_height=in_h, new_width=out_w, new_height=out_h, distortion_crop=dcrop, perform_crop=crop)
     scale, mean, std = 255.0, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
     rgb_f32 = cv2.cvtColor(bgr.astype(np.float32), cv2.COLOR_BGR2RGB)           # == load_image
-    want = np.transpose(pre.apply_rgb(image=rgb_f32, scale_rgb=scale, mean_rgb=mean, std_rgb=std), (2, 0, 1))[None]
     got_u8 = pre.apply_rgb_cuda(torch.from_numpy(bgr).to(DEV), scale, mean, std)
     got_f32 = pre.apply_rgb_cuda(torch.from_numpy(rgb_f32).to(DEV), scale, mean, std)
+    raw = pre.apply_rgb_cuda(torch.from_numpy(bgr).to(DEV), scale, mean, std, normalize_colors=False)
     assert tuple(got_u8.shape) == (1, 3, out_h, out_w) and got_u8.dtype == torch.float32
+
+    def host(normalize):
+        return np.transpose(pre.apply_rgb(image=rgb_f32, scale_rgb=scale, mean_rgb=mean, std_rgb=std, normalize_colors=normalize), (2, 0, 1))[None]
+
+    # (1) OpenCV's own INTER_LINEAR float path (the algorithm restated in csrc/preprocess.cu): equal to rounding
+    use_ipp = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        want, want_raw = host(True), host(False)
+    finally:
+        cv2.ipp.setUseIPP(use_ipp)
     for got in (got_u8, got_f32):
         assert np.abs(got.cpu().numpy() - want).max() <= 2e-6 * 4.5            # |normalised value| <= ~2.7
-    raw = pre.apply_rgb_cuda(torch.from_numpy(bgr).to(DEV), scale, mean, std, normalize_colors=False)
-    want_raw = np.transpose(pre.apply_rgb(image=rgb_f32, scale_rgb=scale, mean_rgb=mean, std_rgb=std, normalize_colors=False), (2, 0, 1))[None]
     assert np.abs(raw.cpu().numpy() - want_raw).max() <= 6.2e-5                 # 2 ulp at 255
+    # (2) this image's cv2 build dispatches float resizes to Intel IPP, whose interpolation coefficients are rounded
+    # differently (measured <= 0.009 on the 0..255 scale for white-noise images, 0 for dyadic scale factors): same bound
+    want_ipp = host(True)
+    assert np.abs(got_u8.cpu().numpy() - want_ipp).max() <= 0.02 / 255.0 / 0.224
 
 
 def test_device_preprocessing_feeds_the_network_like_the_host_path(oracle, synth):
@@ -565,4 +578,4 @@ def test_device_preprocessing_feeds_the_network_like_the_host_path(oracle, synth
     with torch.no_grad():
         a, _ = pipeline.keyframe(mods, pipeline.KeyframeState(), host[0], poses[0], host[1:], poses[1:], K, n_depth_levels=D)
         b, _ = pipeline.keyframe(mods, pipeline.KeyframeState(), dev[0], poses[0], dev[1:], poses[1:], K, n_depth_levels=D)
-    assert oracle.rel_l1_inverse_depth(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
+    assert oracle.rel_l1_inverse_depth(b.cpu().numpy(), a.cpu().numpy()) <= 1e-4     # host side may use IPP's coefficients (see above)

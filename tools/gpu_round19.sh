@@ -7,7 +7,7 @@ run_tests() {  # name, env...
   echo "== tests[$name] exit $?"; tail -4 gpurun_out/pytest_$name.log | cut -c1-400
 }
 run_tests all_on A=1
-run_tests cluster_off DVMVS_CLUSTER_SPLITK=0
+run_tests cluster_on DVMVS_CLUSTER_SPLITK=1
 run_tests cat_off DVMVS_TC_CAT=0 DVMVS_HALO_CAT=0
 bench() { name=$1; shift
   env "$@" timeout 300 python bench.py --cpu-frames 0 --extras 0 --steps 40 2> gpurun_out/bench_$name.err | tee gpurun_out/bench_$name.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$name', d['config']['mode'], round(d['value'],1), round(d['ms_per_step'],4), round(d['e2e']['value'],1), d['gpu_launches'])"
