@@ -24,13 +24,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n); }
+static std::atomic<int> g_pdl_override{-1};      // -1: environment default, 0 / 1: forced by dvmvs_set_programmatic_launch
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DVMVS_PDL");
     v = (e && e[0] == '0') ? 0 : 1;
   }
-  return v == 1;
+  const int o = g_pdl_override.load();
+  return o < 0 ? v == 1 : o == 1;
 }
 
 // =====================================================================================================
@@ -440,6 +442,14 @@ __global__ void depth_reproject_kernel(const float* __restrict__ cur_pose, const
 using namespace dvmvs;
 
 extern "C" int dvmvs_abi_version(void) { return 3; }
+
+// Programmatic dependent launch for the launches that follow (process-wide): 1 on, 0 off, -1 back to the default
+// (on unless DVMVS_PDL=0).  What a launch was enqueued / captured with stays with it.
+extern "C" int dvmvs_set_programmatic_launch(int mode) {
+  DVMVS_REQUIRE(mode >= -1 && mode <= 1, "set_programmatic_launch: mode %d", mode);
+  g_pdl_override.store(mode);
+  return DVMVS_OK;
+}
 
 // Host-side evaluation of the geometry prologue (same code the kernels run); lets the CPU test-suite check the
 // pose algebra without a GPU.  All pointers are HOST pointers here.

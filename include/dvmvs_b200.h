@@ -41,6 +41,9 @@ enum { DVMVS_SWEEP_DOT = 0, DVMVS_SWEEP_SAD = 1 };
 
 /* Library identification / diagnostics. */
 int dvmvs_abi_version(void);                 /* bumps when a signature changes */
+/* Programmatic dependent launch (griddepcontrol) for the launches that follow, process-wide: 1 on, 0 off, -1 default
+ * (on unless the environment says DVMVS_PDL=0).  Launches already enqueued or captured keep what they were made with. */
+int dvmvs_set_programmatic_launch(int mode);
 const char* dvmvs_last_error_string(void);   /* thread-local, static storage */
 int dvmvs_kernel_launch_count(void);         /* kernels launched by this library since load (process-wide) */
 
