@@ -511,7 +511,16 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
       attr_set = true;
     }
     DVMVS_REQUIRE(smem <= 96 * 1024, "plane_sweep: shared memory %zu too large", smem);
-    launch_k(plane_sweep_c32_kernel, dim3(tiles), dim3(kSweepThreads), smem, s, p);
+    // DVMVS_SWEEP_CTAS_PER_SM=n (1..3) pads the dynamic shared memory so that at most n CTAs of this kernel share an SM
+    // (default: 4, the register limit) -- leaves room for other streams' kernels in pipelined engines (experiment switch)
+    static const int occ_limit = []() { const char* e = getenv("DVMVS_SWEEP_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    size_t smem_launch = smem;
+    if (occ_limit >= 1 && occ_limit <= 3) {
+      const size_t want = (size_t)(227 * 1024) / (occ_limit + 1) + 1024;      // occ_limit + 1 CTAs no longer fit
+      if (want > smem_launch && want <= 96 * 1024) smem_launch = want;
+      else if (want > 96 * 1024) smem_launch = 96 * 1024;
+    }
+    launch_k(plane_sweep_c32_kernel, dim3(tiles), dim3(kSweepThreads), smem_launch, s, p);
     return check_launch("plane_sweep_c32_kernel");
   }
   const size_t total = (size_t)B * h * w * D;

@@ -326,6 +326,9 @@ class PipelinedFusionnet:
         # slower on B200 (922 vs 1067 keyframes/s at 3 stages), so it is off by default
         prio = _os.environ.get("DVMVS_PIPE_PRIO", "0") == "1"
         self.streams = [torch.cuda.Stream(device=dev, priority=(-1 if (prio and i == n_stages - 1) else 0)) for i in range(n_stages)]
+        # DVMVS_PIPE_REC_PDL=0: capture the last stage without programmatic dependent launch (its early-launched CTAs then do
+        # not sit on SMs waiting for their predecessor while other stages could use them) -- experiment switch
+        self._rec_pdl = _os.environ.get("DVMVS_PIPE_REC_PDL", "1") == "1"
         if _os.environ.get("DVMVS_PIPE_SERIAL") == "1":        # debugging aid: all stages on one stream (no overlap)
             self.streams = [self.streams[0]] * n_stages
         self.stream_a, self.stream_b = self.streams[0], self.streams[-1]      # first / last stage (timing hooks)
@@ -379,6 +382,8 @@ class PipelinedFusionnet:
         stream = self.streams[i]
         torch.cuda.synchronize(self.device)
         saved = [t.clone() for t in self._static_state] if (i == last and self._static_state is not None) else None
+        if i == last and not self._rec_pdl:
+            _native.lib().dvmvs_set_programmatic_launch(0)
         with torch.cuda.stream(stream), torch.no_grad():
             for _ in range(2):
                 res = self._run_stage(i, slot, with_state)
@@ -401,6 +406,8 @@ class PipelinedFusionnet:
             else:
                 slot["out"][i] = res
         self._kernels[i] = _native.launch_count() - n0
+        if i == last and not self._rec_pdl:
+            _native.lib().dvmvs_set_programmatic_launch(-1)
         slot["graph"][i][with_state if i == last else False] = g
         if saved is not None:
             for dst, src in zip(self._static_state, saved):
