@@ -100,9 +100,19 @@ class DecoderBlock(NativeModule):
         split = [cout, self.convolution1[0].in_channels - cout - (1 if self.plus_one else 0)] + ([1] if self.plus_one else [])
         return ops.ConvLayer(pack_cbr(self.convolution1), split), ops.ConvLayer(pack_cbr(self.convolution2))
 
-    def run(self, x, skip, depth):
+    def run(self, x, skip, depth, depth_producer=None):
+        """depth_producer: callable returning the depth Act (the previous scale's sigmoid head) -- run on a side stream
+        together with the staging of its x2-upsampled operand, next to the up-convolution (they are independent)."""
         c1, c2 = self.packed()
+        fork = None
+        if depth_producer is not None:
+            fork = ops.Fork()
+            with fork:
+                depth = depth_producer()
+                c1.prestage_upsampled(depth)
         x = self.up_convolution.run(x)
+        if fork is not None:
+            fork.join()
         srcs = [(x, D), (skip, D)] if depth is None else [(x, D), (skip, D), (depth, U)]   # cat fused (model.py:112-115)
         return c2.run([(c1.run(srcs), D)])
 
@@ -310,15 +320,36 @@ class CostVolumeDecoder(NativeModule):
     def run(self, image, skip0, skip1, skip2, skip3, bottom):
         heads, r0, r1 = self.packed()
         aux = (float(self.inverse_depth_multiplier), float(self.inverse_depth_base))    # depth = 1/(mult*sigmoid + base)
+        depths = {}
+
+        def head(i, d):
+            # scale-i depth head; returns the sigmoid map the next block concatenates, keeps the depth output
+            def produce():
+                sig, depths[i] = heads[i].run([(d, D)], aux=aux)
+                return sig
+            return produce
+
+        # each head (+ the staging of its upsampled output) is independent of the next block's up-convolution: fork / join
         d1 = self.decoder_block1.run(bottom, skip3, None)
-        s16, depth16 = heads[0].run([(d1, D)], aux=aux)
-        d2 = self.decoder_block2.run(d1, skip2, s16)
-        s8, depth8 = heads[1].run([(d2, D)], aux=aux)
-        d3 = self.decoder_block3.run(d2, skip1, s8)
-        s4, depth4 = heads[2].run([(d3, D)], aux=aux)
-        d4 = self.decoder_block4.run(d3, skip0, s4)
-        s2, depth2 = heads[3].run([(d4, D)], aux=aux)
-        x = r0.run([(d4, U), (s2, U), (image, D)])                                        # cat order model.py:295
+        d2 = self.decoder_block2.run(d1, skip2, None, depth_producer=head(0, d1))
+        d3 = self.decoder_block3.run(d2, skip1, None, depth_producer=head(1, d2))
+        d4 = self.decoder_block4.run(d3, skip0, None, depth_producer=head(2, d3))
+        Ho, Wo = 2 * d4.f32.shape[1], 2 * d4.f32.shape[2]
+        if r0.pack_sources and r0.path(Ho, Wo) == "halo":
+            # refine.0 reads ONE concatenated operand [up(d4), up(sigmoid), image]: the head runs on the side stream while
+            # the two sources that exist already are staged; the sigmoid map is staged after the join
+            fork = ops.Fork()
+            with fork:
+                s2 = head(3, d4)()
+            meta = [(d4.f32, True), ((d4.f32.shape[0], d4.f32.shape[1], d4.f32.shape[2], 1), True), (image.f32, False)]
+            buf = ops.split_blocked(meta, only=(0, 2))
+            fork.join()
+            ops.split_blocked([(d4.f32, True), (s2.f32, True), (image.f32, False)], only=(1,), into=buf)
+            x = r0.run([(d4, U), (s2, U), (image, D)], prestaged=buf)                     # cat order model.py:295
+        else:
+            s2 = head(3, d4)()
+            x = r0.run([(d4, U), (s2, U), (image, D)])                                    # cat order model.py:295
+        depth16, depth8, depth4, depth2 = depths[0], depths[1], depths[2], depths[3]
         x = r1.run([(x, D)])
         _, depth1 = heads[4].run([(x, D)], aux=aux)
         return [t.squeeze(3) for t in (depth1, depth2, depth4, depth8, depth16)]

@@ -3,6 +3,12 @@
 views of the same storage (torch.channels_last strides).  torch is used for device memory and the current
 stream only."""
 import ctypes
+import os as _os_mod
+
+
+def _os_environ_get(k, d):
+    return _os_mod.environ.get(k, d)
+
 
 import torch
 
@@ -403,23 +409,30 @@ def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, w
 
 
 # ================================================================================================ halo (blocked-layout) path
-def split_blocked(sources):
+def split_blocked(sources, only=None, into=None):
     """sources: [(fp32 nhwc tensor, upsample)] -> blocked fp16 pair planes (2, B, C8, H', W', 8) of their channel
     concatenation (torch.cat staged straight into the operand layout of conv_halo_kernel).  Every source starts on an
     8-channel block boundary: narrow sources (the 1-channel depth, the RGB image) are padded to 8 with zero channels --
-    PackedConvHalo(pad_sources_to_8=True) lays the weights out the same way."""
-    shapes = [(t.shape[1] * (2 if up else 1), t.shape[2] * (2 if up else 1)) for t, up in sources]
-    B, (Ho, Wo) = sources[0][0].shape[0], shapes[0]
+    PackedConvHalo(pad_sources_to_8=True) lays the weights out the same way.
+    only / into: stage just the listed source indices into an existing operand tensor (sources not staged yet may be
+    given as (shape tuple, upsample)) -- lets independent producers fill one concatenated operand at different times."""
+    shp = lambda t: tuple(t) if isinstance(t, (tuple, list)) else tuple(t.shape)
+    shapes = [(shp(t)[1] * (2 if up else 1), shp(t)[2] * (2 if up else 1)) for t, up in sources]
+    B, (Ho, Wo) = shp(sources[0][0])[0], shapes[0]
     if any(sh != (Ho, Wo) for sh in shapes):
         raise ValueError("split_blocked: spatial sizes differ: %s" % (shapes,))
-    C8 = sum((t.shape[3] + 7) // 8 for t, _ in sources)
-    planes = torch.empty((2, B, C8, Ho, Wo, 8), dtype=torch.float16, device=sources[0][0].device)
+    C8 = sum((shp(t)[3] + 7) // 8 for t, _ in sources)
+    if into is None:
+        dev = next(t.device for t, _ in sources if isinstance(t, torch.Tensor))
+        into = torch.empty((2, B, C8, Ho, Wo, 8), dtype=torch.float16, device=dev)
+    planes = into
     off = 0
-    for t, up in sources:
-        C = t.shape[3]
+    for i, (t, up) in enumerate(sources):
+        C = shp(t)[3]
         cover = (C + 7) // 8 * 8
-        N.check(N.lib().dvmvs_split_blocked(t.data_ptr(), planes.data_ptr(), B, t.shape[1], t.shape[2], C, C8, 1 if up else 0, off, cover,
-                                            _stream()), "split_blocked")
+        if only is None or i in only:
+            N.check(N.lib().dvmvs_split_blocked(t.data_ptr(), planes.data_ptr(), B, t.shape[1], t.shape[2], C, C8, 1 if up else 0, off, cover,
+                                                _stream()), "split_blocked")
         off += cover
     return planes
 
@@ -536,10 +549,10 @@ def conv_backend():
 class Act:
     """An activation inside a module: fp32 channel-last tensor and/or its fp16 (hi, lo) planes (created on demand,
     cached).  `up` planes = planes of the x2-bilinear-upsampled tensor (F.interpolate materialised for the TMA loader)."""
-    __slots__ = ("f32", "planes", "planes_up", "blk", "version")
+    __slots__ = ("f32", "planes", "planes_up", "blk", "blk_up", "version")
 
     def __init__(self, f32=None, planes=None, blk=None):
-        self.f32, self.planes, self.planes_up, self.blk, self.version = f32, planes, None, blk, None
+        self.f32, self.planes, self.planes_up, self.blk, self.blk_up, self.version = f32, planes, None, blk, None, None
 
     @property
     def channels(self):
@@ -555,6 +568,54 @@ class Act:
         if self.planes is None:
             self.planes = split_planes(self.f32)
         return self.planes
+
+    def get_blk_up(self):
+        """blocked pair planes of the x2-upsampled tensor (operand of conv_halo_kernel), cached"""
+        if self.blk_up is None:
+            self.blk_up = split_blocked([(self.f32, True)])
+        return self.blk_up
+
+
+# ---- fork / join of independent work inside one module call (e.g. a decoder depth head next to the next block's
+# up-convolution): the forked part runs on a per-(device, stream) side stream between two events.  Works eagerly and
+# under CUDA-graph capture (the events become graph edges, the two parts parallel branches).  Protocol that keeps the
+# caching allocator safe without record_stream: every fork starts with the side stream waiting on a fresh event of the
+# main stream, every fork is joined before its results are used, and tensors crossing streams stay referenced until the
+# join.
+_SIDE_STREAMS = {}
+_FORK = _os_environ_get("DVMVS_DECODER_FORK", "1") == "1"
+
+
+class Fork:
+    def __init__(self):
+        self.active = _FORK and not N.DRYRUN and torch.cuda.is_available()
+        if self.active:
+            self.main = torch.cuda.current_stream()
+            key = (self.main.device.index, self.main.cuda_stream)
+            side = _SIDE_STREAMS.get(key)
+            if side is None:
+                side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=self.main.device)
+            self.side = side
+
+    def __enter__(self):
+        if self.active:
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            self.side.wait_event(ev)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self._done = torch.cuda.Event()
+            self._done.record(self.side)
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.active:
+            self.main.wait_event(self._done)
 
 
 def to_act(x, name="input"):
@@ -598,9 +659,27 @@ class ConvLayer:
         return (_HALO and self.uses_tc() and pc.stride == 1 and pc.ksize >= 3 and hout * wout >= _HALO_MIN_PIXELS and
                 residual_mode in (N.RES_NONE, N.RES_SAME) and aux is None)
 
-    def run(self, sources, residual=None, residual_mode=N.RES_NONE, aux=None, want_f32=True, want_planes=True):
+    def path(self, hout, wout, residual_mode=N.RES_NONE, aux=None):
+        """which kernel family run() uses for an output map of hout x wout: 'halo', 'tc' or 'fp32'"""
+        if self.uses_halo(hout, wout, residual_mode, aux):
+            return "halo"
+        return "tc" if self.uses_tc() else "fp32"
+
+    def prestage_upsampled(self, act):
+        """Stage the x2-upsampled operand of `act` (a source this layer reads with SRC_UPSAMPLE2X) now, on the current
+        stream, in the layout run() will want; cached on the Act.  No-op on the fp32 path / for packed-source layers."""
+        if self.pack_sources:
+            return
+        kind = self.path(2 * act.f32.shape[1], 2 * act.f32.shape[2])
+        if kind == "halo":
+            act.get_blk_up()
+        elif kind == "tc":
+            act.get_planes(upsample=True)
+
+    def run(self, sources, residual=None, residual_mode=N.RES_NONE, aux=None, want_f32=True, want_planes=True, prestaged=None):
         """sources: list of (Act, mode).  Returns Act (or (Act, aux tensor)).  want_* only prune outputs of the
-        tensor-core path (the fp32 path always produces fp32)."""
+        tensor-core path (the fp32 path always produces fp32).  prestaged: the concatenated blocked operand of a
+        pack_sources layer on the halo path, already filled by the caller (split_blocked(..., only=, into=))."""
         pc = self.pc
         a0, m0 = sources[0]
         hin = (a0.f32 if a0.f32 is not None else a0.planes[0]).shape[1] * (2 if m0 == N.SRC_UPSAMPLE2X else 1)
@@ -611,9 +690,10 @@ class ConvLayer:
             # sources that already carry blocked planes (outputs of tensor-core layers on large maps) are used as they
             # are -- the kernel concatenates up to three sources along K; upsampled / fp32-only sources are staged
             if self.pack_sources:
-                blks = [split_blocked([(a.f32, mode == N.SRC_UPSAMPLE2X) for a, mode in sources])]
+                blks = [prestaged if prestaged is not None else split_blocked([(a.f32, mode == N.SRC_UPSAMPLE2X) for a, mode in sources])]
             else:
-                blks = [a.blk if (mode == N.SRC_DIRECT and a.blk is not None) else split_blocked([(a.f32, mode == N.SRC_UPSAMPLE2X)])
+                blks = [a.blk if (mode == N.SRC_DIRECT and a.blk is not None) else
+                        (a.blk_up if (mode == N.SRC_UPSAMPLE2X and a.blk_up is not None) else split_blocked([(a.f32, mode == N.SRC_UPSAMPLE2X)]))
                         for a, mode in sources]
             f32, oblk, onhwc = conv2d_halo(blks, self._phalo, residual=residual.f32 if residual is not None else None,
                                            terms=_TC_TERMS, want_f32=True, want_blk=True, want_nhwc=want_planes)
