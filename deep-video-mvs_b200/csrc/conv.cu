@@ -431,13 +431,15 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 constexpr int kLstmWarps = 8;
 
+// PPW = pixels per warp (ceil(h*w / kLstmWarps)), a template parameter so that each thread's gate / cell values are loaded
+// ONCE, all loads in flight together, and stay in registers across the four reduction passes (the kernel sits on the
+// loop-carried critical path of the pipeline; with run-time loops it paid three serialised global-load phases).
+template <int PPW>
 __global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float* __restrict__ gates, const float* __restrict__ c_in,
                                                                      float* __restrict__ h_out, float* __restrict__ c_out, int hw, int C) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sm[];           // [hw][32] values + reduction scratch
-  float* s_val = sm;
-  float* s_red = sm + (size_t)hw * 32;    // [kLstmWarps][32]
+  __shared__ float s_red[kLstmWarps * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const int b = blockIdx.y;
@@ -454,42 +456,55 @@ __global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float
     return t;
   };
 
-  // pass 1: LayerNorm statistics of cc_g over the spatial positions (two-pass: mean, then centred variance)
-  float s = 0.f;
-  for (int p = warp; p < hw; p += kLstmWarps) {
-    const float v = g[(size_t)p * 4 * C + 3 * C + c];
-    s_val[p * 32 + lane] = v;
-    s += v;
+  float vi[PPW], vf[PPW], vo[PPW], vg[PPW], vc[PPW];
+#pragma unroll
+  for (int j = 0; j < PPW; ++j) {
+    const int p = warp + j * kLstmWarps;
+    const bool ok = p < hw;
+    const float* gp = g + (size_t)(ok ? p : 0) * 4 * C;
+    vi[j] = ok ? gp[c] : 0.f;
+    vf[j] = ok ? gp[C + c] : 0.f;
+    vo[j] = ok ? gp[2 * C + c] : 0.f;
+    vg[j] = ok ? gp[3 * C + c] : 0.f;
+    vc[j] = ok ? c_in[((size_t)b * hw + (ok ? p : 0)) * C + c] : 0.f;
   }
+  // LayerNorm statistics of cc_g over the spatial positions (two-pass: mean, then centred variance)
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < PPW; ++j) s += vg[j];                  // absent positions hold 0
   const float mean_g = block_sum(s) * inv_n;
   s = 0.f;
-  for (int p = warp; p < hw; p += kLstmWarps) {
-    const float dlt = s_val[p * 32 + lane] - mean_g;
-    s += dlt * dlt;
+#pragma unroll
+  for (int j = 0; j < PPW; ++j) {
+    const float dlt = vg[j] - mean_g;
+    if (warp + j * kLstmWarps < hw) s += dlt * dlt;
   }
   const float rstd_g = rsqrtf(block_sum(s) * inv_n + 1e-5f);
-  // pass 2: c_next (pre-LN) = f*c + i*celu(LN(cc_g))
+  // c_next (pre-LN) = f*c + i*celu(LN(cc_g))
   s = 0.f;
-  for (int p = warp; p < hw; p += kLstmWarps) {
-    const float* gp = g + (size_t)p * 4 * C;
-    const float ig = sigmoidf_(gp[c]), fg = sigmoidf_(gp[C + c]);
-    const float gg = celu1((s_val[p * 32 + lane] - mean_g) * rstd_g);
-    const float cn = fg * c_in[((size_t)b * hw + p) * C + c] + ig * gg;
-    s_val[p * 32 + lane] = cn;
-    s += cn;
+#pragma unroll
+  for (int j = 0; j < PPW; ++j) {
+    const float ig = sigmoidf_(vi[j]), fg = sigmoidf_(vf[j]);
+    const float gg = celu1((vg[j] - mean_g) * rstd_g);
+    vg[j] = (warp + j * kLstmWarps < hw) ? fg * vc[j] + ig * gg : 0.f;      // vg now holds c_next (pre-LN)
+    s += vg[j];
   }
   const float mean_c = block_sum(s) * inv_n;
   s = 0.f;
-  for (int p = warp; p < hw; p += kLstmWarps) {
-    const float dlt = s_val[p * 32 + lane] - mean_c;
-    s += dlt * dlt;
+#pragma unroll
+  for (int j = 0; j < PPW; ++j) {
+    const float dlt = vg[j] - mean_c;
+    if (warp + j * kLstmWarps < hw) s += dlt * dlt;
   }
   const float rstd_c = rsqrtf(block_sum(s) * inv_n + 1e-5f);
-  for (int p = warp; p < hw; p += kLstmWarps) {
-    const float cn = (s_val[p * 32 + lane] - mean_c) * rstd_c;
-    const float og = sigmoidf_(g[(size_t)p * 4 * C + 2 * C + c]);
-    c_out[((size_t)b * hw + p) * C + c] = cn;
-    h_out[((size_t)b * hw + p) * C + c] = og * celu1(cn);
+#pragma unroll
+  for (int j = 0; j < PPW; ++j) {
+    const int p = warp + j * kLstmWarps;
+    if (p < hw) {
+      const float cn = (vg[j] - mean_c) * rstd_c;
+      c_out[((size_t)b * hw + p) * C + c] = cn;
+      h_out[((size_t)b * hw + p) * C + c] = sigmoidf_(vo[j]) * celu1(cn);
+    }
   }
 }
 
@@ -603,15 +618,14 @@ extern "C" int dvmvs_lstm_gates(const float* gates, const float* c_in, float* h_
   DVMVS_REQUIRE(gates && c_in && h_out && c_out, "lstm_gates: null pointer");
   DVMVS_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && C % 32 == 0, "lstm_gates: bad shape (C must be a multiple of 32)");
   const int hw = h * w;
-  const size_t smem = ((size_t)hw * 32 + kLstmWarps * 32) * sizeof(float);
-  DVMVS_REQUIRE(smem <= 200 * 1024, "lstm_gates: h*w=%d too large", hw);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(lstm_gates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  const int ppw = (hw + kLstmWarps - 1) / kLstmWarps;
+  DVMVS_REQUIRE(ppw <= 64, "lstm_gates: h*w=%d too large (bottleneck maps up to 512 positions)", hw);
   dim3 grid(C / 32, B);
-  launch_k(lstm_gates_kernel, grid, dim3(32 * kLstmWarps), smem, (cudaStream_t)stream, gates, c_in, h_out, c_out, hw, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ppw <= 2) launch_k(lstm_gates_kernel<2>, grid, dim3(32 * kLstmWarps), 0, st, gates, c_in, h_out, c_out, hw, C);
+  else if (ppw <= 8) launch_k(lstm_gates_kernel<8>, grid, dim3(32 * kLstmWarps), 0, st, gates, c_in, h_out, c_out, hw, C);
+  else if (ppw <= 16) launch_k(lstm_gates_kernel<16>, grid, dim3(32 * kLstmWarps), 0, st, gates, c_in, h_out, c_out, hw, C);
+  else launch_k(lstm_gates_kernel<64>, grid, dim3(32 * kLstmWarps), 0, st, gates, c_in, h_out, c_out, hw, C);
   return check_launch("lstm_gates_kernel");
 }
 

@@ -248,9 +248,21 @@ class FeatureShrinker(NativeModule):
         inner, layer = self.packed()
         last = inner[4].run([(feats[4], D)])
         outs = [None] * 4
+        keep, forks = [last], []          # tensors read on the side stream stay referenced until the joins
         for i in (3, 2, 1, 0):
             last = inner[i].run([(feats[i], D)], residual=last, residual_mode=N.RES_NEAREST_UP)
-            outs[i] = layer[i].run([(last, D)])
+            keep.append(last)
+            if i > 0:
+                # the 3x3 output conv of level i is off the top-down chain (inner[i-1] only needs `last`): side stream
+                f = ops.Fork()
+                with f:
+                    outs[i] = layer[i].run([(last, D)])
+                forks.append(f)
+            else:
+                outs[i] = layer[i].run([(last, D)])
+        for f in forks:
+            f.join()
+        del keep
         return outs
 
     def forward(self, layer1, layer2, layer3, layer4, layer5):
@@ -369,10 +381,12 @@ class LSTMFusion(NativeModule):
     def _pack(self):
         return ()
 
-    def forward(self, current_encoding, current_state, previous_pose, current_pose, estimated_current_depth, camera_matrix):
+    def forward(self, current_encoding, current_state, previous_pose, current_pose, estimated_current_depth, camera_matrix,
+                input_gates=None):
+        """input_gates (optional, beyond the reference signature): lstm_cell.input_gates(current_encoding) computed earlier."""
         batch, channel, height, width = current_encoding.size()
         if current_state is None:                                                        # model.py:324-326
             current_state = self.lstm_cell.init_hidden(batch_size=batch, image_size=(height, width))
         return self.lstm_cell(input_tensor=current_encoding, cur_state=list(current_state), previous_pose=previous_pose,
                               current_pose=current_pose, estimated_current_depth=estimated_current_depth,
-                              camera_matrix=camera_matrix)
+                              camera_matrix=camera_matrix, input_gates=input_gates)

@@ -256,6 +256,8 @@ def _stage_enc(mods, slot, swept):
     """Cost-volume encoder (still independent of the recurrent state)."""
     (f2, f4, f8, f16, cv), half_K = swept
     enc = mods["cve"](features_half=f2, features_quarter=f4, features_one_eight=f8, features_one_sixteen=f16, cost_volume=cv)
+    if "lstm" in mods:      # the input half of the ConvLSTM gate convolution does not depend on the recurrent state either
+        slot["input_gates"] = mods["lstm"].lstm_cell.input_gates(enc[4])
     return enc, half_K
 
 
@@ -281,7 +283,8 @@ def _stage_rec(mods, state, slot, enc, half_K):
     else:
         de = torch.zeros(size=(B, 1, H // 32, W // 32), device=reference_image.device)
     state.lstm_state = mods["lstm"](current_encoding=bottom, current_state=state.lstm_state, previous_pose=state.previous_pose,
-                                    current_pose=reference_pose, estimated_current_depth=de, camera_matrix=lstm_K)
+                                    current_pose=reference_pose, estimated_current_depth=de, camera_matrix=lstm_K,
+                                    input_gates=slot.get("input_gates"))
     pred = mods["cvd"](reference_image, s0, s1, s2, s3, state.lstm_state[0])[0]
     state.previous_depth = pred.view(B, 1, H, W)
     state.previous_pose = reference_pose
