@@ -98,7 +98,7 @@ constexpr int kGroup = 8;
 constexpr int kSweepThreads = 256;
 
 struct __align__(16) SweepTapParams {
-  int off[4];     // element offsets of the 4 taps inside one measurement feature map (channel 0)
+  unsigned off[4];   // BYTE offsets of the 4 taps from the start of the measurement feature tensor (clip offset included)
   float w[4];     // bilinear weights, 0 for taps outside the image
 };
 // The two 16-byte halves of entry e are stored at chunk slots 2e + (c ^ ((e >> 2) & 1)): eight consecutive threads
@@ -106,7 +106,7 @@ struct __align__(16) SweepTapParams {
 __device__ __forceinline__ int sweep_chunk(int e, int c) { return 2 * e + (c ^ ((e >> 2) & 1)); }
 
 __device__ __forceinline__ void sweep_phase_a(const SweepParams& p, const float* s_G, const float* s_kd, SweepTapParams* buf, int m,
-                                              int d0, int u0, int v, int npix, float sx, float sy) {
+                                              int d0, int u0, int v, int npix, float sx, float sy, unsigned clip_off) {
   const int pix = threadIdx.x & (kPix - 1), pl = threadIdx.x >> 5;
   const int d = min(d0 + pl, p.D - 1);
   const float uf = (float)(u0 + min(pix, npix - 1)), vf = (float)v;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void sweep_phase_a(const SweepParams& p, const float*
   const float r = __frcp_rn(q2 + 1e-8f);
   const float xs = q0 * r * sx, ys = q1 * r * sy;
   SweepTapParams t;
-  t.off[0] = t.off[1] = t.off[2] = t.off[3] = 0;
+  t.off[0] = t.off[1] = t.off[2] = t.off[3] = clip_off;
   t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
   // some tap inside the image  <=>  -1 < xs < w  and  -1 < ys < h   (false for NaN / Inf)
   if (xs > -1.f && xs < (float)p.w && ys > -1.f && ys < (float)p.h) {
@@ -128,10 +128,10 @@ __device__ __forceinline__ void sweep_phase_a(const SweepParams& p, const float*
     const int x0 = (int)x0f, y0 = (int)y0f;
     const bool vx0 = x0 >= 0, vx1 = x0 + 1 < p.w, vy0 = y0 >= 0, vy1 = y0 + 1 < p.h;
     const int xa = max(x0, 0), xb = min(x0 + 1, p.w - 1), ya = max(y0, 0), yb = min(y0 + 1, p.h - 1);
-    t.off[0] = (ya * p.w + xa) * 32;
-    t.off[1] = (ya * p.w + xb) * 32;
-    t.off[2] = (yb * p.w + xa) * 32;
-    t.off[3] = (yb * p.w + xb) * 32;
+    t.off[0] = clip_off + (unsigned)(ya * p.w + xa) * 128u;
+    t.off[1] = clip_off + (unsigned)(ya * p.w + xb) * 128u;
+    t.off[2] = clip_off + (unsigned)(yb * p.w + xa) * 128u;
+    t.off[3] = clip_off + (unsigned)(yb * p.w + xb) * 128u;
     t.w[0] = (vy0 && vx0) ? gx * gy : 0.f;
     t.w[1] = (vy0 && vx1) ? fx * gy : 0.f;
     t.w[2] = (vy1 && vx0) ? gx * fy : 0.f;
@@ -143,6 +143,7 @@ __device__ __forceinline__ void sweep_phase_a(const SweepParams& p, const float*
   chunks[sweep_chunk(e, 1)] = *reinterpret_cast<const int4*>(t.w);
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(SweepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_ref = reinterpret_cast<float*>(smem_raw);                                     // [kPix][32]
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(Sweep
   const float sx = (float)(p.w - 1) / (float)p.w, sy = (float)(p.h - 1) / (float)p.h;   // the align_corners "shrink" (App. A.1)
   const int n_groups = (p.D + kGroup - 1) / kGroup;
   const int n_steps = n_groups * p.M;                     // step = (plane group, measurement frame), frame fastest
-  sweep_phase_a(p, s_G, s_kd, s_par, 0, 0, u0, v, npix, sx, sy);
+  const unsigned clip_off = (unsigned)b * (unsigned)(p.h * p.w) * 128u;     // host guarantees B*h*w*128 < 2^32
+  sweep_phase_a(p, s_G, s_kd, s_par, 0, 0, u0, v, npix, sx, sy, clip_off);
   {  // wait for the TMA bytes
     uint32_t done = 0;
     while (!done) {
@@ -218,26 +220,26 @@ __global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(Sweep
   const int pix = warp * 4 + (lane >> 3);
   const bool active = pix < npix;
   const float4 f1 = *reinterpret_cast<const float4*>(s_ref + (active ? pix : 0) * 32 + sub * 4);
-  const size_t img_off = (size_t)b * p.h * p.w * 32 + sub * 4;
-  const float scale = (p.mode == DVMVS_SWEEP_DOT) ? (1.f / 32.f) : 1.f;     // utils.py:82 (/C) vs :84
+  const float scale = (MODE == DVMVS_SWEEP_DOT) ? (1.f / 32.f) : 1.f;       // utils.py:82 (/C) vs :84
 
   float acc[kGroup];
 #pragma unroll
   for (int k = 0; k < kGroup; ++k) acc[k] = 0.f;
 
+  const int e0 = active ? pix : 0;
+  int g = 0, m = 0;                                       // step = g * M + m, kept as counters (no division in the loop)
   for (int step = 0; step < n_steps; ++step) {
-    const int g = step / p.M, m = step - g * p.M;
     if (step + 1 < n_steps) {
-      const int g1 = (step + 1) / p.M, m1 = (step + 1) - g1 * p.M;
-      sweep_phase_a(p, s_G, s_kd, s_par + ((step + 1) & 1) * kGroup * kPix, m1, g1 * kGroup, u0, v, npix, sx, sy);
+      const int m1 = (m + 1 == p.M) ? 0 : m + 1, g1 = (m + 1 == p.M) ? g + 1 : g;
+      sweep_phase_a(p, s_G, s_kd, s_par + ((step + 1) & 1) * kGroup * kPix, m1, g1 * kGroup, u0, v, npix, sx, sy, clip_off);
     }
     const int4* par = reinterpret_cast<const int4*>(s_par + (step & 1) * kGroup * kPix);
-    const int e0 = active ? pix : 0;
-    const float* img = p.meas[m] + img_off;
+    // per-lane 64-bit base (frame m, this lane's 4 channels) + 32-bit byte offsets from phase A: one wide add per tap
+    const char* img = reinterpret_cast<const char*>(p.meas[m]) + sub * 16;
 #pragma unroll
     for (int k = 0; k < kGroup; ++k) {
       const int e = k * kPix + e0;
-      const int4 off = par[sweep_chunk(e, 0)];
+      const uint4 off = *reinterpret_cast<const uint4*>(&par[sweep_chunk(e, 0)]);
       const float4 wt = *reinterpret_cast<const float4*>(&par[sweep_chunk(e, 1)]);
       const float4 t00 = __ldg(reinterpret_cast<const float4*>(img + off.x));
       const float4 t01 = __ldg(reinterpret_cast<const float4*>(img + off.y));
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(Sweep
       ws.z = fmaf(t11.z, wt.w, fmaf(t10.z, wt.z, fmaf(t01.z, wt.y, t00.z * wt.x)));
       ws.w = fmaf(t11.w, wt.w, fmaf(t10.w, wt.z, fmaf(t01.w, wt.y, t00.w * wt.x)));
       float part;
-      if (p.mode == DVMVS_SWEEP_DOT)
+      if (MODE == DVMVS_SWEEP_DOT)
         part = fmaf(f1.w, ws.w, fmaf(f1.z, ws.z, fmaf(f1.y, ws.y, f1.x * ws.x)));
       else
         part = fabsf(f1.x - ws.x) + fabsf(f1.y - ws.y) + fabsf(f1.z - ws.z) + fabsf(f1.w - ws.w);
@@ -280,6 +282,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(Sweep
       for (int k = 0; k < kGroup; ++k) acc[k] = 0.f;
     }
     __syncthreads();
+    if (++m == p.M) { m = 0; ++g; }
   }
   // coalesced write-out: [npix][D] is contiguous in the channel-last cost volume
   float* o = p.out + (((size_t)b * p.h + v) * p.w + u0) * p.D;
@@ -500,14 +503,15 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
   p.mode = mode;
   cudaStream_t s = (cudaStream_t)stream;
   const bool aligned = ((uintptr_t)ref % 16 == 0);
-  bool fast = (C == 32) && aligned;
+  bool fast = (C == 32) && aligned && ((size_t)B * h * w * 128 < ((size_t)1 << 32));   // 32-bit tap byte offsets
   for (int m = 0; m < M && fast; ++m) fast = ((uintptr_t)meas_host[m] % 16 == 0);
   if (fast) {
     const int tiles = B * h * ((w + kPix - 1) / kPix);
     const size_t smem = (size_t)(kPix * 32 + M * D * 4 + kMaxMeas * 12 + kPix * D) * sizeof(float) + 2 * kGroup * kPix * sizeof(SweepTapParams);
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(plane_sweep_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(plane_sweep_c32_kernel<DVMVS_SWEEP_SAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       attr_set = true;
     }
     DVMVS_REQUIRE(smem <= 96 * 1024, "plane_sweep: shared memory %zu too large", smem);
@@ -520,7 +524,10 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
       if (want > smem_launch && want <= 96 * 1024) smem_launch = want;
       else if (want > 96 * 1024) smem_launch = 96 * 1024;
     }
-    launch_k(plane_sweep_c32_kernel, dim3(tiles), dim3(kSweepThreads), smem_launch, s, p);
+    if (mode == DVMVS_SWEEP_DOT)
+      launch_k(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT>, dim3(tiles), dim3(kSweepThreads), smem_launch, s, p);
+    else
+      launch_k(plane_sweep_c32_kernel<DVMVS_SWEEP_SAD>, dim3(tiles), dim3(kSweepThreads), smem_launch, s, p);
     return check_launch("plane_sweep_c32_kernel");
   }
   const size_t total = (size_t)B * h * w * D;

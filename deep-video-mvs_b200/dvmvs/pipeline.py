@@ -41,15 +41,87 @@ def build_modules(weights, device="cuda", n_depth_levels=64, pairnet=False):
     return mods
 
 
+class FeatureCache:
+    """half-resolution FPN features of past reference frames, keyed by caller-supplied frame ids.
+
+    The reference recomputes FeatureExtractor + FeatureShrinker for every measurement frame of every keyframe
+    (run-testing.py:153-156, run-testing-online.py:159-162) although each measurement frame was the reference frame of an
+    earlier keyframe (the keyframe buffer only holds past reference frames).  The modules are in eval mode, so those
+    features are the same numbers; this cache keeps them in a fixed ring of device buffers (FIFO eviction, capacity =
+    the keyframe buffer size, Config.test_keyframe_buffer_size) and hands them back.  Ids are explicit because the scripts
+    re-upload the images as fresh tensors each keyframe: nothing on the device identifies a frame without a host sync.
+    A miss is not an error -- the caller computes the features from the image and stores them."""
+
+    def __init__(self, capacity=30):
+        if capacity < 1:
+            raise ValueError("FeatureCache capacity must be >= 1")
+        self.capacity = int(capacity)
+        self._ring = [None] * self.capacity      # (B, h, w, 32) channel-last buffers, allocated on first use
+        self._index = {}                          # frame id -> ring index
+        self._owner = [None] * self.capacity
+        self._next = 0
+        self.hits = 0
+        self.misses = 0
+
+    def clear(self):
+        self._index.clear()
+        self._owner = [None] * self.capacity
+
+    def __contains__(self, frame_id):
+        return frame_id in self._index
+
+    def lookup(self, frame_id):
+        """Cached (B,32,h,w) API tensor (channels_last view of the ring buffer) or None."""
+        idx = self._index.get(frame_id)
+        if idx is None:
+            self.misses += 1
+            return None
+        self.hits += 1
+        return self._ring[idx].permute(0, 3, 1, 2)
+
+    def store(self, frame_id, half_features):
+        """Copies (B,32,h,w) features into the ring on the current stream (a D2D copy; the ring outlives the caller's tensor)."""
+        idx = self._index.get(frame_id)
+        if idx is None:
+            idx = self._next
+            self._next = (self._next + 1) % self.capacity
+            if self._owner[idx] is not None:
+                del self._index[self._owner[idx]]
+            self._owner[idx] = frame_id
+            self._index[frame_id] = idx
+        src = half_features.permute(0, 2, 3, 1)
+        if self._ring[idx] is None or self._ring[idx].shape != src.shape or self._ring[idx].device != src.device:
+            self._ring[idx] = torch.empty(tuple(src.shape), dtype=torch.float32, device=src.device)
+        self._ring[idx].copy_(src)
+        return idx
+
+
 def feature_stage(mods, reference_image, reference_pose, measurement_images, measurement_poses, full_K,
-                  min_depth=0.25, max_depth=20.0, n_depth_levels=64, batch_features=True):
+                  min_depth=0.25, max_depth=20.0, n_depth_levels=64, batch_features=True, cache=None, reference_id=None,
+                  measurement_ids=None):
     """First half of a keyframe -- everything that does not depend on the recurrent state: FeatureExtractor +
     FeatureShrinker on the reference and measurement images and the fused plane-sweep cost volume
-    (run-testing.py:153-171).  Returns (f2, f4, f8, f16, cost_volume, half_K)."""
+    (run-testing.py:153-171).  Returns (f2, f4, f8, f16, cost_volume, half_K).
+
+    With `cache` (FeatureCache) and frame ids, measurement frames whose half-resolution features are cached skip
+    FeatureExtractor + FeatureShrinker (row f1); the reference frame's features are stored under `reference_id`."""
     B = reference_image.shape[0]
     half_K = full_K.clone()
     half_K[:, 0:2, :] = half_K[:, 0:2, :] / 2.0
-    if batch_features and len(measurement_images) > 0:
+    if cache is not None:
+        if measurement_ids is None or len(measurement_ids) != len(measurement_images):
+            raise ValueError("feature cache: need one frame id per measurement image")
+        meas_half = [cache.lookup(i) for i in measurement_ids]
+        todo = [m for m, t in enumerate(meas_half) if t is None]
+        stacked = torch.cat([reference_image] + [measurement_images[m] for m in todo], dim=0) if todo else reference_image
+        a2, a4, a8, a16 = mods["fpn"](*mods["fe"](stacked))
+        if todo:
+            f2, f4, f8, f16 = a2[:B], a4[:B], a8[:B], a16[:B]
+        else:
+            f2, f4, f8, f16 = a2, a4, a8, a16
+        for n, m in enumerate(todo):
+            meas_half[m] = a2[(n + 1) * B:(n + 2) * B]
+    elif batch_features and len(measurement_images) > 0:
         stacked = torch.cat([reference_image] + list(measurement_images), dim=0)
         a2, a4, a8, a16 = mods["fpn"](*mods["fe"](stacked))
         f2, f4, f8, f16 = a2[:B], a4[:B], a8[:B], a16[:B]
@@ -63,6 +135,11 @@ def feature_stage(mods, reference_image, reference_pose, measurement_images, mea
     cv = cost_volume_fusion(image1=f2, image2s=meas_half, pose1=reference_pose, pose2s=measurement_poses, K=half_K,
                             warp_grid=None, min_depth=min_depth, max_depth=max_depth, n_depth_levels=n_depth_levels,
                             device=reference_image.device, dot_product=True)
+    if cache is not None:       # after the sweep: hits are views of ring entries that a store may evict and overwrite
+        for m in todo:
+            cache.store(measurement_ids[m], meas_half[m])
+        if reference_id is not None:
+            cache.store(reference_id, f2)
     return f2, f4, f8, f16, cv, half_K
 
 
@@ -97,15 +174,16 @@ def recurrent_stage(mods, state, features, reference_image, reference_pose, full
 
 
 def keyframe(mods, state, reference_image, reference_pose, measurement_images, measurement_poses, full_K,
-             min_depth=0.25, max_depth=20.0, n_depth_levels=64, batch_features=True):
+             min_depth=0.25, max_depth=20.0, n_depth_levels=64, batch_features=True, cache=None, reference_id=None,
+             measurement_ids=None):
     """One keyframe for B independent clips (tensors batched on dim 0, all CUDA).  With 'lstm' in mods this is the
     fusionnet loop body, without it the pairnet one.  Returns (depth (B,H,W), state).
 
     batch_features=True runs FeatureExtractor + FeatureShrinker ONCE over the reference and the M measurement images
     stacked on the batch axis (eval-mode BatchNorm: identical results, 1/(M+1) of the launches); False reproduces the
-    script's M+1 separate passes (run-testing.py:153-159)."""
+    script's M+1 separate passes (run-testing.py:153-159).  cache / reference_id / measurement_ids: see FeatureCache."""
     feats = feature_stage(mods, reference_image, reference_pose, measurement_images, measurement_poses, full_K, min_depth,
-                          max_depth, n_depth_levels, batch_features)
+                          max_depth, n_depth_levels, batch_features, cache, reference_id, measurement_ids)
     return recurrent_stage(mods, state, feats, reference_image, reference_pose, full_K)
 
 
@@ -219,18 +297,24 @@ def _stage_side_inputs(slot):
     slot["lstm_K"] = lstm_K
 
 
+def _stacked_images(slot):
+    """Reference + measurement images on the batch axis; the reference image alone when the measurement features come
+    from the feature cache (slot["meas_half"], row f1)."""
+    if slot.get("meas_half") is not None:
+        return slot["ref_image"]
+    return torch.cat([slot["ref_image"]] + list(slot["meas_images"]), dim=0)
+
+
 def _stage_fe(mods, slot):
     """Stage 1 of 3: MnasNet trunk on the reference + measurement images stacked on the batch axis."""
     _stage_side_inputs(slot)
-    stacked = torch.cat([slot["ref_image"]] + list(slot["meas_images"]), dim=0)
-    return mods["fe"](stacked)
+    return mods["fe"](_stacked_images(slot))
 
 
 def _stage_fe_head(mods, slot):
     """MnasNet trunk up to layer3 (1/8 resolution) on the stacked images."""
     _stage_side_inputs(slot)
-    stacked = torch.cat([slot["ref_image"]] + list(slot["meas_images"]), dim=0)
-    return mods["fe"].forward_head(stacked)
+    return mods["fe"].forward_head(_stacked_images(slot))
 
 
 def _stage_fe_tail(mods, slot, head):
@@ -243,8 +327,13 @@ def _stage_sweep(mods, slot, fe_out, min_depth, max_depth, n_depth_levels):
     B = slot["ref_image"].shape[0]
     M = len(slot["meas_images"])
     a2, a4, a8, a16 = mods["fpn"](*fe_out)
-    f2, f4, f8, f16 = a2[:B], a4[:B], a8[:B], a16[:B]
-    meas_half = [a2[(m + 1) * B:(m + 2) * B] for m in range(M)]
+    if slot.get("meas_half") is not None:         # feature cache: batch = the reference frames only
+        f2, f4, f8, f16 = a2, a4, a8, a16
+        meas_half = [t.permute(0, 3, 1, 2) for t in slot["meas_half"]]
+        slot["ref_half"] = f2                     # the engine copies it into the cache ring after the stage's graph
+    else:
+        f2, f4, f8, f16 = a2[:B], a4[:B], a8[:B], a16[:B]
+        meas_half = [a2[(m + 1) * B:(m + 2) * B] for m in range(M)]
     half_K = slot["full_K"].clone()
     half_K[:, 0:2, :] = half_K[:, 0:2, :] / 2.0
     cv = cost_volume_fusion(image1=f2, image2s=meas_half, pose1=slot["ref_pose"], pose2s=slot["meas_poses"], K=half_K, warp_grid=None,
@@ -307,9 +396,11 @@ class PipelinedFusionnet:
     """
 
     def __init__(self, mods, batch, height, width, n_measurement_frames, min_depth=0.25, max_depth=20.0, n_depth_levels=64,
-                 device=None, n_stages=3):
+                 device=None, n_stages=3, feature_cache=0):
         if n_stages not in (2, 3, 4, 5):
             raise ValueError("n_stages must be 2, 3, 4 or 5")
+        if feature_cache and n_stages < 3:
+            raise ValueError("the feature cache needs n_stages >= 3 (feature pyramid + plane sweep in one stage)")
         self.mods, self.B, self.H, self.W, self.M = mods, batch, height, width, n_measurement_frames
         self.min_depth, self.max_depth, self.D = min_depth, max_depth, n_depth_levels
         dev = device or next(mods["fe"].parameters()).device
@@ -324,6 +415,14 @@ class PipelinedFusionnet:
                                "out": [None] * n_stages, "depth": z(batch, height, width),
                                "graph": [dict() for _ in range(n_stages)],
                                "done": [torch.cuda.Event() for _ in range(n_stages)]})
+        # row f1: measurement features from a ring of past reference-frame features instead of M extra FE + FPN passes
+        if feature_cache and feature_cache < n_measurement_frames + 1:
+            raise ValueError("feature_cache capacity must be at least n_measurement_frames + 1")
+        self.cache = FeatureCache(feature_cache) if feature_cache else None
+        if self.cache is not None:
+            for slot in self.slots:
+                slot["meas_half"] = [z(batch, height // 2, width // 2, 32) for _ in range(n_measurement_frames)]
+        self._sweep_stage = {2: 0, 3: 1, 4: 2, 5: 2}[n_stages]      # the stage that holds FPN + plane sweep
         import os as _os
         # DVMVS_PIPE_PRIO=1 gives the last stage (the one carrying the loop dependence) a high-priority stream; measured
         # slower on B200 (922 vs 1067 keyframes/s at 3 stages), so it is off by default
@@ -342,6 +441,7 @@ class PipelinedFusionnet:
         self.kernels_per_keyframe = 0
 
     def reset(self):
+        """TRACKING LOST / new clip: drops the recurrent state (the feature cache is keyed by frame id and stays valid)."""
         self._has_state = False
 
     # -- stage bodies -----------------------------------------------------------------------------------------------
@@ -418,18 +518,35 @@ class PipelinedFusionnet:
         torch.cuda.synchronize(self.device)
 
     # -- steady state ----------------------------------------------------------------------------------------------
-    def submit(self, reference_image, reference_pose, measurement_images, measurement_poses, full_K, out=None):
+    def submit(self, reference_image, reference_pose, measurement_images, measurement_poses, full_K, out=None,
+               reference_id=None, measurement_ids=None):
         """Enqueue keyframe t (inputs CPU-pinned or CUDA).  If `out` (pinned host or CUDA tensor (B,H,W)) is given the
-        depth is copied into it on the last stage's stream; otherwise read eng.depth_of(t) after synchronisation."""
+        depth is copied into it on the last stage's stream; otherwise read eng.depth_of(t) after synchronisation.
+
+        Engines built with feature_cache=N take frame ids: `measurement_ids[m]` names measurement frame m, `reference_id`
+        the reference frame.  A measurement frame whose id is in the cache needs no image (pass None): its features are
+        copied from the ring; on a miss the features are computed from the image (eagerly, on the sweep stage's stream)
+        and cached.  The reference frame's features enter the ring under `reference_id`."""
         n, last = self.n_stages, self.n_stages - 1
         slot = self.slots[self.t % n]
         with_state = self._has_state
+        hits = None
+        if self.cache is not None:
+            if measurement_ids is None or len(measurement_ids) != self.M:
+                raise ValueError("feature cache: need %d measurement frame ids" % self.M)
+            hits = [i in self.cache for i in measurement_ids]
+            measurement_images = list(measurement_images)
+            for m, hit in enumerate(hits):
+                if not hit and measurement_images[m] is None:
+                    raise ValueError("feature cache miss for frame id %r and no image given" % (measurement_ids[m],))
+        elif reference_id is not None or measurement_ids is not None:
+            raise ValueError("frame ids given but the engine was built without feature_cache")
         # the inputs were produced on the caller's stream: order the first stage after it and keep CUDA inputs alive
         # (caching-allocator wise) until our copies on the stage stream have run
         caller = torch.cuda.current_stream(self.device)
         self.streams[0].wait_stream(caller)
         for t_in in [reference_image, reference_pose, full_K] + list(measurement_images) + list(measurement_poses):
-            if t_in.is_cuda:
+            if t_in is not None and t_in.is_cuda:
                 t_in.record_stream(self.streams[0])
         if out is not None and out.is_cuda:
             out.record_stream(self.streams[last])
@@ -442,15 +559,20 @@ class PipelinedFusionnet:
                     slot["ref_image"].copy_(reference_image, non_blocking=True)
                     slot["ref_pose"].copy_(reference_pose, non_blocking=True)
                     slot["full_K"].copy_(full_K, non_blocking=True)
-                    for dst, src in zip(slot["meas_images"], measurement_images):
-                        dst.copy_(src, non_blocking=True)
+                    for m, (dst, src) in enumerate(zip(slot["meas_images"], measurement_images)):
+                        if hits is None or not hits[m]:            # cached measurement frames need no image upload
+                            dst.copy_(src, non_blocking=True)
                     for dst, src in zip(slot["meas_poses"], measurement_poses):
                         dst.copy_(src, non_blocking=True)
                 else:
                     stream.wait_event(slot["done"][i - 1])
+                if hits is not None and i == self._sweep_stage:
+                    self._fill_measurement_features(slot, measurement_ids, hits)
                 if key not in slot["graph"][i]:
                     self._capture(i, slot, with_state)
                 slot["graph"][i][key].replay()
+                if hits is not None and i == self._sweep_stage and reference_id is not None:
+                    self.cache.store(reference_id, slot["ref_half"])
                 if i == last and out is not None:
                     out.copy_(slot["depth"], non_blocking=True)
                 slot["done"][i].record(stream)
@@ -459,14 +581,35 @@ class PipelinedFusionnet:
         self.t += 1
         return self.t - 1
 
+    def _fill_measurement_features(self, slot, measurement_ids, hits):
+        """Feature-cache engines, on the sweep stage's stream before its graph: slot["meas_half"][m] <- ring entry (hit) or
+        <- FeatureShrinker(FeatureExtractor(image)) computed here and stored in the ring (miss)."""
+        for m, hit in enumerate(hits):            # hits first: a miss's store may evict the oldest ring entry
+            if hit:
+                slot["meas_half"][m].copy_(self.cache.lookup(measurement_ids[m]).permute(0, 2, 3, 1))
+        for m, hit in enumerate(hits):
+            if not hit:
+                self.cache.misses += 1
+                with torch.no_grad():
+                    half, _, _, _ = self.mods["fpn"](*self.mods["fe"](slot["meas_images"][m]))
+                self.cache.store(measurement_ids[m], half)
+                slot["meas_half"][m].copy_(half.permute(0, 2, 3, 1))
+
     def prime(self, reference_image, reference_pose, measurement_images, measurement_poses, full_K):
         """Captures every (stage, slot) graph -- including both variants of the last stage -- by running 2*n_stages throw-away
         keyframes, then resets the clip state.  Optional: submit() captures lazily; call this to keep the one-off
         captures out of a timed or latency-sensitive region."""
-        for _ in range(2 * self.n_stages):
-            self.submit(reference_image, reference_pose, measurement_images, measurement_poses, full_K)
+        for k in range(2 * self.n_stages):
+            if self.cache is not None:
+                self.submit(reference_image, reference_pose, measurement_images, measurement_poses, full_K,
+                            reference_id=("prime", k), measurement_ids=[("prime-m", k, m) for m in range(self.M)])
+            else:
+                self.submit(reference_image, reference_pose, measurement_images, measurement_poses, full_K)
         self.synchronize()
         self.reset()
+        if self.cache is not None:
+            self.cache.clear()
+            self.cache.hits = self.cache.misses = 0
 
     def depth_of(self, t):
         return self.slots[t % self.n_stages]["depth"]

@@ -30,6 +30,15 @@ for backend in ("fp32", "tc"):
                                          T(clip["K"])[None], n_depth_levels=D, batch_features=batch_features)
             assert tuple(pred.shape) == (1, H, W), pred.shape
             assert tuple(st.lstm_state[0].shape) == (1, 512, H // 32, W // 32)
+    # row f1: measurement features through the feature cache (hits skip FE + FPN; stores after the sweep)
+    cache, st = pipeline.FeatureCache(capacity=M + 1), pipeline.KeyframeState()
+    for ref_i, meas_i in clip["frames"]:
+        T = torch.from_numpy
+        pred, st = pipeline.keyframe(mods, st, T(clip["images"][ref_i])[None], T(clip["poses"][ref_i])[None],
+                                     [T(clip["images"][j])[None] for j in meas_i], [T(clip["poses"][j])[None] for j in meas_i],
+                                     T(clip["K"])[None], n_depth_levels=D, cache=cache, reference_id=ref_i, measurement_ids=meas_i)
+        assert tuple(pred.shape) == (1, H, W)
+    assert cache.misses == M and cache.hits == M, (cache.hits, cache.misses)      # keyframe 0: M misses; keyframe 1: M hits
     # the pipeline engine's stage functions (split MnasNet trunk, sweep / encoder split) compose to a keyframe
     T = torch.from_numpy
     ref_i, meas_i = clip["frames"][0]

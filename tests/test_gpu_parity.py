@@ -361,6 +361,48 @@ def test_pipeline_keyframe_and_cuda_graph_engine_match_script_sequence(oracle, s
             assert oracle.rel_l1_inverse_depth(got.cpu().numpy(), e) <= 1e-6, "pipeline with %d stages" % (pi + 2)
 
 
+def test_feature_cache_reproduces_recomputed_features(oracle, synth):
+    """measurement features taken from the feature cache (keyed by frame id) instead of re-running
+    FeatureExtractor + FeatureShrinker give the script sequence's depths -- eager keyframe() and the pipelined engine,
+    cold cache (misses computed from the images), steady state (all hits, no measurement images passed) and FIFO
+    eviction with the smallest legal capacity."""
+    from dvmvs import pipeline
+    H, W, D, M = 64, 96, 64, 2
+    w = helpers.oracle_weights(oracle, synth, 13, n_depth_levels=D)
+    mods = helpers.build_product_modules(w, n_depth_levels=D)
+    clip = synth.make_clip(9, 7, H, W, M)
+    K = _cuda(clip["K"])[None]
+    st_a, st_b = helpers.ProductState(), pipeline.KeyframeState()
+    cache = pipeline.FeatureCache(capacity=M + 1)
+    pipes = [pipeline.PipelinedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=ns,
+                                         feature_cache=cap) for ns, cap in ((3, 8), (5, M + 1))]
+    expected, piped = [], [[] for _ in pipes]
+    with torch.no_grad():
+        for t, (ref_i, meas_i) in enumerate(clip["frames"]):
+            args = (_cuda(clip["images"][ref_i])[None], _cuda(clip["poses"][ref_i])[None], [_cuda(clip["images"][j])[None] for j in meas_i],
+                    [_cuda(clip["poses"][j])[None] for j in meas_i], K)
+            a, st_a = helpers.product_fusionnet_step(mods, st_a, *args, n_depth_levels=D)
+            b, st_b = pipeline.keyframe(mods, st_b, *args, n_depth_levels=D, cache=cache, reference_id=ref_i, measurement_ids=meas_i)
+            assert oracle.rel_l1_inverse_depth(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
+            expected.append(a.cpu().numpy())
+            for pi, pipe in enumerate(pipes):
+                out = torch.empty((1, H, W), dtype=torch.float32, device=DEV)
+                # steady state: every measurement frame was a reference frame before -> no images needed at all
+                images = args[2] if t == 0 else [None] * M
+                pipe.submit(args[0], args[1], images, args[3], K, out=out, reference_id=ref_i, measurement_ids=meas_i)
+                piped[pi].append(out)
+        for pipe in pipes:
+            pipe.synchronize()
+    assert cache.misses == M and cache.hits == M * (len(clip["frames"]) - 1)
+    for pi, pipe in enumerate(pipes):
+        assert pipe.cache.misses == M and pipe.cache.hits == M * (len(clip["frames"]) - 1)
+        for e, got in zip(expected, piped[pi]):
+            assert oracle.rel_l1_inverse_depth(got.cpu().numpy(), e) <= 1e-5, "cached pipeline %d" % pi
+    # a miss without an image is an error, as is a cache-less engine handed ids
+    with pytest.raises(ValueError):
+        pipes[0].submit(args[0], args[1], [None] * M, args[3], K, reference_id=10 ** 6, measurement_ids=[10 ** 6 + 1, 10 ** 6 + 2])
+
+
 # ------------------------------------------------------------------------------------------------ tcgen05 backend
 TC_CASES = [
     # name, B, H, W, [src real channels], Cout, k, stride, act, block_n, terms, tol
