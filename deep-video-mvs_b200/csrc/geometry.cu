@@ -290,6 +290,117 @@ __global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(Sweep
   for (int i = tid; i < n_items; i += kSweepThreads) o[i] = s_out[i];
 }
 
+// =====================================================================================================
+// Backward of the plane sweep (training entry point fusionnet/run-training.py:231)
+// =====================================================================================================
+// cost[b,d,v,u] = 1/(M*32) * sum_m sum_c f1[c] * sum_t w_t f2_m[q_t][c]      (dot-product mode, utils.py:45-107)
+//   d cost / d f1[c]        = 1/(M*32) * sum_{m,d} g[d] * warped_{m,d}[c]     -> gather, same access pattern as the forward
+//   d cost / d f2_m[q_t][c] = 1/(M*32) * g[d] * w_t * f1[c]                   -> scatter-add (vector red.global.add.v4.f32)
+// Same tiling as the forward kernel: CTA = kPix pixels of a row, phase A (one thread per (pixel, plane): tap offsets and
+// weights) / phase B (a quarter warp per pixel, 4 channels per lane).  The gradient w.r.t. the reference features is
+// accumulated in registers and written once (deterministic); the measurement-feature gradient is accumulated with
+// floating-point atomics into buffers the host zeroes, so its summation order is not reproducible bit-for-bit (as in
+// PyTorch's grid_sampler backward).  Poses and intrinsics receive no gradient (the reference trains with fixed poses).
+struct SweepBwdParams {
+  SweepParams f;
+  const float* gcost;              // (B, h, w, D)
+  float* gref;                     // (B, h, w, 32)
+  float* gmeas[kMaxMeas];          // (B, h, w, 32) each, zero-initialised
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 2) plane_sweep_backward_c32_kernel(SweepBwdParams q) {
+  const SweepParams& p = q.f;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_ref = reinterpret_cast<float*>(smem_raw);                                     // [kPix][32]
+  SweepTapParams* s_par = reinterpret_cast<SweepTapParams*>(s_ref + kPix * 32);          // [kGroup][kPix]
+  float* s_kd = reinterpret_cast<float*>(s_par + kGroup * kPix);                         // [M][D][4]
+  float* s_G = s_kd + p.M * p.D * 4;                                                     // [M][12]
+  float* s_g = s_G + kMaxMeas * 12;                                                      // [kPix][D] upstream gradient
+
+  pdl_launch_dependents();
+  const int tid = threadIdx.x;
+  const int tiles_per_row = (p.w + kPix - 1) / kPix;
+  const int tile = blockIdx.x;
+  const int b = tile / (p.h * tiles_per_row);
+  const int rem = tile - b * (p.h * tiles_per_row);
+  const int v = rem / tiles_per_row;
+  const int u0 = (rem - v * tiles_per_row) * kPix;
+  const int npix = min(kPix, p.w - u0);
+  pdl_wait();
+
+  const size_t pix0 = ((size_t)b * p.h + v) * p.w + u0;
+  if (tid < npix * 8) reinterpret_cast<float4*>(s_ref)[tid] = __ldg(reinterpret_cast<const float4*>(p.ref + pix0 * 32) + tid);
+  const float gscale = 1.f / (32.f * (float)p.M);
+  for (int i = tid; i < npix * p.D; i += kSweepThreads) s_g[i] = q.gcost[pix0 * p.D + i] * gscale;
+  if (tid < p.M) {
+    float G[9], Kt[3];
+    sweep_matrices(p.pose1 + b * 16, p.pose2[tid] + b * 16, p.K + b * 9, G, Kt);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s_G[tid * 12 + i] = G[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s_G[tid * 12 + 9 + i] = Kt[i];
+  }
+  __syncthreads();
+  for (int i = tid; i < p.M * p.D; i += kSweepThreads) {
+    const int m = i / p.D, d = i - m * p.D;
+    const float this_depth = (float)(1.0 / (p.inv_base + d * p.inv_step));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s_kd[i * 4 + k] = s_G[m * 12 + 9 + k] / this_depth;
+  }
+  __syncthreads();
+
+  const float sx = (float)(p.w - 1) / (float)p.w, sy = (float)(p.h - 1) / (float)p.h;
+  const unsigned clip_off = (unsigned)b * (unsigned)(p.h * p.w) * 128u;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int sub = lane & 7;
+  const int pix = warp * 4 + (lane >> 3);
+  const bool active = pix < npix;
+  const int e0 = active ? pix : 0;
+  const float4 f1 = *reinterpret_cast<const float4*>(s_ref + e0 * 32 + sub * 4);
+  float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n_groups = (p.D + kGroup - 1) / kGroup;
+  for (int g = 0; g < n_groups; ++g) {
+    for (int m = 0; m < p.M; ++m) {
+      sweep_phase_a(p, s_G, s_kd, s_par, m, g * kGroup, u0, v, npix, sx, sy, clip_off);
+      __syncthreads();
+      if (active) {
+        const int4* par = reinterpret_cast<const int4*>(s_par);
+        const char* img = reinterpret_cast<const char*>(p.meas[m]) + sub * 16;
+        char* gimg = reinterpret_cast<char*>(q.gmeas[m]) + sub * 16;
+#pragma unroll 2
+        for (int k = 0; k < kGroup; ++k) {
+          const int d = g * kGroup + k;
+          if (d >= p.D) break;
+          const float gd = s_g[e0 * p.D + d];
+          if (gd == 0.f) continue;
+          const int e = k * kPix + e0;
+          const uint4 off = *reinterpret_cast<const uint4*>(&par[sweep_chunk(e, 0)]);
+          const float4 wt = *reinterpret_cast<const float4*>(&par[sweep_chunk(e, 1)]);
+          const float4 t00 = __ldg(reinterpret_cast<const float4*>(img + off.x));
+          const float4 t01 = __ldg(reinterpret_cast<const float4*>(img + off.y));
+          const float4 t10 = __ldg(reinterpret_cast<const float4*>(img + off.z));
+          const float4 t11 = __ldg(reinterpret_cast<const float4*>(img + off.w));
+          gacc.x = fmaf(gd, fmaf(t11.x, wt.w, fmaf(t10.x, wt.z, fmaf(t01.x, wt.y, t00.x * wt.x))), gacc.x);
+          gacc.y = fmaf(gd, fmaf(t11.y, wt.w, fmaf(t10.y, wt.z, fmaf(t01.y, wt.y, t00.y * wt.x))), gacc.y);
+          gacc.z = fmaf(gd, fmaf(t11.z, wt.w, fmaf(t10.z, wt.z, fmaf(t01.z, wt.y, t00.z * wt.x))), gacc.z);
+          gacc.w = fmaf(gd, fmaf(t11.w, wt.w, fmaf(t10.w, wt.z, fmaf(t01.w, wt.y, t00.w * wt.x))), gacc.w);
+          const float c0 = gd * wt.x, c1 = gd * wt.y, c2 = gd * wt.z, c3 = gd * wt.w;     // zero weight <=> tap outside the image
+          if (c0 != 0.f) red_add_v4(reinterpret_cast<float*>(gimg + off.x), c0 * f1.x, c0 * f1.y, c0 * f1.z, c0 * f1.w);
+          if (c1 != 0.f) red_add_v4(reinterpret_cast<float*>(gimg + off.y), c1 * f1.x, c1 * f1.y, c1 * f1.z, c1 * f1.w);
+          if (c2 != 0.f) red_add_v4(reinterpret_cast<float*>(gimg + off.z), c2 * f1.x, c2 * f1.y, c2 * f1.z, c2 * f1.w);
+          if (c3 != 0.f) red_add_v4(reinterpret_cast<float*>(gimg + off.w), c3 * f1.x, c3 * f1.y, c3 * f1.z, c3 * f1.w);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (active) *reinterpret_cast<float4*>(q.gref + (pix0 + pix) * 32 + sub * 4) = gacc;
+}
+
 // ---- generic path: any C, one thread per (pixel, plane); also the on-device cross-check of the fast path.
 __global__ void plane_sweep_generic_kernel(SweepParams p) {
   pdl_launch_dependents();
@@ -401,6 +512,64 @@ __global__ void hidden_warp_kernel(const float* __restrict__ h_in, const float* 
       }
   }
   *reinterpret_cast<float4*>(h_out + ((size_t)b * h * w + pix) * C + cg * 4) = o;
+}
+
+// Backward of the hidden-state warp w.r.t. the warped tensor (row f3; BPTT through convlstm.py:33-41): the forward's
+// bilinear weights scattered back, gh_in[q_t] += w_t * g[p] for valid depths (masked positions pass no gradient).
+// The depth comes from the ground truth in training (run-training.py:245-258) and gets no gradient.  gh_in is zeroed by
+// the host.
+__global__ void hidden_warp_backward_kernel(const float* __restrict__ g_out, const float* __restrict__ depth,
+                                            const float* __restrict__ prev_pose, const float* __restrict__ cur_pose,
+                                            const float* __restrict__ K, float* __restrict__ gh_in, int B, int C, int h, int w,
+                                            float invalid_thresh) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float s_T[16];
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    if (prev_pose != nullptr) {
+      float inv[16], T[16];
+      mat4_rigid_free_inverse(prev_pose + b * 16, inv);
+      mat4_mul(inv, cur_pose + b * 16, T);
+      for (int i = 0; i < 16; ++i) s_T[i] = T[i];
+    } else {
+      for (int i = 0; i < 16; ++i) s_T[i] = cur_pose[b * 16 + i];
+    }
+  }
+  __syncthreads();
+  const int c4 = C >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= h * w * c4) return;
+  const int cg = idx % c4;
+  const int pix = idx / c4;
+  const int u = pix % w, v = pix / w;
+  const float* Kb = K + b * 9;
+  const float fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
+  const float d = depth[(size_t)b * h * w + pix];
+  if (d <= invalid_thresh) return;
+  const float X = ((float)u - cx) / fx * d, Y = ((float)v - cy) / fy * d, Z = d;
+  const float x = fmaf(s_T[0], X, fmaf(s_T[1], Y, s_T[2] * Z)) + s_T[3];
+  const float y = fmaf(s_T[4], X, fmaf(s_T[5], Y, s_T[6] * Z)) + s_T[7];
+  float z = fmaf(s_T[8], X, fmaf(s_T[9], Y, s_T[10] * Z)) + s_T[11];
+  z = fmaxf(z, 0.f);
+  const float scale = (fabsf(z) > 1e-8f) ? 1.f / z : 1.f;
+  const float us = x * scale * fx + cx, vs = y * scale * fy + cy;
+  const float gx = us * (2.f / (float)(w - 1)) - 1.f, gy = vs * (2.f / (float)(h - 1)) - 1.f;
+  const float xs = ((gx + 1.f) * 0.5f) * (float)(w - 1), ys = ((gy + 1.f) * 0.5f) * (float)(h - 1);
+  const float x0f = floorf(xs), y0f = floorf(ys);
+  const float wx[2] = {(x0f + 1.f) - xs, xs - x0f}, wy[2] = {(y0f + 1.f) - ys, ys - y0f};
+  const float4 g = __ldg(reinterpret_cast<const float4*>(g_out + ((size_t)b * h * w + pix) * C + cg * 4));
+  float* gimg = gh_in + (size_t)b * h * w * C + cg * 4;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const float xf = x0f + dx, yf = y0f + dy;
+      if (xf >= 0.f && xf <= (float)(w - 1) && yf >= 0.f && yf <= (float)(h - 1)) {
+        const float wt = wx[dx] * wy[dy];
+        red_add_v4(gimg + ((size_t)(int)yf * w + (int)xf) * C, wt * g.x, wt * g.y, wt * g.z, wt * g.w);
+      }
+    }
 }
 
 // =====================================================================================================
@@ -533,6 +702,77 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
   const size_t total = (size_t)B * h * w * D;
   launch_k(plane_sweep_generic_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, s, p);
   return check_launch("plane_sweep_generic_kernel");
+}
+
+// ---- backward entry points (row f3) -------------------------------------------------------------------------------
+extern "C" int dvmvs_plane_sweep_backward(const float* ref, const float* const* meas_host, const float* pose1,
+                                          const float* const* pose2_host, const float* K, const float* grad_cost, float* grad_ref,
+                                          float* const* grad_meas_host, int B, int C, int h, int w, int D, int M, float min_depth,
+                                          float max_depth, int mode, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(ref && meas_host && pose1 && pose2_host && K && grad_cost && grad_ref && grad_meas_host, "plane_sweep_backward: null pointer");
+  DVMVS_REQUIRE(B > 0 && h > 1 && w > 1, "plane_sweep_backward: bad shape B=%d h=%d w=%d", B, h, w);
+  DVMVS_REQUIRE(C == 32, "plane_sweep_backward: C=%d (the training path sweeps the 32-channel half-resolution features)", C);
+  DVMVS_REQUIRE(mode == DVMVS_SWEEP_DOT, "plane_sweep_backward: only the dot-product cost is differentiable here (mode %d)", mode);
+  DVMVS_REQUIRE(D >= 2 && D <= kMaxPlanes, "plane_sweep_backward: D=%d outside [2,%d]", D, kMaxPlanes);
+  DVMVS_REQUIRE(M >= 1 && M <= kMaxMeas, "plane_sweep_backward: M=%d outside [1,%d]", M, kMaxMeas);
+  DVMVS_REQUIRE(min_depth > 0.f && max_depth > min_depth, "plane_sweep_backward: bad depth range");
+  DVMVS_REQUIRE((size_t)B * h * w * 128 < ((size_t)1 << 32), "plane_sweep_backward: feature tensor too large for 32-bit tap offsets");
+  SweepBwdParams q;
+  SweepParams& p = q.f;
+  p.ref = ref;
+  DVMVS_REQUIRE((uintptr_t)ref % 16 == 0 && (uintptr_t)grad_ref % 16 == 0, "plane_sweep_backward: pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int m = 0; m < M; ++m) {
+    DVMVS_REQUIRE(meas_host[m] && pose2_host[m] && grad_meas_host[m], "plane_sweep_backward: null measurement pointer %d", m);
+    DVMVS_REQUIRE((uintptr_t)meas_host[m] % 16 == 0 && (uintptr_t)grad_meas_host[m] % 16 == 0, "plane_sweep_backward: pointers must be 16-byte aligned");
+    p.meas[m] = meas_host[m];
+    p.pose2[m] = pose2_host[m];
+    q.gmeas[m] = grad_meas_host[m];
+  }
+  p.pose1 = pose1;
+  p.K = K;
+  p.out = nullptr;
+  p.B = B; p.C = C; p.h = h; p.w = w; p.D = D; p.M = M;
+  p.inv_base = 1.0 / (double)max_depth;
+  p.inv_step = (1.0 / (double)min_depth - 1.0 / (double)max_depth) / (double)(D - 1);
+  p.mode = mode;
+  q.gcost = grad_cost;
+  q.gref = grad_ref;
+  // the same measurement tensor may appear more than once in grad_meas_host (aliased gradients accumulate); zero each once
+  for (int m = 0; m < M; ++m) {
+    bool seen = false;
+    for (int j = 0; j < m; ++j) seen = seen || grad_meas_host[j] == grad_meas_host[m];
+    if (!seen && cudaMemsetAsync(grad_meas_host[m], 0, (size_t)B * h * w * 32 * sizeof(float), s) != cudaSuccess) {
+      set_error("plane_sweep_backward: memset failed");
+      return DVMVS_ELAUNCH;
+    }
+  }
+  const int tiles = B * h * ((w + kPix - 1) / kPix);
+  const size_t smem = (size_t)(kPix * 32 + M * D * 4 + kMaxMeas * 12 + kPix * D) * sizeof(float) + kGroup * kPix * sizeof(SweepTapParams);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(plane_sweep_backward_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  DVMVS_REQUIRE(smem <= 96 * 1024, "plane_sweep_backward: shared memory %zu too large", smem);
+  launch_k(plane_sweep_backward_c32_kernel, dim3(tiles), dim3(kSweepThreads), smem, s, q);
+  return check_launch("plane_sweep_backward_c32_kernel");
+}
+
+extern "C" int dvmvs_hidden_warp_backward(const float* grad_out, const float* depth, const float* prev_pose, const float* cur_pose,
+                                          const float* K, float* grad_h_in, int B, int C, int h, int w, float invalid_thresh,
+                                          dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(grad_out && depth && cur_pose && K && grad_h_in, "hidden_warp_backward: null pointer");
+  DVMVS_REQUIRE(B > 0 && C > 0 && C % 4 == 0 && h > 1 && w > 1, "hidden_warp_backward: bad shape (C must be a multiple of 4)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(grad_h_in, 0, (size_t)B * h * w * C * sizeof(float), s) != cudaSuccess) {
+    set_error("hidden_warp_backward: memset failed");
+    return DVMVS_ELAUNCH;
+  }
+  const int total = h * w * (C / 4);
+  launch_k(hidden_warp_backward_kernel, dim3((total + 127) / 128, B), dim3(128), 0, s, grad_out, depth, prev_pose, cur_pose, K, grad_h_in, B, C,
+           h, w, invalid_thresh);
+  return check_launch("hidden_warp_backward_kernel");
 }
 
 // test hook: force the generic path (used by tests to cross-check the fast path on the device)

@@ -13,12 +13,15 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 SRC_DIRECT, SRC_UPSAMPLE2X = 0, 1
 RES_NONE, RES_SAME, RES_NEAREST_UP = 0, 1, 2
 SWEEP_DOT, SWEEP_SAD = 0, 1
+LOSS_L1, LOSS_L1_INV, LOSS_L1_REL, LOSS_HUBER = 0, 1, 2, 3
 
 # every symbol include/dvmvs_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "dvmvs_abi_version", "dvmvs_set_programmatic_launch", "dvmvs_last_error_string", "dvmvs_kernel_launch_count", "dvmvs_plane_sweep_fused",
     "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_conv2d_halo", "dvmvs_split_blocked", "dvmvs_split_planes", "dvmvs_stem_conv", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
     "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw", "dvmvs_preprocess_rgb",
+    "dvmvs_plane_sweep_backward", "dvmvs_hidden_warp_backward", "dvmvs_lstm_gates_backward", "dvmvs_depth_loss_forward",
+    "dvmvs_depth_loss_backward",
 ]
 
 
@@ -112,6 +115,12 @@ def lib():
         L.dvmvs_preprocess_rgb.argtypes = [p, i, i, i, i, i, i, p, i, i, i, f, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), p]
         L.dvmvs_nchw_to_nhwc.argtypes = [p, p, i, i, i, i, p]
         L.dvmvs_nhwc_to_nchw.argtypes = [p, p, i, i, i, i, p]
+        L.dvmvs_plane_sweep_backward.argtypes = [p, p, p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
+        L.dvmvs_hidden_warp_backward.argtypes = [p, p, p, p, p, p, i, i, i, i, f, p]
+        L.dvmvs_lstm_gates_backward.argtypes = [p, p, p, p, p, p, i, i, i, i, p]
+        ip, fp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
+        L.dvmvs_depth_loss_forward.argtypes = [p, ip, ip, i, p, p, i, i, i, p]
+        L.dvmvs_depth_loss_backward.argtypes = [p, p, ip, ip, fp, i, p, p, p, i, i, i, i, p]
         _lib = L
     return _lib
 

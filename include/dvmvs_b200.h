@@ -38,6 +38,7 @@ enum { DVMVS_ACT_NONE = 0, DVMVS_ACT_RELU = 1, DVMVS_ACT_SIGMOID = 2 };
 enum { DVMVS_SRC_DIRECT = 0, DVMVS_SRC_UPSAMPLE2X = 1 };     /* conv input source modes */
 enum { DVMVS_RES_NONE = 0, DVMVS_RES_SAME = 1, DVMVS_RES_NEAREST_UP = 2 };
 enum { DVMVS_SWEEP_DOT = 0, DVMVS_SWEEP_SAD = 1 };
+enum { DVMVS_LOSS_L1 = 0, DVMVS_LOSS_L1_INV = 1, DVMVS_LOSS_L1_REL = 2, DVMVS_LOSS_HUBER = 3 };   /* losses.py:33-40 loss_type */
 
 /* Library identification / diagnostics. */
 int dvmvs_abi_version(void);                 /* bumps when a signature changes */
@@ -215,6 +216,51 @@ int dvmvs_upsample2x(const float* x, float* y, int B, int H, int W, int C, dvmvs
 int dvmvs_preprocess_rgb(const void* image, int is_u8, int swap_rb, int in_h, int in_w, int crop_x, int crop_y, float* out,
                          int out_h, int out_w, int normalize, float scale, const float* mean3, const float* std3,
                          dvmvs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Training step, backward kernels.  The reference differentiates these ops with
+ * autograd (fusionnet/run-training.py:227-278 forward_pass; train.py:33-40 loss.backward()); here each has a
+ * hand-written derivative.  Gradient buffers with scatter-adds are zeroed by the entry point (cudaMemsetAsync on
+ * `stream`); their accumulation uses fp32 atomics, so sums are reproducible to round-off, not bit-for-bit.
+ * ------------------------------------------------------------------------------------------------------ */
+
+/* Backward of dvmvs_plane_sweep_fused in DOT mode, C = 32 (dvmvs/utils.py:45-107 under autograd).
+ *   grad_cost      [B][h][w][D]   d loss / d cost volume
+ *   grad_ref       [B][h][w][32]  out: d loss / d image1 (written, deterministic)
+ *   grad_meas_host host array of M device pointers [B][h][w][32]: out, d loss / d image2s[m] (zeroed here, then
+ *                  accumulated; the same pointer may appear for several m -- their gradients add up).
+ * Poses, intrinsics and depth range get no gradient (the reference trains with given poses). */
+int dvmvs_plane_sweep_backward(const float* ref, const float* const* meas_host, const float* pose1,
+                               const float* const* pose2_host, const float* K, const float* grad_cost, float* grad_ref,
+                               float* const* grad_meas_host, int B, int C, int h, int w, int D, int M, float min_depth,
+                               float max_depth, int mode, dvmvs_stream_t stream);
+
+/* Backward of dvmvs_hidden_warp w.r.t. h_in (BPTT through dvmvs/convlstm.py:33-41): grad_h_in [B][h][w][C] (zeroed
+ * here) += bilinear weights * grad_out at positions with depth > invalid_thresh.  The depth (ground truth in training,
+ * run-training.py:245-258) gets no gradient. */
+int dvmvs_hidden_warp_backward(const float* grad_out, const float* depth, const float* prev_pose, const float* cur_pose,
+                               const float* K, float* grad_h_in, int B, int C, int h, int w, float invalid_thresh,
+                               dvmvs_stream_t stream);
+
+/* Backward of dvmvs_lstm_gates (dvmvs/convlstm.py:45-59): from the saved pre-activations `gates` and `c_in` and the
+ * incoming grad_h / grad_c [B][h][w][C] (grad_c may be NULL) writes grad_gates [B][h][w][4*C] (i,f,o,g order) and
+ * grad_c_in [B][h][w][C].  Forward values are recomputed inside the kernel. */
+int dvmvs_lstm_gates_backward(const float* gates, const float* c_in, const float* grad_h, const float* grad_c, float* grad_gates,
+                              float* grad_c_in, int B, int h, int w, int C, dvmvs_stream_t stream);
+
+/* Multi-scale depth loss, dvmvs/losses.py:43-82 calculate_loss for every prediction scale in ONE launch.
+ *   preds_host   host array of n_scales device pointers, prediction j is [B][hs_host[j]][ws_host[j]]
+ *   groundtruth  [B][H][W]; scale j compares against its nearest-neighbour down-sampling (F.interpolate 'nearest'),
+ *                pixels with ground truth 0 are invalid
+ *   sums         out [n_scales][5]: sum |g-p|, sum smooth_l1(p,g), sum |1/g-1/p|, sum |g-p|/g, valid count */
+int dvmvs_depth_loss_forward(const float* const* preds_host, const int* hs_host, const int* ws_host, int n_scales,
+                             const float* groundtruth, float* sums, int B, int H, int W, dvmvs_stream_t stream);
+
+/* d/d prediction of  sum_j weights_host[j] * sums[j][loss_type] / sums[j][count]  (losses.py:33-40), times the scalar
+ * upstream gradient read from DEVICE memory; written to grads_host[j] (same shapes as the predictions). */
+int dvmvs_depth_loss_backward(const float* const* preds_host, float* const* grads_host, const int* hs_host, const int* ws_host,
+                              const float* weights_host, int n_scales, const float* groundtruth, const float* sums,
+                              const float* upstream, int loss_type, int B, int H, int W, dvmvs_stream_t stream);
 
 /* Layout helpers: NCHW <-> NHWC fp32 copies. */
 int dvmvs_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, dvmvs_stream_t stream);
