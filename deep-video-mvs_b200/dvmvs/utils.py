@@ -36,6 +36,13 @@ def cost_volume_fusion(image1, image2s, pose1, pose2s, K, warp_grid, min_depth, 
     tensors are never materialised.  Returns (B, D, h, w) fp32 (channels_last strides)."""
     image2s, pose2s = list(image2s), list(pose2s)
     _check_sweep_args(image1, image2s, pose2s)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in [image1] + image2s):
+        # training (run-training.py:231): same forward kernel, hand-written backward kernel (dvmvs/training.py, row f3)
+        if not dot_product:
+            raise NotImplementedError("only the dot-product cost volume is differentiable (the SAD branch is used by the baselines' "
+                                      "inference only, utils.py:83-84)")
+        from .training import plane_sweep_cost_volume
+        return plane_sweep_cost_volume(image1, image2s, pose1, pose2s, K, min_depth, max_depth, n_depth_levels)
     ref = ops.to_nhwc(image1, "image1")
     meas = [ops.to_nhwc(t, "image2") for t in image2s]
     cost = ops.plane_sweep(ref, meas, pose1, pose2s, K, min_depth, max_depth, n_depth_levels, bool(dot_product))
@@ -81,6 +88,9 @@ def warp_frame_depth(image_src, depth_dst, src_trans_dst, camera_matrix, normali
     if normalize_points or sampling_mode != 'bilinear':
         raise NotImplementedError("the sm_100a kernel implements normalize_points=False, sampling_mode='bilinear' "
                                   "(the only combination the reference uses, convlstm.py:33-38)")
+    if torch.is_grad_enabled() and image_src.requires_grad:
+        from .training import warp_hidden_state
+        return warp_hidden_state(image_src, depth_dst, None, src_trans_dst, camera_matrix, float("-inf"))
     out = ops.hidden_warp(ops.to_nhwc(image_src, "image_src"), depth_dst, None, src_trans_dst, camera_matrix, float("-inf"))
     return ops.to_api(out)
 

@@ -237,7 +237,9 @@ int dvmvs_plane_sweep_backward(const float* ref, const float* const* meas_host, 
 
 /* Backward of dvmvs_hidden_warp w.r.t. h_in (BPTT through dvmvs/convlstm.py:33-41): grad_h_in [B][h][w][C] (zeroed
  * here) += bilinear weights * grad_out at positions with depth > invalid_thresh.  The depth (ground truth in training,
- * run-training.py:245-258) gets no gradient. */
+ * run-training.py:245-258) gets no gradient.  NOTE: the reference applies its mask with `h_cur.data[non_valid] = 0.0`
+ * (convlstm.py:41), which autograd does not see -- its gradient is that of the UNMASKED warp; the Python binding
+ * therefore passes invalid_thresh = -inf here (dvmvs/training.py). */
 int dvmvs_hidden_warp_backward(const float* grad_out, const float* depth, const float* prev_pose, const float* cur_pose,
                                const float* K, float* grad_h_in, int B, int C, int h, int w, float invalid_thresh,
                                dvmvs_stream_t stream);

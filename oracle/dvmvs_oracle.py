@@ -310,14 +310,54 @@ def lstm_fusion(sd, current_encoding, current_state, previous_pose, current_pose
         T = torch.bmm(torch.inverse(previous_pose), current_pose)                     # convlstm.py:30
         non_valid = estimated_current_depth <= 0.01                                   # :32
         h_cur = warp_frame_depth(h_cur, estimated_current_depth, T, camera_matrix)    # :33-38
-        h_cur = torch.where(non_valid.expand_as(h_cur), torch.zeros_like(h_cur), h_cur)   # :39-41
+        # :39-41 `h_cur.data[non_valid] = 0.0` -- a .data write autograd does not see: the VALUE is zeroed, the
+        # gradient passes through the masked positions into the warp as if they were not masked.  Same here.
+        h_cur = h_cur - (h_cur * non_valid.expand_as(h_cur).to(h_cur.dtype)).detach()
     cc = F.conv2d(torch.cat([current_encoding, h_cur], dim=1), sd["lstm_cell.conv.weight"], None, 1, 1)   # :43-44
-    cc_i, cc_f, cc_o, cc_g = torch.split(cc, C, dim=1)                                # :45
+    return lstm_gate_epilogue(cc, c_cur)
+
+
+def lstm_gate_epilogue(combined_conv, c_cur):
+    """dvmvs/convlstm.py:45-59: the gate arithmetic after the convolution (differentiable: the training tests take
+    torch autograd through this restatement as the reference gradient)."""
+    B, C4, h, w = combined_conv.shape
+    C = C4 // 4
+    cc_i, cc_f, cc_o, cc_g = torch.split(combined_conv, C, dim=1)                     # :45
     i, f, o = torch.sigmoid(cc_i), torch.sigmoid(cc_f), torch.sigmoid(cc_o)
     g = torch.celu(torch.layer_norm(cc_g, [h, w]))                                    # :52-53
     c_next = torch.layer_norm(f * c_cur + i * g, [h, w])                              # :55-56
     h_next = o * torch.celu(c_next)                                                   # :57
     return h_next, c_next
+
+
+# --------------------------------------------------------------------------------------------------
+# training loss (dvmvs/losses.py), restated; differentiable
+# --------------------------------------------------------------------------------------------------
+def calculate_loss(groundtruth, prediction):
+    """dvmvs/losses.py:53-82: sums over the pixels whose nearest-down-sampled ground truth is non-zero.
+    Returns (l1, huber, l1_inv, l1_rel, valid_count)."""
+    B, H, W = groundtruth.shape
+    _, hs, ws = prediction.shape
+    gt = F.interpolate(groundtruth.view(B, 1, H, W), size=(hs, ws), mode="nearest")   # :61-63
+    pred = prediction.view(B, 1, hs, ws)
+    valid = gt != 0                                                                    # :65
+    count = int(valid.sum())
+    g, p = gt[valid], pred[valid]
+    diff = torch.abs(g - p)                                                            # :73
+    huber = F.smooth_l1_loss(p, g, reduction="none").sum()                             # :75-76
+    return diff.sum(), huber, torch.abs(1.0 / g - 1.0 / p).sum(), (diff / g).sum(), count   # :78-82
+
+
+def update_losses(predictions, weights, groundtruth, loss_type):
+    """dvmvs/losses.py:26-40, is_training branch: sum_j weights[j] * loss_j / valid_count_j.
+    Returns (optimizer_loss, per-scale (n,5) sums as python floats)."""
+    column = {"L1": 0, "Huber": 1, "L1-inv": 2, "L1-rel": 3}[loss_type]
+    total, sums = 0, []
+    for wgt, prediction in zip(weights, predictions):
+        parts = calculate_loss(groundtruth, prediction)
+        total = total + wgt * (parts[column] / parts[4])
+        sums.append([float(v.detach()) if torch.is_tensor(v) else float(v) for v in parts])
+    return total, sums
 
 
 # --------------------------------------------------------------------------------------------------

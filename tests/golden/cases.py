@@ -138,3 +138,36 @@ def module_inputs(synth, c):
     pose0 = np.stack([synth.camera_pose(3)] * B)
     pose1 = np.stack([synth.camera_pose(4)] * B)
     return dict(image=image, cost_volume=cost_volume, depth_est=depth_est, lstm_K=np.stack([lstm_K] * B), pose0=pose0, pose1=pose1)
+
+
+# ---------------------------------------------------------------------------------------------- training (row f3)
+# Gradient cases: which forward cases get a seeded upstream gradient pushed through the REFERENCE under autograd
+# (oracle/make_golden_training.py -> tests/golden/training.npz).
+SWEEP_GRAD_CASES = ["dot_small", "dot_c1", "dot_m3", "dot_wide"]
+HIDDEN_WARP_GRAD_CASES = ["bottleneck", "batched", "degenerate"]
+LSTM_GRAD_CASES = ["warp", "nowarp"]
+
+
+def upstream(synth, key, shape, seed):
+    """Seeded upstream gradient d loss / d output for a gradient case."""
+    return synth.tensor("grad/" + key, shape, seed=seed)
+
+
+LOSS_CASE = dict(B=2, H=64, W=96, seed=51, weights=[1.0, 0.5, 2.0, 1.0, 1.5])
+LOSS_TYPES = ["L1", "L1-inv", "L1-rel", "Huber"]
+
+
+def loss_inputs(synth, c):
+    """Ground-truth depth with invalid (zero) pixels and five prediction scales (1/16 ... full), as
+    update_losses receives them (fusionnet/run-training.py:270)."""
+    B, H, W = c["B"], c["H"], c["W"]
+    gt = (0.5 + 3.0 * np.abs(synth.tensor("loss/%d/gt" % c["seed"], (B, H, W), seed=c["seed"]))).astype(np.float32)
+    gt[:, 0:5, :] = 0.0
+    gt[:, :, 7::13] = 0.0
+    preds = []
+    for k, s in enumerate((16, 8, 4, 2, 1)):
+        p = (0.4 + 3.0 * np.abs(synth.tensor("loss/%d/p%d" % (c["seed"], k), (B, H // s, W // s), seed=c["seed"]))).astype(np.float32)
+        preds.append(p)
+    preds[4][:, 10:20, 10:20] = gt[:, 10:20, 10:20]          # exact hits: sign(0) = 0 in every loss
+    preds[4][:, 30:34, 30:34] = gt[:, 30:34, 30:34] + 0.25   # inside the quadratic zone of smooth_l1
+    return dict(groundtruth=gt, predictions=preds)
