@@ -241,10 +241,15 @@ __global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(Sweep
       const int e = k * kPix + e0;
       const uint4 off = *reinterpret_cast<const uint4*>(&par[sweep_chunk(e, 0)]);
       const float4 wt = *reinterpret_cast<const float4*>(&par[sweep_chunk(e, 1)]);
-      const float4 t00 = __ldg(reinterpret_cast<const float4*>(img + off.x));
-      const float4 t01 = __ldg(reinterpret_cast<const float4*>(img + off.y));
-      const float4 t10 = __ldg(reinterpret_cast<const float4*>(img + off.z));
-      const float4 t11 = __ldg(reinterpret_cast<const float4*>(img + off.w));
+      // taps outside the image carry weight 0 (phase A) and are not fetched at all: predicated-off lanes generate no L1
+      // wavefronts, and on a forward-moving camera a quarter of all (pixel, plane) samples fall off the image at the
+      // near planes.  grid_sample's zero padding contributes exactly 0 there, as does a skipped tap.
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 t00 = zero4, t01 = zero4, t10 = zero4, t11 = zero4;
+      if (wt.x != 0.f) t00 = __ldg(reinterpret_cast<const float4*>(img + off.x));
+      if (wt.y != 0.f) t01 = __ldg(reinterpret_cast<const float4*>(img + off.y));
+      if (wt.z != 0.f) t10 = __ldg(reinterpret_cast<const float4*>(img + off.z));
+      if (wt.w != 0.f) t11 = __ldg(reinterpret_cast<const float4*>(img + off.w));
       float4 ws;
       ws.x = fmaf(t11.x, wt.w, fmaf(t10.x, wt.z, fmaf(t01.x, wt.y, t00.x * wt.x)));
       ws.y = fmaf(t11.y, wt.w, fmaf(t10.y, wt.z, fmaf(t01.y, wt.y, t00.y * wt.x)));

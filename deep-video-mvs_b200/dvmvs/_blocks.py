@@ -200,6 +200,7 @@ class FeatureExtractor(NativeModule):
             outs.append(x)
         return outs
 
+    @ops.family_terms("fe")
     def forward(self, image):
         B, C, H, W = image.shape
         if C != 3 or H % 32 != 0 or W % 32 != 0:
@@ -209,11 +210,13 @@ class FeatureExtractor(NativeModule):
             return tuple(ops.act_to_api(t) for t in self.run(None, image_nchw=image))
         return tuple(ops.act_to_api(t) for t in self.run(ops.to_act(image, "image")))
 
+    @ops.family_terms("fe")
     def forward_head(self, image):
         """layer1..layer3 only (pipeline engines split the trunk here); forward_tail(head) completes it."""
         ops.require_cuda_f32(image, "image")
         return tuple(ops.act_to_api(t) for t in self.run(None, image_nchw=image.contiguous(), part="head"))
 
+    @ops.family_terms("fe")
     def forward_tail(self, head):
         l1, l2, l3 = head
         tail = self.run(ops.to_act(l3, "layer3"), part="tail")
@@ -265,6 +268,7 @@ class FeatureShrinker(NativeModule):
         del keep
         return outs
 
+    @ops.family_terms("fpn")
     def forward(self, layer1, layer2, layer3, layer4, layer5):
         feats = [ops.to_act(t, "layer%d" % (i + 1)) for i, t in enumerate((layer1, layer2, layer3, layer4, layer5))]
         return tuple(ops.act_to_api(t) for t in self.run(feats))
@@ -300,6 +304,7 @@ class CostVolumeEncoder(NativeModule):
         out3 = self.encoder_block3.run(inp3)
         return inp0, inp1, inp2, inp3, out3
 
+    @ops.family_terms("cve")
     def forward(self, features_half, features_quarter, features_one_eight, features_one_sixteen, cost_volume):
         args = [ops.to_act(t, n) for t, n in ((features_half, "features_half"), (features_quarter, "features_quarter"),
                                               (features_one_eight, "features_one_eight"),
@@ -366,6 +371,7 @@ class CostVolumeDecoder(NativeModule):
         _, depth1 = heads[4].run([(x, D)], aux=aux)
         return [t.squeeze(3) for t in (depth1, depth2, depth4, depth8, depth16)]
 
+    @ops.family_terms("cvd")
     def forward(self, image, skip0, skip1, skip2, skip3, bottom):
         args = [ops.to_act(t, n) for t, n in ((image, "image"), (skip0, "skip0"), (skip1, "skip1"), (skip2, "skip2"),
                                               (skip3, "skip3"), (bottom, "bottom"))]
@@ -381,6 +387,7 @@ class LSTMFusion(NativeModule):
     def _pack(self):
         return ()
 
+    @ops.family_terms("lstm")
     def forward(self, current_encoding, current_state, previous_pose, current_pose, estimated_current_depth, camera_matrix,
                 input_gates=None):
         """input_gates (optional, beyond the reference signature): lstm_cell.input_gates(current_encoding) computed earlier."""

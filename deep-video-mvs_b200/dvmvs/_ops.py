@@ -546,6 +546,53 @@ def conv_backend():
     return _BACKEND
 
 
+# Per-family operand precision of the tensor-core path: module family ("fe", "fpn", "cve", "lstm", "cvd") -> terms
+# (3 = fp16 (hi, lo) pairs, three products, ~fp32 accuracy; 1 = plain fp16 operands, fp32 accumulate).  Families not
+# listed use the global `terms` of set_conv_backend.  The top-level modules' forwards run under family_terms(), so the
+# shared building blocks (StandardLayer, EncoderBlock, ...) follow the module they are used in.
+_TERMS_POLICY = {}
+
+
+def set_precision_policy(policy=None):
+    """policy: dict family -> 1 | 3, or None / {} to clear.  Also accepts "fe=1,fpn=1,cve=1" (DVMVS_TC_POLICY syntax)."""
+    global _TERMS_POLICY
+    if isinstance(policy, str):
+        policy = {k.strip(): int(v) for k, v in (item.split("=") for item in policy.split(",") if item.strip())}
+    policy = dict(policy or {})
+    for k, v in policy.items():
+        if k not in ("fe", "fpn", "cve", "lstm", "cvd") or v not in (1, 3):
+            raise ValueError("precision policy: family in fe/fpn/cve/lstm/cvd, terms 1 or 3 (got %r=%r)" % (k, v))
+    _TERMS_POLICY = policy
+
+
+def precision_policy():
+    return dict(_TERMS_POLICY)
+
+
+if _os.environ.get("DVMVS_TC_POLICY"):
+    set_precision_policy(_os.environ["DVMVS_TC_POLICY"])
+
+
+def family_terms(family):
+    """Decorator for the forward of a top-level module: convolutions launched inside use the family's terms."""
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapped(*a, **k):
+            global _TC_TERMS
+            t = _TERMS_POLICY.get(family)
+            if t is None:
+                return fn(*a, **k)
+            saved, _TC_TERMS = _TC_TERMS, t
+            try:
+                return fn(*a, **k)
+            finally:
+                _TC_TERMS = saved
+        return wrapped
+    return deco
+
+
 class Act:
     """An activation inside a module: fp32 channel-last tensor and/or its fp16 (hi, lo) planes (created on demand,
     cached).  `up` planes = planes of the x2-bilinear-upsampled tensor (F.interpolate materialised for the TMA loader)."""

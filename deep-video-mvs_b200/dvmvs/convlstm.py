@@ -36,6 +36,7 @@ class MVSLayernormConvLSTMCell(NativeModule):
         conv_h = ops.ConvLayer(ops.PackedConv(w[:, self.input_dim:], None, None, stride=1, act=N.ACT_NONE))
         return conv_x, conv_h
 
+    @ops.family_terms("lstm")
     def input_gates(self, input_tensor):
         """The state-independent half of the gate pre-activations, conv(W[:, :input_dim], input): (B,4*hidden,h,w).  Pass it
         to forward(..., input_gates=) to keep it off the recurrent critical path (PipelinedFusionnet does)."""
