@@ -166,6 +166,7 @@ def run_ours(args, rank, world, local_rank):
             p0.record(pipe.stream_a)
             for i in range(args.steps):
                 pipe.submit(*frames_dev[args.warmup + i], out=pred)
+            wall_enq = time.perf_counter()          # host side done enqueueing (the device may still be far behind)
             p1.record(pipe.stream_b)
             pipe.synchronize()
             torch.cuda.synchronize()
@@ -315,6 +316,31 @@ def run_ours(args, rank, world, local_rank):
                 ms = q0.elapsed_time(q1)
                 extras["batched"] = {"clips_per_gpu": EB, "frames_per_s_per_gpu": EB * 8 / (ms * 1e-3), "ms_per_step": ms / 8}
                 del pb, fb
+            # the other operand precision of the tensor path (fp16 (hi, lo) pairs, three products: ~fp32 accuracy)
+            if args.backend == "tc" and args.mode == "pipeline":
+                other = 3 if args.tc_terms == 1 else 1
+                ops.set_conv_backend("tc", terms=other, stride2=True)
+                po = pipeline.PipelinedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=args.stages)
+                outo = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+                po.prime(*frames_dev[0])
+                for t in range(args.warmup):
+                    po.submit(*frames_dev[t], out=outo)
+                po.synchronize()
+                torch.cuda.synchronize()
+                o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                o0.record(po.stream_a)
+                for t in range(args.warmup, n_frames):
+                    po.submit(*frames_dev[t], out=outo)
+                o1.record(po.stream_b)
+                po.synchronize()
+                torch.cuda.synchronize()
+                ms = o0.elapsed_time(o1)
+                d = (1.0 / outo - 1.0 / pred).abs().sum() / (1.0 / outo).abs().sum()
+                extras["operands_%s" % ("fp16_pairs_3_terms" if other == 3 else "fp16_1_term")] = {
+                    "frames_per_s_per_gpu": B * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                    "rel_l1_inverse_depth_between_the_two_precisions_last_keyframe": float(d)}
+                del po
+                ops.set_conv_backend("tc", terms=args.tc_terms, stride2=True)
             # measurement features from the feature cache (every measurement frame of the synthetic stream
             # was the reference frame of an earlier keyframe).  Reported beside the headline, never as it: the headline
             # recomputes FeatureExtractor + FeatureShrinker for all M+1 images like the reference does.
@@ -355,12 +381,14 @@ def run_ours(args, rank, world, local_rank):
     result = {
         "metric": "fusionnet depth frames/sec @256x256x64planes", "value": total_frames / (dev_ms * 1e-3), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.backend == "fp32" else "f16x2+f32acc", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.backend == "fp32" else ("f16+f32acc" if args.tc_terms == 1 else "f16x2+f32acc"), "data": "synthetic",
         "config": {"workload": WORKLOAD % B, "clips_per_gpu": B, "height": H, "width": W, "planes": D, "measurement_frames": M,
                    "weights": "random-init (seeded) reference architecture", "mode": args.mode + (" (%d stages)" % args.stages if args.mode == "pipeline" else ""),
-                   "conv_backend": args.backend + ("" if args.backend == "fp32" else " (tcgen05, fp16-pair operands x%d terms, fp32 accumulate)" % args.tc_terms), "l2": ("per-step working set (weights 138 MB + activations) exceeds the 126 MB L2; steps run back to back (pipelined)"
+                   "conv_backend": args.backend + ("" if args.backend == "fp32" else (" (tcgen05, fp16 operands, fp32 accumulate; parity 4e-5 synthetic / 1.1e-4 shipped weights vs 1e-3 budget, profiles/r01_terms_probe.jsonl)"
+                                                                                       if args.tc_terms == 1 else " (tcgen05, fp16-pair operands x3 terms, fp32 accumulate)")), "l2": ("per-step working set (weights 138 MB + activations) exceeds the 126 MB L2; steps run back to back (pipelined)"
                           if args.mode == "pipeline" else "flushed (256 MiB write) between timed steps"),
-                   "parallelism": "clip-sharded x%d, no data-path collective" % world, "host_loop_wall_ms_per_step": (wall1 - wall0) * 1e3 / args.steps},
+                   "parallelism": "clip-sharded x%d, no data-path collective" % world, "host_loop_wall_ms_per_step": (wall1 - wall0) * 1e3 / args.steps,
+                   "host_enqueue_ms_per_step": ((wall_enq - wall0) * 1e3 / args.steps) if args.mode == "pipeline" else None},
         "clocks": clocks,
         "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": int(lt[0]),
@@ -437,7 +465,9 @@ def main():
                          "stage on a second stream; graph: one CUDA graph per keyframe, strictly sequential; eager: one host "
                          "launch per kernel")
     ap.add_argument("--backend", default=os.environ.get("DVMVS_CONV_BACKEND", "tc"), choices=["tc", "fp32"])
-    ap.add_argument("--tc-terms", type=int, default=3)
+    ap.add_argument("--tc-terms", type=int, default=1, choices=[1, 3],
+                    help="operand precision of the tcgen05 convolutions: 1 = fp16 operands, fp32 accumulate (default; measured "
+                         "<= 1.1e-4 rel-L1 on inverse depth, budget 1e-3); 3 = fp16 (hi, lo) pairs, three products (~1e-6)")
     ap.add_argument("--stages", type=int, default=5, choices=[2, 3, 4, 5], help="pipeline depth of --mode pipeline")
     ap.add_argument("--extras", type=int, default=1, help="also measure sequential latency and batched throughput (0 to skip)")
     ap.add_argument("--extra-clips", type=int, default=8)

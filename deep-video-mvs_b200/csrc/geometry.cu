@@ -51,6 +51,7 @@ struct SweepParams {
   int B, C, h, w, D, M;
   double inv_base, inv_step;   // python doubles in the reference (utils.py:59-60)
   int mode;
+  int prefetch;                // forward fast path: phase A prefetches the tap lines of the NEXT step into L1
 };
 
 // Per (b, m): G = K R K^-1 (9 floats), Kt = K t (3 floats)    (utils.py:51-56)
@@ -136,6 +137,16 @@ __device__ __forceinline__ void sweep_phase_a(const SweepParams& p, const float*
     t.w[1] = (vy0 && vx1) ? fx * gy : 0.f;
     t.w[2] = (vy1 && vx0) ? gx * fy : 0.f;
     t.w[3] = (vy1 && vx1) ? fx * fy : 0.f;
+    if (p.prefetch) {
+      // phase B of this (plane group, frame) runs one step later: start the 128-byte tap lines towards L1 now, so that its
+      // gathers hit (the kernel is bound by load latency -- 47 % of the stall samples are long-scoreboard -- not by
+      // wavefront throughput).  One prefetch per distinct row pair: taps (x0, x0+1) are adjacent 128-byte lines.
+      const char* mb = reinterpret_cast<const char*>(p.meas[m]);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(mb + t.off[0]));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(mb + t.off[1]));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(mb + t.off[2]));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(mb + t.off[3]));
+    }
   }
   int4* chunks = reinterpret_cast<int4*>(buf);
   const int e = pl * kPix + pix;
@@ -675,6 +686,8 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
   p.inv_base = 1.0 / (double)max_depth;                                   // utils.py:59-60
   p.inv_step = (1.0 / (double)min_depth - 1.0 / (double)max_depth) / (double)(D - 1);
   p.mode = mode;
+  static const int prefetch_env = []() { const char* e = getenv("DVMVS_SWEEP_PREFETCH"); return e ? atoi(e) : 1; }();
+  p.prefetch = prefetch_env;
   cudaStream_t s = (cudaStream_t)stream;
   const bool aligned = ((uintptr_t)ref % 16 == 0);
   bool fast = (C == 32) && aligned && ((size_t)B * h * w * 128 < ((size_t)1 << 32));   // 32-bit tap byte offsets
@@ -741,6 +754,7 @@ extern "C" int dvmvs_plane_sweep_backward(const float* ref, const float* const* 
   p.inv_base = 1.0 / (double)max_depth;
   p.inv_step = (1.0 / (double)min_depth - 1.0 / (double)max_depth) / (double)(D - 1);
   p.mode = mode;
+  p.prefetch = 0;
   q.gcost = grad_cost;
   q.gref = grad_ref;
   // the same measurement tensor may appear more than once in grad_meas_host (aliased gradients accumulate); zero each once
@@ -795,6 +809,7 @@ extern "C" int dvmvs_plane_sweep_generic(const float* ref, const float* const* m
   p.inv_base = 1.0 / (double)max_depth;
   p.inv_step = (1.0 / (double)min_depth - 1.0 / (double)max_depth) / (double)(D - 1);
   p.mode = mode;
+  p.prefetch = 0;
   const size_t total = (size_t)B * h * w * D;
   launch_k(plane_sweep_generic_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, p);
   return check_launch("plane_sweep_generic_kernel");

@@ -448,17 +448,24 @@ def test_conv2d_tc_vs_fp32_kernel_and_torch(synth, case):
         assert rel_err(got.cpu().numpy(), fp32.cpu().numpy()) <= tol, name
 
 
-def test_fusionnet_c2_tensor_core_backend_vs_oracle(oracle, synth):
-    """BASELINE config 2 through the modules with the tcgen05 backend (stride-2 convs included): <= 1e-3 rel-L1 on
-    inverse depth vs the CPU oracle (the north-star tolerance); measured ~1e-6 with 3-term fp16 pairs."""
+# operand precision of the tensor path: (terms, bound on rel-L1 inverse depth).  3 = fp16 (hi, lo) pairs, measured ~1e-6
+# (synthetic) / ~1e-5 (shipped weights); 1 = plain fp16 operands with fp32 accumulation -- what bench.py runs -- measured
+# 4e-5 / 1.1e-4 (profiles/r01_terms_probe.jsonl).  The north-star budget is 1e-3; the bounds below keep a 3x margin.
+TC_PRECISIONS = [(3, 1e-4), (1, 3.3e-4)]
+
+
+@pytest.mark.parametrize("cfg", [("c2", 256, 256, 64, 2, 3), ("c2", 256, 256, 64, 2, 1), ("c3", 256, 320, 96, 4, 1)])
+def test_fusionnet_tensor_core_backend_vs_oracle(oracle, synth, cfg):
+    """BASELINE configs 2 / 3 through the modules with the tcgen05 backend (stride-2 convs included) vs the CPU oracle."""
     from dvmvs import _ops as ops
     from dvmvs import pipeline
-    H, W, D, M = 256, 256, 64, 2
+    name, H, W, D, M, terms = cfg
+    bound = dict(TC_PRECISIONS)[terms] if name == "c2" else 1e-3      # c2 was measured (3x margin kept); c3: the budget itself
     w = helpers.oracle_weights(oracle, synth, 7, n_depth_levels=D)
     clip = synth.make_clip(0, 3, H, W, M)
     K = T(clip["K"])[None]
     old = ops.conv_backend()
-    ops.set_conv_backend("tc", terms=3, stride2=True)
+    ops.set_conv_backend("tc", terms=terms, stride2=True)
     try:
         mods = helpers.build_product_modules(w, n_depth_levels=D)
         st_o, st_p = oracle.FusionnetState(), pipeline.KeyframeState()
@@ -470,19 +477,20 @@ def test_fusionnet_c2_tensor_core_backend_vs_oracle(oracle, synth):
                 pred, st_p = pipeline.keyframe(mods, st_p, ri.to(DEV), rp.to(DEV), [x.to(DEV) for x in mi], [p.to(DEV) for p in mp],
                                                K.to(DEV), n_depth_levels=D)
                 e = oracle.rel_l1_inverse_depth(pred.cpu().numpy(), gold.numpy())
-                assert e <= 1e-3, "tc backend, frame ref=%d: %.3e" % (ref_i, e)
+                assert e <= bound, "tc backend %s terms=%d, frame ref=%d: %.3e" % (name, terms, ref_i, e)
     finally:
-        ops.set_conv_backend(old)
+        ops.set_conv_backend(old, terms=3)
 
 
-def test_fusionnet_shipped_weights_tensor_core_backend_vs_shipped_golden():
+@pytest.mark.parametrize("terms,bound", TC_PRECISIONS)
+def test_fusionnet_shipped_weights_tensor_core_backend_vs_shipped_golden(terms, bound):
     w = scene_fixture.load_shipped_weights("fusionnet")
     if w is None:
         pytest.skip("shipped weights not fetched (tools/fetch_fixtures.py needs /root/reference in the build container)")
     from dvmvs import _ops as ops
     from oracle import dvmvs_oracle as oracle
     old = ops.conv_backend()
-    ops.set_conv_backend("tc", terms=3, stride2=True)
+    ops.set_conv_backend("tc", terms=terms, stride2=True)
     try:
         mods = helpers.build_product_modules(w)
         frames, full_K, gold = scene_fixture.load_scene()
@@ -494,10 +502,10 @@ def test_fusionnet_shipped_weights_tensor_core_backend_vs_shipped_golden():
                                                              [_cuda(x)[None] for x in fr["measurement_images"]],
                                                              [_cuda(p)[None] for p in fr["measurement_poses"]], _cuda(full_K)[None])
                 errs.append(oracle.rel_l1_inverse_depth(pred[0].cpu().numpy(), gold[i]))
-        print("tc backend rel-L1(inverse depth) vs shipped golden per frame:", ["%.2e" % e for e in errs])
-        assert max(errs) <= 1e-3, errs
+        print("tc backend terms=%d rel-L1(inverse depth) vs shipped golden per frame:" % terms, ["%.2e" % e for e in errs])
+        assert max(errs) <= bound, errs
     finally:
-        ops.set_conv_backend(old)
+        ops.set_conv_backend(old, terms=3)
 
 
 HALO_CASES = [
