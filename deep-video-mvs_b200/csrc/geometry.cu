@@ -138,9 +138,8 @@ __device__ __forceinline__ void sweep_phase_a(const SweepParams& p, const float*
     t.w[2] = (vy1 && vx0) ? gx * fy : 0.f;
     t.w[3] = (vy1 && vx1) ? fx * fy : 0.f;
     if (p.prefetch) {
-      // phase B of this (plane group, frame) runs one step later: start the 128-byte tap lines towards L1 now, so that its
-      // gathers hit (the kernel is bound by load latency -- 47 % of the stall samples are long-scoreboard -- not by
-      // wavefront throughput).  One prefetch per distinct row pair: taps (x0, x0+1) are adjacent 128-byte lines.
+      // experiment (off by default, slower when measured): phase B of this (plane group, frame) runs one step later;
+      // start the 128-byte tap lines towards L1 now so that its gathers hit.
       const char* mb = reinterpret_cast<const char*>(p.meas[m]);
       asm volatile("prefetch.global.L1 [%0];" ::"l"(mb + t.off[0]));
       asm volatile("prefetch.global.L1 [%0];" ::"l"(mb + t.off[1]));
@@ -686,7 +685,9 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
   p.inv_base = 1.0 / (double)max_depth;                                   // utils.py:59-60
   p.inv_step = (1.0 / (double)min_depth - 1.0 / (double)max_depth) / (double)(D - 1);
   p.mode = mode;
-  static const int prefetch_env = []() { const char* e = getenv("DVMVS_SWEEP_PREFETCH"); return e ? atoi(e) : 1; }();
+  // measured and rejected: 96 us with the prefetches vs 75 us without (B200, c2) -- the extra LSU traffic of phase A costs
+  // more than the hits save; kept behind DVMVS_SWEEP_PREFETCH=1 as an experiment switch
+  static const int prefetch_env = []() { const char* e = getenv("DVMVS_SWEEP_PREFETCH"); return e ? atoi(e) : 0; }();
   p.prefetch = prefetch_env;
   cudaStream_t s = (cudaStream_t)stream;
   const bool aligned = ((uintptr_t)ref % 16 == 0);
