@@ -9,7 +9,7 @@ from dvmvs import pipeline, _ops as ops
 from dvmvs.fusionnet.model import FeatureExtractor, FeatureShrinker, CostVolumeEncoder, LSTMFusion, CostVolumeDecoder
 
 H = W = 256; D = 64; M = 2; dev = torch.device("cuda", 0)
-ops.set_conv_backend("tc", terms=3, stride2=True)
+ops.set_conv_backend("tc", terms=int(os.environ.get("DVMVS_TC_TERMS", "3")), stride2=True)
 mods = {"fe": FeatureExtractor(), "fpn": FeatureShrinker(), "cve": CostVolumeEncoder(), "lstm": LSTMFusion(), "cvd": CostVolumeDecoder()}
 for tag, m in mods.items():
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
