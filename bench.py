@@ -33,8 +33,8 @@ H, W, D, M = 256, 256, 64, 2
 WORKLOAD = "fusionnet inference 256x256, 64 planes, 2 measurement frames, batch=%d clip(s)/GPU (BASELINE.json configs[1])"
 SWEEP_BYTES_PER_CLIP = ((1 + M) * 32 + D) * (H // 2) * (W // 2) * 4        # 10,485,760 B at c2
 # dram__bytes_read.sum + dram__bytes_write.sum of plane_sweep_c32_kernel at c2, B=1, from the committed ncu --set full
-# capture profiles/r01_plane_sweep_v3_ncu.md (6.6 MB read, 0 B written: the 4 MiB cost volume stays in L2)
-SWEEP_DRAM_TRAFFIC_PER_CLIP = 6616320
+# capture profiles/r01_plane_sweep_v5_ncu.md (6.68 MB read, 512 B written: the 4 MiB cost volume stays in L2)
+SWEEP_DRAM_TRAFFIC_PER_CLIP = 6684672 + 512
 
 
 def measured_peaks():
@@ -71,7 +71,7 @@ class ClockSampler(threading.Thread):
                 except Exception:
                     r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 self.samples.append((mhz, [n for n, b in bits.items() if r & b]))
-                self.stop_flag.wait(0.05)
+                self.stop_flag.wait(0.004)
         except Exception as e:  # noqa: BLE001
             self.samples.append((None, ["nvml unavailable: %s" % e]))
 
@@ -316,6 +316,44 @@ def run_ours(args, rank, world, local_rank):
                 ms = q0.elapsed_time(q1)
                 extras["batched"] = {"clips_per_gpu": EB, "frames_per_s_per_gpu": EB * 8 / (ms * 1e-3), "ms_per_step": ms / 8}
                 del pb, fb
+            # BASELINE.json configs[2]: 320x256, 96 planes, 4 measurement frames (its own module set: aggregator0 has D+32 inputs)
+            if args.mode == "pipeline":
+                from dvmvs.config import Config as _Config
+                H3, W3, D3, M3 = 256, 320, 96, 4
+                saved_levels = _Config.train_n_depth_levels
+                _Config.train_n_depth_levels = D3
+                try:
+                    mods3 = {"fe": FeatureExtractor(), "fpn": FeatureShrinker(), "cve": CostVolumeEncoder(), "lstm": LSTMFusion(), "cvd": CostVolumeDecoder()}
+                finally:
+                    _Config.train_n_depth_levels = saved_levels
+                for tag, m in mods3.items():
+                    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+                    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes, seed=7).items()}, strict=True)
+                    m.to(dev).eval()
+                clip3 = synth.make_clip(7000 + rank, 16, H3, W3, M3)
+                f3 = []
+                for ref_i, meas_i in clip3["frames"]:
+                    up = lambda a: torch.from_numpy(np.ascontiguousarray(a))[None].to(dev)
+                    f3.append((up(clip3["images"][ref_i]), up(clip3["poses"][ref_i]), [up(clip3["images"][j]) for j in meas_i],
+                               [up(clip3["poses"][j]) for j in meas_i], up(clip3["K"])))
+                p3 = pipeline.PipelinedFusionnet(mods3, batch=1, height=H3, width=W3, n_measurement_frames=M3, n_depth_levels=D3, n_stages=args.stages)
+                out3 = torch.empty((1, H3, W3), dtype=torch.float32, device=dev)
+                p3.prime(*f3[0])
+                for t in range(4):
+                    p3.submit(*f3[t], out=out3)
+                p3.synchronize()
+                torch.cuda.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record(p3.stream_a)
+                for t in range(4, 16):
+                    p3.submit(*f3[t], out=out3)
+                r1.record(p3.stream_b)
+                p3.synchronize()
+                torch.cuda.synchronize()
+                ms = r0.elapsed_time(r1)
+                extras["config_c3_320x256_96planes_4frames"] = {"frames_per_s_per_gpu": 12 / (ms * 1e-3), "ms_per_step": ms / 12,
+                                                                "finite": bool(torch.isfinite(out3).all())}
+                del p3, mods3, f3
             # the other operand precision of the tensor path (fp16 (hi, lo) pairs, three products: ~fp32 accuracy)
             if args.backend == "tc" and args.mode == "pipeline":
                 other = 3 if args.tc_terms == 1 else 1
@@ -456,7 +494,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)       # ~60 ms timed region: enough for a dozen in-region clock samples
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--clips", type=int, default=1, help="independent clips per GPU (batched through the modules)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
