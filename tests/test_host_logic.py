@@ -142,3 +142,54 @@ def test_device_preprocessing_refuses_host_tensors_and_bad_shapes():
     assert (pre.crop_x, pre.crop_y) == (8, 0)
     with pytest.raises(RuntimeError, match="CUDA"):
         pre.apply_rgb_cuda(torch.zeros(48, 64, 3, dtype=torch.uint8), 255.0, [0, 0, 0], [1, 1, 1])
+
+
+def test_feature_cache_ring_semantics():
+    """Row f1 host logic (no kernels involved): FIFO eviction at capacity, re-store of a live id keeps its slot, lookups
+    return channels_last views of the ring entries, counters."""
+    from dvmvs.pipeline import FeatureCache
+    cache = FeatureCache(capacity=3)
+    feats = {i: torch.full((1, 32, 4, 6), float(i)).contiguous(memory_format=torch.channels_last) for i in range(5)}
+    assert cache.lookup(0) is None and cache.misses == 1
+    for i in range(3):
+        cache.store(i, feats[i])
+    assert all(i in cache for i in range(3))
+    got = cache.lookup(1)
+    assert got.shape == (1, 32, 4, 6) and got.is_contiguous(memory_format=torch.channels_last) and float(got.mean()) == 1.0
+    slot_of_1 = cache._index[1]
+    cache.store(1, feats[4])                      # same id again: same slot, new content, nobody evicted
+    assert cache._index[1] == slot_of_1 and float(cache.lookup(1).mean()) == 4.0 and 0 in cache and 2 in cache
+    cache.store(3, feats[3])                      # capacity reached: the oldest entry (id 0) goes
+    assert 0 not in cache and 1 in cache and 2 in cache and 3 in cache
+    cache.store(4, feats[4])
+    assert 1 not in cache and float(cache.lookup(3).mean()) == 3.0
+    assert cache.hits == 3 and cache.misses == 1
+    cache.clear()
+    assert 3 not in cache and cache.lookup(3) is None
+    with pytest.raises(ValueError):
+        FeatureCache(0)
+
+
+def test_precision_policy_parsing_and_scoping():
+    from dvmvs import _ops as ops
+    try:
+        ops.set_precision_policy("fe=1, fpn=1,cvd=3")
+        assert ops.precision_policy() == {"fe": 1, "fpn": 1, "cvd": 3}
+        seen = []
+
+        @ops.family_terms("fe")
+        def inner():
+            seen.append(ops._TC_TERMS)
+            raise KeyError("x")
+
+        before = ops._TC_TERMS
+        with pytest.raises(KeyError):
+            inner()
+        assert seen == [1] and ops._TC_TERMS == before          # restored even when the forward raises
+        with pytest.raises(ValueError):
+            ops.set_precision_policy({"fe": 2})
+        with pytest.raises(ValueError):
+            ops.set_precision_policy({"decoder": 1})
+    finally:
+        ops.set_precision_policy(None)
+    assert ops.precision_policy() == {}
