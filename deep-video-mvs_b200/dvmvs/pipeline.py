@@ -617,3 +617,57 @@ class PipelinedFusionnet:
     def synchronize(self):
         for s in self.streams:
             s.synchronize()
+
+
+class OnlineFusionnet:
+    """The loop body of fusionnet/run-testing-online.py:103-215 as an object: feed every incoming (pose, image) to push();
+    it polls the keyframe buffer (dvmvs.keyframe_buffer.KeyframeBuffer, same selection as the script), and for a new
+    keyframe runs one fusionnet keyframe with the selected measurement frames, carrying the recurrent state and resetting
+    it on tracking loss (run-testing-online.py:106-113).
+
+    Unlike the script it keys a FeatureCache with the buffer's frame ids: a measurement frame
+    that was a reference frame before is neither pre-processed nor pushed through FeatureExtractor + FeatureShrinker
+    again.  Only the buffer's very first frame (stored without a prediction, response 0) ever misses.
+
+        online = OnlineFusionnet(mods, full_K, preprocess=lambda raw: <(1,3,H,W) CUDA tensor>)
+        depth = online.push(pose_4x4_numpy, raw_image)        # (1,H,W) CUDA tensor, or None when no keyframe was due
+
+    `preprocess` maps whatever the caller stores in the buffer as "image" (a decoded frame, a file name, ...) to the
+    network input; it is called for the reference frame and for cache misses only."""
+
+    def __init__(self, mods, full_K, preprocess, n_measurement_frames=None, min_depth=0.25, max_depth=20.0, n_depth_levels=64,
+                 buffer=None, cache_capacity=None):
+        from .config import Config
+        from .keyframe_buffer import KeyframeBuffer
+        self.mods, self.preprocess = mods, preprocess
+        self.device = next(mods["fe"].parameters()).device
+        self.full_K = full_K.to(self.device).reshape(1, 3, 3).float()
+        self.M = Config.test_n_measurement_frames if n_measurement_frames is None else int(n_measurement_frames)
+        self.depth_args = (min_depth, max_depth, n_depth_levels)
+        self.buffer = buffer if buffer is not None else KeyframeBuffer(
+            buffer_size=Config.test_keyframe_buffer_size, keyframe_pose_distance=Config.test_keyframe_pose_distance,
+            optimal_t_score=Config.test_optimal_t_measure, optimal_R_score=Config.test_optimal_R_measure, store_return_indices=False)
+        self.cache = FeatureCache(cache_capacity or self.buffer.buffer.maxlen)
+        self.state = KeyframeState()
+        self.responses = []
+
+    def _pose(self, pose):
+        import numpy as np
+        return torch.from_numpy(np.ascontiguousarray(pose, dtype=np.float32)).reshape(1, 4, 4).to(self.device)
+
+    def push(self, pose, image):
+        response = self.buffer.try_new_keyframe(pose, image)
+        self.responses.append(response)
+        if response == 3:                              # tracking lost: forget the recurrent state (run-testing-online.py:109-113)
+            self.state.reset()
+        if response != 1:
+            return None
+        reference_id = self.buffer.last_frame_id
+        frames, ids = self.buffer.get_best_measurement_frames(self.M, with_ids=True)
+        measurement_images = [None if i in self.cache else self.preprocess(f[1]) for f, i in zip(frames, ids)]
+        measurement_poses = [self._pose(f[0]) for f in frames]
+        with torch.no_grad():
+            pred, self.state = keyframe(self.mods, self.state, self.preprocess(image), self._pose(pose), measurement_images,
+                                        measurement_poses, self.full_K, *self.depth_args, cache=self.cache,
+                                        reference_id=reference_id, measurement_ids=ids)
+        return pred

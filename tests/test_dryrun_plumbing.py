@@ -39,6 +39,17 @@ for backend in ("fp32", "tc"):
                                      T(clip["K"])[None], n_depth_levels=D, cache=cache, reference_id=ref_i, measurement_ids=meas_i)
         assert tuple(pred.shape) == (1, H, W)
     assert cache.misses == M and cache.hits == M, (cache.hits, cache.misses)      # keyframe 0: M misses; keyframe 1: M hits
+    # the online loop: keyframe buffer -> feature cache -> keyframe(); poses 0.15 m apart so that every frame is a keyframe
+    import numpy as np
+    online = pipeline.OnlineFusionnet(mods, T(clip["K"]), preprocess=lambda i: T(clip["images"][i])[None], n_measurement_frames=M, n_depth_levels=D)
+    outs = []
+    for i in range(4):
+        pose = np.eye(4)
+        pose[0, 3] = 0.15 * i
+        outs.append(online.push(pose, i))
+    assert outs[0] is None and all(tuple(o.shape) == (1, H, W) for o in outs[1:]) and online.responses == [0, 1, 1, 1]
+    assert online.cache.misses == 1 and online.cache.hits == 2 + 2
+    assert online.push(np.full((4, 4), np.nan), 9) is None and online.responses[-1] == 5
     # the pipeline engine's stage functions (split MnasNet trunk, sweep / encoder split) compose to a keyframe
     T = torch.from_numpy
     ref_i, meas_i = clip["frames"][0]

@@ -403,6 +403,45 @@ def test_feature_cache_reproduces_recomputed_features(oracle, synth):
         pipes[0].submit(args[0], args[1], [None] * M, args[3], K, reference_id=10 ** 6, measurement_ids=[10 ** 6 + 1, 10 ** 6 + 2])
 
 
+def test_online_engine_reproduces_shipped_golden_with_keyframe_buffer_and_feature_cache():
+    """fusionnet/run-testing-online.py's loop as dvmvs.pipeline.OnlineFusionnet: every frame of fixture scene 000 (pose only
+    for the ones that never become keyframes) goes through the from-scratch KeyframeBuffer; the keyframes it selects, with
+    the measurement frames it picks (3, as in the shipped run), through the shipped fusionnet weights with measurement
+    features from the feature cache.  The first 10 predictions match the reference's shipped golden predictions, and only
+    the buffer's very first frame misses the cache."""
+    import os
+    from dvmvs import pipeline
+    from oracle import dvmvs_oracle as oracle
+    w = scene_fixture.load_shipped_weights("fusionnet")
+    if w is None:
+        pytest.skip("shipped weights not fetched (tools/fetch_fixtures.py needs /root/reference in the build container)")
+    gold_dir = os.path.join(scene_fixture.REPO, "tests", "golden", "keyframes")
+    poses = np.load(os.path.join(gold_dir, "poses_000.npy"))
+    names = open(os.path.join(gold_dir, "image_names_000.txt")).read().split()
+    _, full_K, gold = scene_fixture.load_scene()
+    mods = helpers.build_product_modules(w)
+    calls = []
+
+    def preprocess(name):
+        calls.append(name)
+        img, _, _ = scene_fixture.preprocess_rgb(os.path.join(scene_fixture.SCENE, "images", name), 320, 256)
+        return _cuda(img)[None]
+
+    online = pipeline.OnlineFusionnet(mods, T(full_K), preprocess, n_measurement_frames=3)
+    preds = []
+    for pose, name in zip(poses, names):
+        out = online.push(pose, name)
+        if out is not None:
+            preds.append(out[0].cpu().numpy())
+            if len(preds) == len(gold):
+                break
+    assert len(preds) == len(gold) == 10
+    errs = [oracle.rel_l1_inverse_depth(p, g) for p, g in zip(preds, gold)]
+    assert max(errs) <= 1e-3, errs
+    assert online.cache.misses == 1 and online.cache.hits == 2 + 3 * 8      # keyframe 1: one miss; keyframe 2: 2 hits; then 3 each
+    assert len(calls) == 10 + 1                                                        # each keyframe once + the first frame
+
+
 # ------------------------------------------------------------------------------------------------ tcgen05 backend
 TC_CASES = [
     # name, B, H, W, [src real channels], Cout, k, stride, act, block_n, terms, tol

@@ -193,3 +193,58 @@ def test_precision_policy_parsing_and_scoping():
     finally:
         ops.set_precision_policy(None)
     assert ops.precision_policy() == {}
+
+
+@pytest.mark.parametrize("n_measurement_frames", [1, 2, 3])
+def test_keyframe_buffer_regenerates_the_shipped_index_files(n_measurement_frames):
+    """dvmvs.keyframe_buffer.KeyframeBuffer, driven the way simulate_keyframe_buffer.py:21-47 drives the reference's, over the
+    373 poses of fixture scene 000 reproduces the reference's shipped selection files line for line (which frames become
+    keyframes, which measurement frames are picked, and in which order)."""
+    from dvmvs.config import Config
+    from dvmvs.keyframe_buffer import KeyframeBuffer
+    gold_dir = os.path.join(REPO, "tests", "golden", "keyframes")
+    poses = np.load(os.path.join(gold_dir, "poses_000.npy"))
+    names = open(os.path.join(gold_dir, "image_names_000.txt")).read().split()
+    buf = KeyframeBuffer(buffer_size=Config.test_keyframe_buffer_size, keyframe_pose_distance=Config.test_keyframe_pose_distance,
+                         optimal_t_score=Config.test_optimal_t_measure, optimal_R_score=Config.test_optimal_R_measure,
+                         store_return_indices=True)
+    lines, id_of_index = [], {}
+    for i, pose in enumerate(poses):
+        response = buf.try_new_keyframe(pose, None, index=i)
+        if response in (0, 1):
+            id_of_index[i] = buf.last_frame_id
+        if response == 3:
+            lines.append("TRACKING LOST")
+        elif response == 1:
+            frames, ids = buf.get_best_measurement_frames(n_measurement_frames, with_ids=True)
+            assert ids == [id_of_index[f[2]] for f in frames]            # the ids name the frames that were handed out
+            lines.append(" ".join([names[i]] + [names[f[2]] for f in frames]))
+    gold = open(os.path.join(gold_dir, "keyframe+hololens-dataset+000+nmeas+%d" % n_measurement_frames)).read().splitlines()
+    assert len(lines) == len(gold) == 286
+    assert lines == gold
+
+
+def test_keyframe_buffer_response_codes_and_tracking_loss():
+    from dvmvs.keyframe_buffer import KeyframeBuffer, SimpleBuffer
+    eye = np.eye(4)
+    moved = np.eye(4)
+    moved[0, 3] = 0.2
+    bad = np.full((4, 4), np.nan)
+    buf = KeyframeBuffer(4, 0.1, 0.15, 0.0, store_return_indices=False)
+    assert buf.try_new_keyframe(bad, "x") == 5 and buf.last_frame_id is None
+    assert buf.try_new_keyframe(eye, "a") == 0 and buf.last_frame_id == 0
+    assert buf.try_new_keyframe(eye, "b") == 2                       # no motion
+    assert buf.try_new_keyframe(moved, "c") == 1 and buf.last_frame_id == 1
+    (pose, image), = buf.get_best_measurement_frames(3)              # only one candidate: n is clipped
+    assert image == "a" and np.array_equal(pose, eye)
+    for k in range(30):
+        assert buf.try_new_keyframe(bad, None) == 5
+    assert buf.try_new_keyframe(bad, None) == 3 and len(buf.buffer) == 0
+    assert buf.try_new_keyframe(bad, None) == 4
+    assert buf.try_new_keyframe(eye, "d") == 0 and buf.last_frame_id == 2      # ids keep counting across a loss
+    with pytest.raises(ValueError):
+        KeyframeBuffer(4, 0.1, 0.15, 0.0, store_return_indices=True).try_new_keyframe(eye, None)
+    sb = SimpleBuffer(2, store_return_indices=True)
+    assert [sb.try_new_keyframe(eye, None, index=k) for k in range(4)] == [0, 1, 1, 1]
+    frames, ids = sb.get_measurement_frames(with_ids=True)
+    assert [f[2] for f in frames] == [1, 2] and ids == [1, 2]
