@@ -71,7 +71,31 @@ def full(path, out):
     print("wrote", out)
 
 
+def table(path, out):
+    """One row per profiled launch: duration, tensor-pipe activity, issue slots, DRAM traffic -- the compact evidence table."""
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    reader = csv.reader(io.StringIO(txt))
+    header = next(reader)
+    next(reader)
+    rows = list(reader)
+    idx = {h: i for i, h in enumerate(header)}
+    cols = [("us", "gpu__time_duration.sum"), ("tensor pipe %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+            ("tensor (elapsed) %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+            ("SM busy %", "sm__throughput.avg.pct_of_peak_sustained_elapsed"), ("grid", "launch__grid_size"),
+            ("DRAM rd MB", "dram__bytes_read.sum"), ("DRAM wr MB", "dram__bytes_write.sum")]
+    cols = [(n, k) for n, k in cols if k in idx]
+    with open(out, "w") as fh:
+        fh.write("# per-launch table from `%s` (ncu --set full, --clock-control none)\n\n" % path)
+        fh.write("| # | kernel | " + " | ".join(n for n, _ in cols) + " |\n|---|---|" + "---:|" * len(cols) + "\n")
+        for r in rows:
+            fh.write("| %s | `%s` | %s |\n" % (r[idx["ID"]], short(r[idx["Kernel Name"]]), " | ".join(r[idx[k]] for _, k in cols)))
+    print("wrote", out)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "table":
+        table(sys.argv[2], sys.argv[3])
+        sys.exit(0)
     if sys.argv[1] == "launches":
         skip = int(sys.argv[sys.argv.index("--skip") + 1]) if "--skip" in sys.argv else 0
         launches(sys.argv[2], sys.argv[3], skip)
