@@ -521,9 +521,12 @@ def conv2d_halo(sources_blk, ph, residual=None, terms=3, want_f32=True, want_blk
 # ================================================================================================ backend dispatch
 import os as _os
 
-_BACKEND = _os.environ.get("DVMVS_CONV_BACKEND", "fp32")     # "fp32": CUDA-core kernels; "tc": tcgen05 where eligible
-_TC_TERMS = int(_os.environ.get("DVMVS_TC_TERMS", "3"))
-_TC_STRIDE2 = _os.environ.get("DVMVS_TC_STRIDE2", "0") == "1"
+# "tc" (default): tcgen05 implicit-GEMM kernels wherever a layer is eligible, CUDA-core kernels for the rest (stem, depthwise,
+# depth heads); "fp32": exact-fp32 CUDA-core kernels everywhere -- the device-side cross-check the parity tests pin the
+# tensor path against (tests/conftest.py selects it for the op-level tests).
+_BACKEND = _os.environ.get("DVMVS_CONV_BACKEND", "tc")
+_TC_TERMS = int(_os.environ.get("DVMVS_TC_TERMS", "3"))        # 3: fp16 (hi, lo) pairs ~ fp32 accuracy; 1: plain fp16 operands
+_TC_STRIDE2 = _os.environ.get("DVMVS_TC_STRIDE2", "1") == "1"  # stride-2 convolutions on the tensor path too
 _HALO = _os.environ.get("DVMVS_HALO", "1") == "1"          # blocked-layout halo kernel for large stride-1 k>=3 convolutions
 _HALO_CAT = _os.environ.get("DVMVS_HALO_CAT", "1") == "1"  # two-MMA (concatenated hi/lo weights) form of the three-term product
 _HALO_MIN_PIXELS = int(_os.environ.get("DVMVS_HALO_MIN_PIXELS", "4096"))   # >= 64x64 maps; smaller maps: split-K conv_tc

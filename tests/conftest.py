@@ -4,6 +4,10 @@ import sys
 
 import pytest
 
+# Unless a test selects a backend itself (the tensor-core tests do), the suite runs the exact-fp32 CUDA-core convolutions:
+# they are the device-side reference the 2e-5 op / module tolerances are written for.  The library default is "tc".
+os.environ.setdefault("DVMVS_CONV_BACKEND", "fp32")
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG_DIR = os.path.join(REPO, "deep-video-mvs_b200")
 for p in (REPO, PKG_DIR):

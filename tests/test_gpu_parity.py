@@ -493,7 +493,8 @@ def test_conv2d_tc_vs_fp32_kernel_and_torch(synth, case):
 TC_PRECISIONS = [(3, 1e-4), (1, 3.3e-4)]
 
 
-@pytest.mark.parametrize("cfg", [("c2", 256, 256, 64, 2, 3), ("c2", 256, 256, 64, 2, 1), ("c3", 256, 320, 96, 4, 1)])
+@pytest.mark.parametrize("cfg", [("c2", 256, 256, 64, 2, 3), ("c2", 256, 256, 64, 2, 1), ("c3", 256, 320, 96, 4, 1),
+                                 ("tiny", 64, 96, 64, 2, 3)])        # tiny: 2x3 bottleneck maps through the TMA / split-K paths
 def test_fusionnet_tensor_core_backend_vs_oracle(oracle, synth, cfg):
     """BASELINE configs 2 / 3 through the modules with the tcgen05 backend (stride-2 convs included) vs the CPU oracle."""
     from dvmvs import _ops as ops
