@@ -49,6 +49,8 @@ struct TcParams {
   float aux_mult, aux_base;
   int act;
   float* workspace;           // split-K partial sums [ksplit][out elements]
+  unsigned* tile_counters;    // fused finish: arrival counters, one per (pixel tile, n-block); zero before and after a launch
+  int fused_finish;           // split-K: the last CTA to arrive for a tile reduces the partials in split order + epilogue
   int cluster_reduce;         // split-K splits form one thread-block cluster and reduce through distributed shared memory
   int cat;                    // terms == 3 as two MMAs per K step: x_hi * [w_hi ; w_lo] (2*BLOCK_N columns) + x_lo * w_hi
   int num_stages, stage_bytes, a_bytes, w_bytes;   // smem ring geometry (runtime: sized by the widest K chunk in use)
@@ -316,7 +318,46 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
         }
       }
     }
+    if (split && p.fused_finish) __threadfence();      // this thread's partial sums are visible before the CTA signs in
     tc_fence_before();
+  }
+  if (p.fused_finish) {
+    // ---- split-K, fused finish: every split has published its fp32 partial tile; the LAST CTA to arrive for this
+    // (pixel tile, n-block) -- an atomic counter that cleans itself for the next launch -- sums the partials in split order
+    // (deterministic, same order as conv_tc_finish_kernel) and runs the epilogue.  Saves the finishing launch.
+    volatile uint32_t* last_flag = tmem_slot + 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned* slot = p.tile_counters + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      const unsigned prev = atomicAdd(slot, 1u);
+      const bool last = prev + 1u == (unsigned)p.ksplit;
+      if (last) *slot = 0u;
+      *last_flag = last ? 1u : 0u;
+    }
+    __syncthreads();
+    if (*last_flag && warp >= 2) {
+      __threadfence();
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int ty = row / p.tile_w, tx = row - ty * p.tile_w;
+      const int oy = oy0 + ty, ox = ox0 + tx;
+      if (oy < p.Hout && ox < p.Wout) {
+        const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
+        const size_t plane_stride = (size_t)p.B * p.Hout * p.Wout * p.Cout;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
+          const int cbase = n0 + c0;
+          if (cbase >= p.Cout) break;
+          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          const float* src = p.workspace + pix * p.Cout + cbase;
+          for (int sp = 0; sp < p.ksplit; ++sp, src += plane_stride) {
+            const float4 a0 = __ldcg(reinterpret_cast<const float4*>(src)), a1 = __ldcg(reinterpret_cast<const float4*>(src + 4));
+            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+          }
+          tc_emit8(p, v, b, oy, ox, cbase);
+        }
+      }
+    }
   }
   if (p.cluster_reduce) {
     // split-K over the CTAs of this cluster (blockIdx.z): every CTA has parked its fp32 partial tile in its own shared
@@ -653,10 +694,14 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   const int ctas = p.tiles_x * p.tiles_y * d->B * n_tiles;
   p.ksplit = 1;
   const int n_taps = d->ksize * d->ksize;
-  p.workspace = d->workspace;
+  // head of the workspace: arrival counters of the fused split-K finish (the owner zero-initialises the buffer once, the
+  // kernel leaves them zero); the partial sums follow
+  const long long counter_bytes = 16384;
+  p.tile_counters = reinterpret_cast<unsigned*>(d->workspace);
+  p.workspace = d->workspace ? reinterpret_cast<float*>(reinterpret_cast<char*>(d->workspace) + counter_bytes) : nullptr;
   const size_t out_elems = (size_t)d->B * p.Hout * p.Wout * d->Cout;
-  if (d->allow_split && d->workspace && ctas < 74 && n_taps > 1) {
-    long long fit = d->workspace_bytes / (long long)(out_elems * sizeof(float));
+  if (d->allow_split && d->workspace && d->workspace_bytes > counter_bytes && ctas < 74 && n_taps > 1) {
+    long long fit = (d->workspace_bytes - counter_bytes) / (long long)(out_elems * sizeof(float));
     p.ksplit = (int)max(1LL, min((long long)min(n_taps, (148 + ctas - 1) / ctas), fit));
     const int per = (n_taps + p.ksplit - 1) / p.ksplit;
     p.ksplit = (n_taps + per - 1) / per;              // no empty splits
@@ -669,12 +714,16 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   // cluster barriers) than the 21 short finish launches it removes.  Kept for the record and for larger split counts.
   static const bool cluster_env = []() { const char* e = getenv("DVMVS_CLUSTER_SPLITK"); return e && e[0] == '1'; }();
   p.cluster_reduce = (p.ksplit > 1 && cluster_env && d->Cout % 8 == 0) ? 1 : 0;
+  // DVMVS_SPLITK_FUSED=0 restores the separate finishing kernel (A/B switch)
+  static const bool fused_env = []() { const char* e = getenv("DVMVS_SPLITK_FUSED"); return !(e && e[0] == '0'); }();
+  p.fused_finish = (p.ksplit > 1 && !p.cluster_reduce && fused_env && d->Cout % 8 == 0 &&
+                    (long long)grid.x * grid.y * (long long)sizeof(unsigned) <= counter_bytes) ? 1 : 0;
   int rc;
   if (d->block_n == 32) rc = launch_tc<32>(p, grid, kc_max, s);
   else if (d->block_n == 64) rc = launch_tc<64>(p, grid, kc_max, s);
   else rc = launch_tc<128>(p, grid, kc_max, s);
   if (rc != DVMVS_OK) return rc;
-  if (p.ksplit > 1 && !p.cluster_reduce) {     // launch_tc clears cluster_reduce when it had to fall back to the workspace path
+  if (p.ksplit > 1 && !p.cluster_reduce && !p.fused_finish) {     // launch_tc clears cluster_reduce when it had to fall back to the workspace path
     launch_k(conv_tc_finish_kernel, dim3((unsigned)((out_elems + 255) / 256)), dim3(256), 0, s, p);
     return check_launch("conv_tc_finish_kernel");
   }
