@@ -714,8 +714,10 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   // cluster barriers) than the 21 short finish launches it removes.  Kept for the record and for larger split counts.
   static const bool cluster_env = []() { const char* e = getenv("DVMVS_CLUSTER_SPLITK"); return e && e[0] == '1'; }();
   p.cluster_reduce = (p.ksplit > 1 && cluster_env && d->Cout % 8 == 0) ? 1 : 0;
-  // DVMVS_SPLITK_FUSED=0 restores the separate finishing kernel (A/B switch)
-  static const bool fused_env = []() { const char* e = getenv("DVMVS_SPLITK_FUSED"); return !(e && e[0] == '0'); }();
+  // opt-in (DVMVS_SPLITK_FUSED=1): measured SLOWER on B200 (c2: 1 110 vs 1 677 keyframes/s pipelined, 1.58 vs 1.14 ms sequential):
+  // the one CTA that finishes a tile walks ksplit x BLOCK_N/8 dependent L2 round trips with 128 threads, while the separate
+  // finishing kernel spreads the same reads over the whole GPU and overlaps the next kernel's prologue (PDL).
+  static const bool fused_env = []() { const char* e = getenv("DVMVS_SPLITK_FUSED"); return e && e[0] == '1'; }();
   p.fused_finish = (p.ksplit > 1 && !p.cluster_reduce && fused_env && d->Cout % 8 == 0 &&
                     (long long)grid.x * grid.y * (long long)sizeof(unsigned) <= counter_bytes) ? 1 : 0;
   int rc;
