@@ -153,8 +153,10 @@ __device__ __forceinline__ void sweep_phase_a(const SweepParams& p, const float*
   chunks[sweep_chunk(e, 1)] = *reinterpret_cast<const int4*>(t.w);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_kernel(SweepParams p) {
+// MINB = CTAs per SM the register allocation is capped for (4: 64 registers, 32 resident warps; 3: 85 registers, 24 warps
+// with more gathers in flight per warp -- DVMVS_SWEEP_MINB selects, default 4)
+template <int MODE, int MINB = 4>
+__global__ void __launch_bounds__(kSweepThreads, MINB) plane_sweep_c32_kernel(SweepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_ref = reinterpret_cast<float*>(smem_raw);                                     // [kPix][32]
   SweepTapParams* s_par = reinterpret_cast<SweepTapParams*>(s_ref + kPix * 32);          // [2][kGroup][kPix]
@@ -712,7 +714,17 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
       if (want > smem_launch && want <= 96 * 1024) smem_launch = want;
       else if (want > 96 * 1024) smem_launch = 96 * 1024;
     }
-    if (mode == DVMVS_SWEEP_DOT)
+    static const int minb = []() { const char* e = getenv("DVMVS_SWEEP_MINB"); return e ? atoi(e) : 4; }();
+    if (mode == DVMVS_SWEEP_DOT && (minb == 2 || minb == 3)) {
+      static bool attr2 = false;
+      if (!attr2) {
+        cudaFuncSetAttribute(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr2 = true;
+      }
+      if (minb == 2) launch_k(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT, 2>, dim3(tiles), dim3(kSweepThreads), smem_launch, s, p);
+      else launch_k(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT, 3>, dim3(tiles), dim3(kSweepThreads), smem_launch, s, p);
+    } else if (mode == DVMVS_SWEEP_DOT)
       launch_k(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT>, dim3(tiles), dim3(kSweepThreads), smem_launch, s, p);
     else
       launch_k(plane_sweep_c32_kernel<DVMVS_SWEEP_SAD>, dim3(tiles), dim3(kSweepThreads), smem_launch, s, p);
