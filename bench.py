@@ -525,6 +525,9 @@ def main():
         raise RuntimeError("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line (rank 0): NCCL's own banner / debug lines ("NCCL version ...", printed when the
+        # environment sets NCCL_DEBUG) go to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     result = run_ours(args, rank, world, local_rank)
     if rank == 0:
