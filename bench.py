@@ -525,10 +525,19 @@ def main():
         raise RuntimeError("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
     if world > 1:
         import torch.distributed as dist
-        # stdout carries exactly one JSON line (rank 0): NCCL's own banner / debug lines ("NCCL version ...", printed when the
-        # environment sets NCCL_DEBUG) go to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries exactly one JSON line (rank 0): NCCL prints its "NCCL version ..." banner with a bare printf when the
+        # first communicator is created, so file descriptor 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     result = run_ours(args, rank, world, local_rank)
     if rank == 0:
         if args.cpu_frames > 0:
