@@ -469,9 +469,30 @@ def cpu_baseline(n_frames, threads):
             if sum(times) > 45.0 and len(times) >= 3:          # bounded sample
                 break
     times = times[1:]
-    return {"value": len(times) / sum(times), "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": "%d recurrent keyframes of one c2 clip (256x256, D=64, M=2) after 1 warm-up, torch %s CPU, %d threads"
-                      % (len(times), torch.__version__, threads)}
+    out = {"value": len(times) / sum(times), "unit": "frames/s", "cores": threads, "kind": "port",
+           "sample": "%d recurrent keyframes of one c2 clip (256x256, D=64, M=2) after 1 warm-up, torch %s CPU, %d threads"
+                     % (len(times), torch.__version__, threads)}
+    try:        # the reference's cost_volume_fusion alone, beside the GPU kernel's roofline entry (never fatal)
+        g = torch.Generator().manual_seed(0)
+        f1 = torch.randn(1, 32, H // 2, W // 2, generator=g) * 4
+        f2 = [torch.randn(1, 32, H // 2, W // 2, generator=g) * 4 for _ in range(M)]
+        ref_i, meas_i = clip["frames"][0]
+        half_K = K.clone()
+        half_K[:, 0:2, :] /= 2.0
+        grid = oracle.get_warp_grid_for_cost_volume_calculation(W // 2, H // 2)
+        poses = [torch.from_numpy(clip["poses"][j])[None] for j in meas_i]
+        sw = []
+        with torch.no_grad():
+            for _ in range(3):
+                t0 = time.perf_counter()
+                oracle.cost_volume_fusion(f1, f2, torch.from_numpy(clip["poses"][ref_i])[None], poses, half_K, grid, 0.25, 20.0, D, "cpu", True)
+                sw.append(time.perf_counter() - t0)
+        best = min(sw[1:])
+        out["plane_sweep"] = {"ms_per_cost_volume": best * 1e3, "algorithmic_GBps": SWEEP_BYTES_PER_CLIP / best / 1e9,
+                              "sample": "cost_volume_fusion of one c2 clip (128x128x32 features, D=64, M=2), best of 2 after 1 warm-up"}
+    except Exception as e:  # noqa: BLE001
+        out["plane_sweep"] = {"error": str(e)[:200]}
+    return out
 
 
 def run_reference(args):
