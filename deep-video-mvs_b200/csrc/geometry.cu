@@ -10,6 +10,8 @@
 
 #include <atomic>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dvmvs {
@@ -418,6 +420,178 @@ __global__ void __launch_bounds__(kSweepThreads, 2) plane_sweep_backward_c32_ker
   if (active) *reinterpret_cast<float4*>(q.gref + (pix0 + pix) * 32 + sub * 4) = gacc;
 }
 
+// =====================================================================================================
+// Plane sweep over 16-bit measurement features -- EXPERIMENTAL, opt-in (DVMVS_SWEEP_FP16=1 in the Python binding), not yet
+// measured on hardware.  Motivation: the fp32 kernel sits on the L1 gather path; a CPU probe with the
+// oracle (tools/feature_fp16_probe.py) shows that rounding the sweep's feature inputs to fp16 moves the final inverse depth
+// by <= 1.3e-6 (budget 1e-3), and the FPN's output convolution already emits the fp16 "hi" plane of its result.
+//   * a measurement pixel is 64 bytes, so the two taps of one bilinear ROW (x, x+1) are one contiguous 128-byte span:
+//     a quarter warp fetches it with ONE 16-byte load per lane (lanes 0-3: left pixel, 4-7: right pixel) -- two load
+//     instructions and <= 4 cache lines per sample instead of four and four;
+//   * no blended vector is formed: cost = sum_taps w_t * (f1 . tap_t) is linear, each lane dots its 8 channels of its side
+//     with the matching 8 reference channels and scales by its side's weight; the butterfly over the 8 lanes then adds
+//     channels and sides at once.  fp32 accumulation; dot-product mode only.
+// Phase A (one thread per (pixel, plane)) stores per row the byte offset of the in-image pixel pair (xa, xa+1),
+// xa = clamp(x0, 0, w-2), and the weights of its left / right member (0 where the tap falls outside the image).
+struct __align__(16) SweepPairParams {
+  unsigned off[2];     // byte offsets of the pixel pairs of the two rows (clip offset included)
+  unsigned pad[2];
+  float w[4];          // row0-left, row0-right, row1-left, row1-right
+};
+
+__device__ __forceinline__ void sweep_phase_a_h16(const SweepParams& p, const float* s_G, const float* s_kd, SweepPairParams* buf, int m,
+                                                  int d0, int u0, int v, int npix, float sx, float sy, unsigned clip_off) {
+  const int pix = threadIdx.x & (kPix - 1), pl = threadIdx.x >> 5;
+  const int d = min(d0 + pl, p.D - 1);
+  const float uf = (float)(u0 + min(pix, npix - 1)), vf = (float)v;
+  const float* G = s_G + m * 12;
+  const float* kd = s_kd + (m * p.D + d) * 4;
+  const float q0 = fmaf(G[0], uf, fmaf(G[1], vf, G[2])) + kd[0];
+  const float q1 = fmaf(G[3], uf, fmaf(G[4], vf, G[5])) + kd[1];
+  const float q2 = fmaf(G[6], uf, fmaf(G[7], vf, G[8])) + kd[2];
+  const float r = __frcp_rn(q2 + 1e-8f);
+  const float xs = q0 * r * sx, ys = q1 * r * sy;
+  SweepPairParams t;
+  t.off[0] = t.off[1] = clip_off;
+  t.pad[0] = t.pad[1] = 0u;
+  t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
+  if (xs > -1.f && xs < (float)p.w && ys > -1.f && ys < (float)p.h) {
+    const float x0f = floorf(xs), y0f = floorf(ys);
+    const float fx = xs - x0f, fy = ys - y0f;
+    const float gx = (x0f + 1.f) - xs, gy = (y0f + 1.f) - ys;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    // pair (xa, xa+1) inside the image; the weights follow the taps: x0 -> gx, x0+1 -> fx
+    const int xa = min(max(x0, 0), p.w - 2);
+    const float wl = (x0 == xa) ? gx : ((x0 + 1 == xa) ? fx : 0.f);          // tap that lands on pixel xa
+    const float wr = (x0 + 1 == xa + 1) ? fx : ((x0 == xa + 1) ? gx : 0.f);  // tap that lands on pixel xa + 1
+    const bool vy0 = y0 >= 0, vy1 = y0 + 1 < p.h;
+    const int ya = max(y0, 0), yb = min(y0 + 1, p.h - 1);
+    t.off[0] = clip_off + (unsigned)(ya * p.w + xa) * 64u;
+    t.off[1] = clip_off + (unsigned)(yb * p.w + xa) * 64u;
+    t.w[0] = vy0 ? wl * gy : 0.f;
+    t.w[1] = vy0 ? wr * gy : 0.f;
+    t.w[2] = vy1 ? wl * fy : 0.f;
+    t.w[3] = vy1 ? wr * fy : 0.f;
+  }
+  int4* chunks = reinterpret_cast<int4*>(buf);
+  const int e = pl * kPix + pix;
+  chunks[sweep_chunk(e, 0)] = *reinterpret_cast<const int4*>(t.off);
+  chunks[sweep_chunk(e, 1)] = *reinterpret_cast<const int4*>(t.w);
+}
+
+__device__ __forceinline__ float dot8_h(const uint4 raw, const float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+  const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+  return fmaf(f[7], d.y, fmaf(f[6], d.x, fmaf(f[5], c.y, fmaf(f[4], c.x, fmaf(f[3], b.y, fmaf(f[2], b.x, fmaf(f[1], a.y, f[0] * a.x)))))));
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 4) plane_sweep_c32_h16_kernel(SweepParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_ref = reinterpret_cast<float*>(smem_raw);                                     // [kPix][32] fp32
+  SweepPairParams* s_par = reinterpret_cast<SweepPairParams*>(s_ref + kPix * 32);        // [2][kGroup][kPix]
+  float* s_kd = reinterpret_cast<float*>(s_par + 2 * kGroup * kPix);                     // [M][D][4]
+  float* s_G = s_kd + p.M * p.D * 4;                                                     // [M][12]
+  float* s_out = s_G + kMaxMeas * 12;                                                    // [kPix][D]
+
+  pdl_launch_dependents();
+  const int tid = threadIdx.x;
+  const int tiles_per_row = (p.w + kPix - 1) / kPix;
+  const int tile = blockIdx.x;
+  const int b = tile / (p.h * tiles_per_row);
+  const int rem = tile - b * (p.h * tiles_per_row);
+  const int v = rem / tiles_per_row;
+  const int u0 = (rem - v * tiles_per_row) * kPix;
+  const int npix = min(kPix, p.w - u0);
+  pdl_wait();
+  const size_t pix0 = ((size_t)b * p.h + v) * p.w + u0;
+  if (tid < npix * 8) reinterpret_cast<float4*>(s_ref)[tid] = __ldg(reinterpret_cast<const float4*>(p.ref + pix0 * 32) + tid);
+  if (tid < p.M) {
+    float G[9], Kt[3];
+    sweep_matrices(p.pose1 + b * 16, p.pose2[tid] + b * 16, p.K + b * 9, G, Kt);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s_G[tid * 12 + i] = G[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s_G[tid * 12 + 9 + i] = Kt[i];
+  }
+  __syncthreads();
+  for (int i = tid; i < p.M * p.D; i += kSweepThreads) {
+    const int m = i / p.D, d = i - m * p.D;
+    const float this_depth = (float)(1.0 / (p.inv_base + d * p.inv_step));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s_kd[i * 4 + k] = s_G[m * 12 + 9 + k] / this_depth;
+  }
+  __syncthreads();
+
+  const float sx = (float)(p.w - 1) / (float)p.w, sy = (float)(p.h - 1) / (float)p.h;
+  const unsigned clip_off = (unsigned)b * (unsigned)(p.h * p.w) * 64u;
+  const int n_groups = (p.D + kGroup - 1) / kGroup;
+  const int n_steps = n_groups * p.M;
+  sweep_phase_a_h16(p, s_G, s_kd, s_par, 0, 0, u0, v, npix, sx, sy, clip_off);
+  __syncthreads();
+
+  const int lane = tid & 31, warp = tid >> 5;
+  const int sub = lane & 7;                 // lanes 0-3: left pixel of the pair, 4-7: right pixel; channels (sub & 3) * 8 .. + 7
+  const int side = sub >> 2;
+  const int pix = warp * 4 + (lane >> 3);
+  const bool active = pix < npix;
+  const int e0 = active ? pix : 0;
+  float f1[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) f1[c] = s_ref[e0 * 32 + (sub & 3) * 8 + c];
+
+  float acc[kGroup];
+#pragma unroll
+  for (int k = 0; k < kGroup; ++k) acc[k] = 0.f;
+  int g = 0, m = 0;
+  for (int step = 0; step < n_steps; ++step) {
+    if (step + 1 < n_steps) {
+      const int m1 = (m + 1 == p.M) ? 0 : m + 1, g1 = (m + 1 == p.M) ? g + 1 : g;
+      sweep_phase_a_h16(p, s_G, s_kd, s_par + ((step + 1) & 1) * kGroup * kPix, m1, g1 * kGroup, u0, v, npix, sx, sy, clip_off);
+    }
+    const int4* par = reinterpret_cast<const int4*>(s_par + (step & 1) * kGroup * kPix);
+    const char* img = reinterpret_cast<const char*>(p.meas[m]) + sub * 16;      // 16 bytes = 8 halfs of this lane's pixel of the pair
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) {
+      const int e = k * kPix + e0;
+      const uint4 off = *reinterpret_cast<const uint4*>(&par[sweep_chunk(e, 0)]);
+      const float4 wt = *reinterpret_cast<const float4*>(&par[sweep_chunk(e, 1)]);
+      const float w0 = side ? wt.y : wt.x, w1 = side ? wt.w : wt.z;           // this lane's side, rows 0 / 1
+      float part = 0.f;
+      if (w0 != 0.f) part = w0 * dot8_h(__ldg(reinterpret_cast<const uint4*>(img + off.x)), f1);
+      if (w1 != 0.f) part = fmaf(w1, dot8_h(__ldg(reinterpret_cast<const uint4*>(img + off.y)), f1), part);
+      acc[k] = fmaf(part, 1.f / 32.f, acc[k]);
+    }
+    if (m == p.M - 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float send = (sub & 4) ? acc[k] : acc[k + 4];
+        const float keep = (sub & 4) ? acc[k + 4] : acc[k];
+        acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float send = (sub & 2) ? acc[k] : acc[k + 2];
+        const float keep = (sub & 2) ? acc[k + 2] : acc[k];
+        acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      {
+        const float send = (sub & 1) ? acc[0] : acc[1];
+        const float keep = (sub & 1) ? acc[1] : acc[0];
+        acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      const int d = g * kGroup + sub;
+      if (active && d < p.D) s_out[pix * p.D + d] = acc[0] / (float)p.M;
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k) acc[k] = 0.f;
+    }
+    __syncthreads();
+    if (++m == p.M) { m = 0; ++g; }
+  }
+  float* o = p.out + pix0 * p.D;
+  const int n_items = npix * p.D;
+  for (int i = tid; i < n_items; i += kSweepThreads) o[i] = s_out[i];
+}
+
 // ---- generic path: any C, one thread per (pixel, plane); also the on-device cross-check of the fast path.
 __global__ void plane_sweep_generic_kernel(SweepParams p) {
   pdl_launch_dependents();
@@ -733,6 +907,43 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
   const size_t total = (size_t)B * h * w * D;
   launch_k(plane_sweep_generic_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, s, p);
   return check_launch("plane_sweep_generic_kernel");
+}
+
+// EXPERIMENTAL (see plane_sweep_c32_h16_kernel): reference features fp32 [B][h][w][32], measurement features FP16 [B][h][w][32]
+// (the "hi" plane a tensor-core convolution emits), dot-product cost only.
+extern "C" int dvmvs_plane_sweep_fused_h16(const float* ref, const void* const* meas_h16_host, const float* pose1,
+                                           const float* const* pose2_host, const float* K, float* cost_out, int B, int C, int h, int w,
+                                           int D, int M, float min_depth, float max_depth, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(ref && meas_h16_host && pose1 && pose2_host && K && cost_out, "plane_sweep_h16: null pointer");
+  DVMVS_REQUIRE(B > 0 && C == 32 && h > 1 && w > 1, "plane_sweep_h16: bad shape B=%d C=%d h=%d w=%d (C must be 32)", B, C, h, w);
+  DVMVS_REQUIRE(D >= 2 && D <= kMaxPlanes, "plane_sweep_h16: D=%d outside [2,%d]", D, kMaxPlanes);
+  DVMVS_REQUIRE(M >= 1 && M <= kMaxMeas, "plane_sweep_h16: M=%d outside [1,%d]", M, kMaxMeas);
+  DVMVS_REQUIRE(min_depth > 0.f && max_depth > min_depth, "plane_sweep_h16: bad depth range");
+  DVMVS_REQUIRE((size_t)B * h * w * 64 < ((size_t)1 << 32), "plane_sweep_h16: feature tensor too large for 32-bit offsets");
+  DVMVS_REQUIRE((uintptr_t)ref % 16 == 0, "plane_sweep_h16: pointers must be 16-byte aligned");
+  SweepParams p;
+  p.ref = ref;
+  for (int m = 0; m < M; ++m) {
+    DVMVS_REQUIRE(meas_h16_host[m] && pose2_host[m] && (uintptr_t)meas_h16_host[m] % 16 == 0, "plane_sweep_h16: bad measurement pointer %d", m);
+    p.meas[m] = reinterpret_cast<const float*>(meas_h16_host[m]);
+    p.pose2[m] = pose2_host[m];
+  }
+  p.pose1 = pose1; p.K = K; p.out = cost_out;
+  p.B = B; p.C = C; p.h = h; p.w = w; p.D = D; p.M = M;
+  p.inv_base = 1.0 / (double)max_depth;
+  p.inv_step = (1.0 / (double)min_depth - 1.0 / (double)max_depth) / (double)(D - 1);
+  p.mode = DVMVS_SWEEP_DOT;
+  p.prefetch = 0;
+  const int tiles = B * h * ((w + kPix - 1) / kPix);
+  const size_t smem = (size_t)(kPix * 32 + M * D * 4 + kMaxMeas * 12 + kPix * D) * sizeof(float) + 2 * kGroup * kPix * sizeof(SweepPairParams);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(plane_sweep_c32_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  DVMVS_REQUIRE(smem <= 96 * 1024, "plane_sweep_h16: shared memory %zu too large", smem);
+  launch_k(plane_sweep_c32_h16_kernel, dim3(tiles), dim3(kSweepThreads), smem, (cudaStream_t)stream, p);
+  return check_launch("plane_sweep_c32_h16_kernel");
 }
 
 // ---- backward entry points (row f3) -------------------------------------------------------------------------------

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_conv2d_halo", "dvmvs_split_blocked", "dvmvs_split_planes", "dvmvs_stem_conv", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
     "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw", "dvmvs_preprocess_rgb",
     "dvmvs_plane_sweep_backward", "dvmvs_hidden_warp_backward", "dvmvs_lstm_gates_backward", "dvmvs_depth_loss_forward",
-    "dvmvs_depth_loss_backward",
+    "dvmvs_depth_loss_backward", "dvmvs_plane_sweep_fused_h16",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
         L.dvmvs_last_error_string.restype = ctypes.c_char_p
         L.dvmvs_plane_sweep_fused.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
         L.dvmvs_plane_sweep_generic.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
+        L.dvmvs_plane_sweep_fused_h16.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, p]
         L.dvmvs_hidden_warp.argtypes = [p, p, p, p, p, p, i, i, i, i, f, p]
         L.dvmvs_depth_reproject.argtypes = [p, p, p, p, p, p, i, i, i, p]
         L.dvmvs_conv2d.argtypes = [ctypes.POINTER(ConvDesc), p]

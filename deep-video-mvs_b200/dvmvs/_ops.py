@@ -203,6 +203,28 @@ def plane_sweep(ref_nhwc, meas_nhwc_list, pose1, pose2_list, K, min_depth, max_d
     return out
 
 
+def plane_sweep_h16(ref_nhwc, meas_h16_list, pose1, pose2_list, K, min_depth, max_depth, n_depth_levels):
+    """EXPERIMENTAL (opt-in, DVMVS_SWEEP_FP16=1): the fused plane sweep gathering fp16 measurement features -- (B,h,w,32)
+    float16 tensors, e.g. the hi plane of a tensor-core convolution's output; dot-product cost only."""
+    B, h, w, C = ref_nhwc.shape
+    M = len(meas_h16_list)
+    for m in meas_h16_list:
+        if m.dtype != torch.float16 or tuple(m.shape) != (B, h, w, C) or not m.is_contiguous():
+            raise ValueError("plane_sweep_h16: measurement features must be contiguous float16 %s" % ((B, h, w, C),))
+    pose1 = require_cuda_f32(pose1, "pose1").contiguous()
+    K = require_cuda_f32(K, "K").contiguous()
+    poses = [require_cuda_f32(p, "pose2").contiguous() for p in pose2_list]
+    out = torch.empty((B, h, w, int(n_depth_levels)), dtype=torch.float32, device=ref_nhwc.device)
+    meas_ptrs = (ctypes.c_void_p * M)(*[m.data_ptr() for m in meas_h16_list])
+    pose_ptrs = (ctypes.c_void_p * M)(*[p.data_ptr() for p in poses])
+    N.check(N.lib().dvmvs_plane_sweep_fused_h16(ref_nhwc.data_ptr(), meas_ptrs, pose1.data_ptr(), pose_ptrs, K.data_ptr(), out.data_ptr(), B, C,
+                                                h, w, int(n_depth_levels), M, float(min_depth), float(max_depth), _stream()), "plane_sweep_h16")
+    return out
+
+
+SWEEP_FP16 = _os_environ_get("DVMVS_SWEEP_FP16", "0") == "1"      # experimental, see plane_sweep_h16
+
+
 def preprocess_rgb(image_hwc, crop_x, crop_y, out_h, out_w, scale, mean, std, normalize=True, bgr=None, out=None):
     """Device pre-processing of one decoded frame (dataset_loader.py:260-263,322-334 + run-testing.py:127): image_hwc is a
     CUDA tensor (H,W,3), uint8 (as cv2.imread returns it: BGR unless bgr=False) or float32 (as load_image returns it: RGB

@@ -44,6 +44,11 @@ def cost_volume_fusion(image1, image2s, pose1, pose2s, K, warp_grid, min_depth, 
         from .training import plane_sweep_cost_volume
         return plane_sweep_cost_volume(image1, image2s, pose1, pose2s, K, min_depth, max_depth, n_depth_levels)
     ref = ops.to_nhwc(image1, "image1")
+    if ops.SWEEP_FP16 and dot_product and ref.shape[-1] == 32 and ref.shape[2] >= 2:
+        # experimental (DVMVS_SWEEP_FP16=1): gather the fp16 "hi" plane of the measurement features -- already there when they
+        # come out of a tensor-core convolution, split off once otherwise
+        hi = [ops.to_act(t, "image2").get_planes()[0] for t in image2s]
+        return ops.to_api(ops.plane_sweep_h16(ref, hi, pose1, pose2s, K, min_depth, max_depth, n_depth_levels))
     meas = [ops.to_nhwc(t, "image2") for t in image2s]
     cost = ops.plane_sweep(ref, meas, pose1, pose2s, K, min_depth, max_depth, n_depth_levels, bool(dot_product))
     return ops.to_api(cost)

@@ -65,6 +65,15 @@ int dvmvs_plane_sweep_fused(const float* ref, const float* const* meas_host, con
                             int B, int C, int h, int w, int D, int M, float min_depth, float max_depth,
                             int mode, dvmvs_stream_t stream);
 
+/* EXPERIMENTAL, opt-in (Python: DVMVS_SWEEP_FP16=1), not yet measured on hardware: the same fused plane sweep (DOT mode,
+ * C = 32) gathering 16-bit measurement features -- meas_h16_host: host array of M device pointers to FP16 [B][h][w][32]
+ * tensors (the "hi" plane a tensor-core convolution emits); ref stays fp32.  Replaces dvmvs/utils.py:89-107 like
+ * dvmvs_plane_sweep_fused; rounding the sweep's feature inputs to fp16 moves the final inverse depth by <= 1.3e-6 in the
+ * CPU oracle (tools/feature_fp16_probe.py). */
+int dvmvs_plane_sweep_fused_h16(const float* ref, const void* const* meas_h16_host, const float* pose1,
+                                const float* const* pose2_host, const float* K, float* cost_out, int B, int C, int h, int w,
+                                int D, int M, float min_depth, float max_depth, dvmvs_stream_t stream);
+
 /* Pose-aware hidden-state warp with the invalid-depth mask fused.
  * Replaces dvmvs/utils.py:205-258 warp_frame_depth plus dvmvs/convlstm.py:30-41 (transformation =
  * inverse(previous_pose) @ current_pose; h[depth <= invalid_thresh] = 0).

@@ -47,6 +47,27 @@ def test_plane_sweep_fast_path_equals_generic_path(synth, cases):
         assert rel_err(fast.cpu().numpy(), gen.cpu().numpy()) <= 1e-5
 
 
+@pytest.mark.skipif(__import__("os").environ.get("DVMVS_SWEEP_FP16") != "1",
+                    reason="experimental fp16-feature plane sweep: opt-in (DVMVS_SWEEP_FP16=1), not yet measured on hardware")
+def test_plane_sweep_fp16_features_vs_fp32_kernel(synth, cases):
+    """plane_sweep_c32_h16_kernel (16-bit measurement features, one 128-byte pair load per bilinear row) against the fp32
+    kernel fed the SAME fp16-rounded features (<= 2e-5: same arithmetic up to summation order) and against the unrounded
+    features (<= 2e-3: the rounding itself), including the wide-baseline case with taps off every image edge."""
+    from dvmvs import _ops as ops
+    for name in ("dot_small", "dot_c1", "dot_m3", "dot_wide", "dot_ident"):
+        c = cases.PLANE_SWEEP_CASES[name]
+        inp = cases.plane_sweep_inputs(synth, c)
+        ref = ops.to_nhwc(_cuda(inp["image1"]))
+        meas = [ops.to_nhwc(_cuda(x)) for x in inp["image2s"]]
+        hi = [m.to(torch.float16).contiguous() for m in meas]
+        args = (_cuda(inp["pose1"]), [_cuda(p) for p in inp["pose2s"]], _cuda(inp["K"]), c["min_depth"], c["max_depth"], c["D"])
+        got = ops.plane_sweep_h16(ref, hi, *args).cpu().numpy()
+        same_inputs = ops.plane_sweep(ref, [t.float() for t in hi], *args).cpu().numpy()
+        exact = ops.plane_sweep(ref, meas, *args).cpu().numpy()
+        assert rel_err(got, same_inputs) <= 2e-5, name
+        assert rel_err(got, exact) <= 2e-3, name
+
+
 def test_calculate_cost_volume_by_warping_is_single_frame_fusion(oracle, synth, cases):
     from dvmvs.utils import calculate_cost_volume_by_warping
     c = cases.PLANE_SWEEP_CASES["dot_c1"]
