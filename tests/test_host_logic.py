@@ -248,3 +248,30 @@ def test_keyframe_buffer_response_codes_and_tracking_loss():
     assert [sb.try_new_keyframe(eye, None, index=k) for k in range(4)] == [0, 1, 1, 1]
     frames, ids = sb.get_measurement_frames(with_ids=True)
     assert [f[2] for f in frames] == [1, 2] and ids == [1, 2]
+
+
+def test_pixel_pair_formulation_of_the_fp16_sweep_equals_zero_padded_bilinear(oracle):
+    """The experimental fp16-feature sweep kernel (plane_sweep_c32_h16_kernel) fetches, per bilinear ROW, the in-image pixel
+    pair (xa, xa+1), xa = clamp(x0, 0, w-2), and moves the two tap weights onto its members (0 for a tap outside the image).
+    This restates that rule in numpy (same expressions as sweep_phase_a_h16) and checks it against grid_sample-style
+    zero-padded bilinear sampling (the oracle's bilinear_sample_zeros), including positions off every edge."""
+    rng = np.random.RandomState(0)
+    h, w, C = 7, 9, 4
+    img = rng.randn(1, C, h, w).astype(np.float32)
+    xs = np.concatenate([rng.uniform(-1.5, w + 0.5, 400), [-1.0, -0.999, 0.0, w - 1.0, w - 1.001, w - 0.5, 3.0, -0.5]]).astype(np.float32)
+    ys = np.concatenate([rng.uniform(-1.5, h + 0.5, 400), [2.0, -0.5, h - 1.0, h - 0.25, 0.0, -1.0, h - 1.0, -0.999]]).astype(np.float32)
+    want = oracle.bilinear_sample_zeros(torch.from_numpy(img), torch.from_numpy(xs).reshape(1, 1, -1), torch.from_numpy(ys).reshape(1, 1, -1)).numpy()[0, :, 0]
+    got = np.zeros((C, xs.size), dtype=np.float64)
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        if not (x > -1.0 and x < w and y > -1.0 and y < h):
+            continue
+        x0, y0 = int(np.floor(x)), int(np.floor(y))
+        fx, fy = x - np.floor(x), y - np.floor(y)
+        gx, gy = (np.floor(x) + 1.0) - x, (np.floor(y) + 1.0) - y
+        xa = min(max(x0, 0), w - 2)
+        wl = gx if x0 == xa else (fx if x0 + 1 == xa else 0.0)
+        wr = fx if x0 + 1 == xa + 1 else (gx if x0 == xa + 1 else 0.0)
+        rows = ((max(y0, 0), gy if y0 >= 0 else 0.0), (min(y0 + 1, h - 1), fy if y0 + 1 < h else 0.0))
+        for yy, wy in rows:
+            got[:, i] += wy * (wl * img[0, :, yy, xa] + wr * img[0, :, yy, xa + 1])
+    assert np.abs(got - want).max() <= 1e-5
