@@ -171,7 +171,25 @@ def get_non_differentiable_rectangle_depth_estimation(reference_pose_torch, meas
 # --------------------------------------------------------------------------------------------------
 # layers
 # --------------------------------------------------------------------------------------------------
+BN_TRAINING = False      # True inside train_mode(): BatchNorm normalises with the batch statistics (nn.Module.train())
+
+
+class train_mode:
+    """Context manager: the functional modules below behave like the reference's nn.Modules after .train()
+    (dvmvs/train.py:10-15: batch statistics in every BatchNorm; running statistics are not tracked here)."""
+
+    def __enter__(self):
+        global BN_TRAINING
+        self._saved, BN_TRAINING = BN_TRAINING, True
+
+    def __exit__(self, *exc):
+        global BN_TRAINING
+        BN_TRAINING = self._saved
+
+
 def _bn(sd, p, x):
+    if BN_TRAINING:
+        return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], True, 0.0, BN_EPS)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
                         False, 0.0, BN_EPS)
 
@@ -358,6 +376,35 @@ def update_losses(predictions, weights, groundtruth, loss_type):
         total = total + wgt * (parts[column] / parts[4])
         sums.append([float(v.detach()) if torch.is_tensor(v) else float(v) for v in parts])
     return total, sums
+
+
+def fusionnet_training_forward(weights, images, depths, poses, K, min_depth=0.25, max_depth=20.0, n_depth_levels=64,
+                               loss_type="L1-inv"):
+    """dvmvs/fusionnet/run-training.py:183-281 forward_pass (is_training=True), restated: features of every frame of the
+    subsequence, then for i >= 1 the pair (reference i, measurement i-1): single-frame cost volume, encoder, ConvLSTM with
+    the hidden state warped by the GROUND-TRUTH depth of the reference frame (nearest 1/32, :245-249), decoder, five-scale
+    loss with unit weights (:270-278).  images / depths / poses: lists over the subsequence of (B,3,H,W) / (B,H,W) /
+    (B,4,4).  Returns the optimizer loss (differentiable w.r.t. `weights`).  Call under train_mode()."""
+    B, _, H, W = images[0].shape
+    half_K = K.clone()
+    half_K[:, 0:2, :] = half_K[:, 0:2, :] * 0.5                                        # :191-192 (scaling = 0.5)
+    lstm_K = K.clone()
+    lstm_K[:, 0:2, :] = lstm_K[:, 0:2, :] / 32.0                                       # :194-195
+    grid = get_warp_grid_for_cost_volume_calculation(W // 2, H // 2)
+    feats = [feature_shrinker(weights["fpn"], *feature_extractor(weights["fe"], im)) for im in images]   # :206-215
+    loss, state = 0, None
+    for i in range(1, len(images)):
+        f2, f4, f8, f16 = feats[i]
+        cv = calculate_cost_volume_by_warping(f2, feats[i - 1][0], poses[i], poses[i - 1], half_K, grid, min_depth, max_depth,
+                                              n_depth_levels, "cpu", True)             # :231-241
+        s0, s1, s2, s3, bottom = cost_volume_encoder(weights["cve"], f2, f4, f8, f16, cv)
+        de = F.interpolate(depths[i].view(B, 1, H, W), scale_factor=1.0 / 32.0, mode="nearest")          # :249-253
+        state = lstm_fusion(weights["lstm"], bottom, state, poses[i - 1], poses[i], de, lstm_K)           # :255-260
+        full, half, quarter, eighth, sixteenth = cost_volume_decoder(weights["cvd"], images[i], s0, s1, s2, s3, state[0],
+                                                                      min_depth, max_depth)
+        step_loss, _ = update_losses([sixteenth, eighth, quarter, half, full], [1, 1, 1, 1, 1], depths[i], loss_type)
+        loss = loss + step_loss
+    return loss
 
 
 # --------------------------------------------------------------------------------------------------

@@ -171,3 +171,31 @@ def loss_inputs(synth, c):
     preds[4][:, 10:20, 10:20] = gt[:, 10:20, 10:20]          # exact hits: sign(0) = 0 in every loss
     preds[4][:, 30:34, 30:34] = gt[:, 30:34, 30:34] + 0.25   # inside the quadratic zone of smooth_l1
     return dict(groundtruth=gt, predictions=preds)
+
+
+# ---------------------------------------------------------------------------------------------- whole training step
+# BASELINE.json config 5 scaled down: batch 2, subsequence of 3 (two reference / measurement pairs), 128 x 160, 64 planes
+# (large enough that the train-mode BatchNorms at 1/32 resolution see 40 samples: at 64 x 96 the gradients of the reference
+# differ from THEMSELVES by 1e-3 between 1 and 8 threads).
+TRAIN_STEP_CASE = dict(B=2, T=3, H=128, W=160, D=64, seed=61, loss_type="L1-inv")
+# (module, parameter, slice or None): gradients stored in full
+TRAIN_STEP_FULL_GRADS = [
+    ("fe", "layer1.0.weight", None), ("fe", "layer5.0.0.layers.6.weight", None), ("fpn", "fpn.inner_blocks.4.weight", None),
+    ("fpn", "fpn.layer_blocks.0.bias", None), ("cve", "aggregator0.0.weight", None), ("cve", "encoder_block3.standard_convolution.conv2.1.weight", None),
+    ("lstm", "lstm_cell.conv.weight", (slice(0, 16), slice(0, 16))), ("cvd", "refine.1.0.weight", None), ("cvd", "depth_layer_full.0.bias", None),
+    ("cvd", "decoder_block1.up_convolution.conv.0.weight", (slice(0, 8), slice(0, 8))),
+]
+
+
+def train_step_inputs(synth, c):
+    B, T_, H, W = c["B"], c["T"], c["H"], c["W"]
+    images, depths, poses = [], [], []
+    for t in range(T_):
+        images.append(np.stack([synth.smooth_image("train/%d/img%d_%d" % (c["seed"], b, t), H, W, seed=c["seed"] + b) for b in range(B)]))
+        d = (0.6 + 2.5 * np.abs(synth.tensor("train/%d/depth%d" % (c["seed"], t), (B, H, W), seed=c["seed"]))).astype(np.float32)
+        d[:, 0:3, :] = 0.0                 # invalid ground truth: masked in the loss and in the hidden-state warp
+        d[:, :, 5::17] = 0.0
+        depths.append(d)
+        poses.append(np.stack([synth.camera_pose(t + b) for b in range(B)]))
+    K = np.stack([synth.intrinsics(H, W)] * B)
+    return dict(images=images, depths=depths, poses=poses, K=K)
