@@ -149,7 +149,7 @@ class _DepthLoss(torch.autograd.Function):
                 raise ValueError("predictions must be (B, h, w) tensors, got %s" % (tuple(p.shape),))
         hs = (ctypes.c_int * n)(*[p.shape[1] for p in preds])
         ws = (ctypes.c_int * n)(*[p.shape[2] for p in preds])
-        sums = torch.empty((n, 5), dtype=torch.float32, device=gt.device)
+        sums = (torch.zeros if N.DRYRUN else torch.empty)((n, 5), dtype=torch.float32, device=gt.device)   # zeroed by the entry point
         N.check(N.lib().dvmvs_depth_loss_forward(_ptr_array(preds), hs, ws, n, gt.data_ptr(), sums.data_ptr(), B, H, W, ops._stream()),
                 "depth_loss_forward")
         ctx.save_for_backward(gt, sums, *preds)

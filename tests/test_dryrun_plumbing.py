@@ -50,6 +50,22 @@ for backend in ("fp32", "tc"):
     assert outs[0] is None and all(tuple(o.shape) == (1, H, W) for o in outs[1:]) and online.responses == [0, 1, 1, 1]
     assert online.cache.misses == 1 and online.cache.hits == 2 + 2
     assert online.push(np.full((4, 4), np.nan), 9) is None and online.responses[-1] == 5
+    # the reference-named loss entry points over the fused loss kernels (stubbed here: shapes / bookkeeping only)
+    from dvmvs import losses
+    gt = torch.rand(2, H, W) + 0.5
+    preds = [(torch.rand(2, H // s, W // s) + 0.5).requires_grad_(True) for s in (16, 8, 4, 2, 1)]
+    class Recorder(losses.LossMeter):               # the stubbed kernels leave `sums` unwritten: record, do not divide
+        def update(self, loss, count):
+            self.sum, self.count = loss, count
+    meters = [Recorder() for _ in range(4)]
+    for training in (True, False):
+        out = losses.update_losses(preds, [1, 1, 1, 1, 1], gt, training, *meters, loss_type="L1-inv")
+        assert (torch.is_tensor(out) and out.dim() == 0) if training else out == 0
+    assert len(losses.calculate_loss(gt, preds[-1])) == 5
+    m = losses.LossMeter()
+    m.update(6.0, 3)
+    m.update(2.0, 1)
+    assert (m.sum, m.count, m.avg, m.item_average, repr(m)) == (8.0, 4.0, 2.0, 2.0, "2.0000 (2.0000)")
     # the pipeline engine's stage functions (split MnasNet trunk, sweep / encoder split) compose to a keyframe
     T = torch.from_numpy
     ref_i, meas_i = clip["frames"][0]
