@@ -7,6 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdvmvs_sm100.so")
 
 c_float_p = ctypes.c_void_p
+ABI_VERSION = 4      # dvmvs_abi_version() the descriptor mirrors below were written for; bump with every descriptor / signature change
 _lib = None
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
@@ -21,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_conv2d_halo", "dvmvs_split_blocked", "dvmvs_split_planes", "dvmvs_stem_conv", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
     "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw", "dvmvs_preprocess_rgb",
     "dvmvs_plane_sweep_backward", "dvmvs_hidden_warp_backward", "dvmvs_lstm_gates_backward", "dvmvs_depth_loss_forward",
-    "dvmvs_depth_loss_backward", "dvmvs_plane_sweep_fused_h16",
+    "dvmvs_depth_loss_backward", "dvmvs_plane_sweep_fused_h16", "dvmvs_plane_sweep_tc",
 ]
 
 
@@ -97,11 +98,15 @@ def lib():
             raise RuntimeError("dvmvs: %s not found -- build it with `python deep-video-mvs_b200/build_native.py` "
                                "(there is no CPU / eager fallback)" % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
+        if L.dvmvs_abi_version() != ABI_VERSION:
+            raise RuntimeError("dvmvs: %s has ABI version %d, this binding was written for %d -- rebuild it with "
+                               "`python deep-video-mvs_b200/build_native.py --force`" % (LIB_PATH, L.dvmvs_abi_version(), ABI_VERSION))
         i, f, p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
         L.dvmvs_last_error_string.restype = ctypes.c_char_p
         L.dvmvs_plane_sweep_fused.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
         L.dvmvs_plane_sweep_generic.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
         L.dvmvs_plane_sweep_fused_h16.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, p]
+        L.dvmvs_plane_sweep_tc.argtypes = [p, p, p, p, p, p, p, p, i, i, i, i, i, f, f, i, p]
         L.dvmvs_hidden_warp.argtypes = [p, p, p, p, p, p, i, i, i, i, f, p]
         L.dvmvs_depth_reproject.argtypes = [p, p, p, p, p, p, i, i, i, p]
         L.dvmvs_conv2d.argtypes = [ctypes.POINTER(ConvDesc), p]

@@ -222,6 +222,44 @@ def plane_sweep_h16(ref_nhwc, meas_h16_list, pose1, pose2_list, K, min_depth, ma
     return out
 
 
+def plane_sweep_tc(ref_planes, meas_planes_list, pose1, pose2_list, K, min_depth, max_depth, n_depth_levels, terms=3, out=None):
+    """The fused plane sweep in its tensor-core form (correlate the epipolar band on tcgen05, then blend four scalars per
+    sample; csrc/sweep_tc.cu).  ref_planes / meas_planes_list[m]: fp16 (hi, lo) planes of the 32-channel half-resolution
+    features -- either a (2,B,h,w,32) tensor or a (hi, lo) pair of (B,h,w,32) tensors (batch slices of a stacked tensor).
+    terms=3: fp32-equivalent dot products; terms=1: plain fp16 features (hi planes only).  Dot-product cost only."""
+    def pair(t):
+        hi, lo = (t[0], t[1]) if not isinstance(t, torch.Tensor) or t.dim() == 5 else (t, None)
+        for x in (hi, lo):
+            if x is not None and (x.dtype != torch.float16 or x.dim() != 4 or x.shape[3] != 32 or not x.is_contiguous()):
+                raise ValueError("plane_sweep_tc: feature planes must be contiguous float16 (B,h,w,32), got %s %s" % (tuple(x.shape), x.dtype))
+        return hi, lo
+    rhi, rlo = pair(ref_planes)
+    meas = [pair(t) for t in meas_planes_list]
+    B, h, w, _ = rhi.shape
+    M = len(meas)
+    if M < 1 or M != len(pose2_list):
+        raise ValueError("plane_sweep_tc: need >= 1 measurement frame and as many poses (got %d, %d)" % (M, len(pose2_list)))
+    if any(tuple(hi.shape) != (B, h, w, 32) for hi, _ in meas):
+        raise ValueError("plane_sweep_tc: measurement features differ in shape from the reference features %s" % ((B, h, w, 32),))
+    if terms == 3 and (rlo is None or any(lo is None for _, lo in meas)):
+        raise ValueError("plane_sweep_tc: terms=3 needs the lo planes")
+    pose1 = require_cuda_f32(pose1, "pose1").contiguous()
+    K = require_cuda_f32(K, "K").contiguous()
+    poses = [require_cuda_f32(p, "pose2").contiguous() for p in pose2_list]
+    if tuple(pose1.shape) != (B, 4, 4) or tuple(K.shape) != (B, 3, 3) or any(tuple(p.shape) != (B, 4, 4) for p in poses):
+        raise ValueError("plane_sweep_tc: poses must be (B,4,4) and K (B,3,3)")
+    if out is None:
+        out = torch.empty((B, h, w, int(n_depth_levels)), dtype=torch.float32, device=rhi.device)
+    hi_ptrs = (ctypes.c_void_p * M)(*[hi.data_ptr() for hi, _ in meas])
+    lo_ptrs = (ctypes.c_void_p * M)(*[(lo.data_ptr() if lo is not None else None) for _, lo in meas])
+    pose_ptrs = (ctypes.c_void_p * M)(*[p.data_ptr() for p in poses])
+    N.check(N.lib().dvmvs_plane_sweep_tc(rhi.data_ptr(), rlo.data_ptr() if rlo is not None else None, hi_ptrs, lo_ptrs, pose1.data_ptr(), pose_ptrs,
+                                         K.data_ptr(), out.data_ptr(), B, h, w, int(n_depth_levels), M, float(min_depth), float(max_depth),
+                                         int(terms), _stream()), "plane_sweep_tc")
+    return out
+
+
+SWEEP_TC_MAX_PLANES = 128
 SWEEP_FP16 = _os_environ_get("DVMVS_SWEEP_FP16", "0") == "1"      # experimental, see plane_sweep_h16
 
 

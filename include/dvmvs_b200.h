@@ -74,6 +74,20 @@ int dvmvs_plane_sweep_fused_h16(const float* ref, const void* const* meas_h16_ho
                                 const float* const* pose2_host, const float* K, float* cost_out, int B, int C, int h, int w,
                                 int D, int M, float min_depth, float max_depth, dvmvs_stream_t stream);
 
+/* The fused plane sweep (DOT mode, C = 32, D <= 128) in its tensor-core form: correlate-then-interpolate.  Replaces
+ * dvmvs/utils.py:89-107 like dvmvs_plane_sweep_fused.  The cost is linear in the four bilinear taps, so the kernel forms the
+ * 32-channel dot products of a 16x4 tile of reference pixels with the band of measurement pixels around the tile's
+ * epipolar segment on tcgen05 (band rows fetched by TMA with zero fill = grid_sample's zero padding; accumulators in TMEM),
+ * parks them in shared memory and blends four SCALARS per (pixel, plane) sample.  Degenerate homographies and bands that
+ * do not fit take a direct gather path inside the same kernel.
+ *   ref_hi / ref_lo            fp16 [B][h][w][32]: x = hi + lo (lo unused / may be NULL when terms == 1)
+ *   meas_hi_host / meas_lo_host  host arrays of M device pointers, same layout
+ *   terms                      3: hi*hi + lo*hi + hi*lo (fp32-equivalent dot products); 1: plain fp16 features
+ *   other arguments as dvmvs_plane_sweep_fused. */
+int dvmvs_plane_sweep_tc(const void* ref_hi, const void* ref_lo, const void* const* meas_hi_host, const void* const* meas_lo_host,
+                         const float* pose1, const float* const* pose2_host, const float* K, float* cost_out, int B, int h, int w,
+                         int D, int M, float min_depth, float max_depth, int terms, dvmvs_stream_t stream);
+
 /* Pose-aware hidden-state warp with the invalid-depth mask fused.
  * Replaces dvmvs/utils.py:205-258 warp_frame_depth plus dvmvs/convlstm.py:30-41 (transformation =
  * inverse(previous_pose) @ current_pose; h[depth <= invalid_thresh] = 0).

@@ -12,6 +12,7 @@ from tests.helpers import T, rel_err
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda"
+REPO_DIR = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
 
 
 def _cuda(x):
@@ -66,6 +67,57 @@ def test_plane_sweep_fp16_features_vs_fp32_kernel(synth, cases):
         exact = ops.plane_sweep(ref, meas, *args).cpu().numpy()
         assert rel_err(got, same_inputs) <= 2e-5, name
         assert rel_err(got, exact) <= 2e-3, name
+
+
+@pytest.mark.parametrize("terms,tol", [(3, 2e-5), (1, 2e-3)])
+def test_plane_sweep_tensor_core_form_vs_reference_golden(synth, cases, golden_ops, terms, tol):
+    """plane_sweep_tc_kernel (band correlation on tcgen05 + scalar interpolation) against the golden vectors of the unmodified
+    reference, every dot-product case: small / single-frame / three frames with rotation / wide baseline with samples off
+    every edge and behind the camera (direct path) / identity pose.  terms=3 (fp16 (hi, lo) pairs) is held to the fp32
+    tolerance of the gather kernel; terms=1 carries the rounding of the features to fp16 (<= 2e-3 of the cost volume's
+    magnitude; <= 1.3e-6 on the final inverse depth, profiles/r01_feature_fp16_probe_cpu.jsonl)."""
+    from dvmvs import _ops as ops
+    for name, c in cases.PLANE_SWEEP_CASES.items():
+        if not c["dot"] or c["C"] != 32:
+            continue
+        inp = cases.plane_sweep_inputs(synth, c)
+        ref = ops.split_planes(ops.to_nhwc(_cuda(inp["image1"])))
+        meas = [ops.split_planes(ops.to_nhwc(_cuda(x))) for x in inp["image2s"]]
+        out = ops.plane_sweep_tc(ref, meas, _cuda(inp["pose1"]), [_cuda(p) for p in inp["pose2s"]], _cuda(inp["K"]), c["min_depth"],
+                                 c["max_depth"], c["D"], terms=terms)
+        got = out.permute(0, 3, 1, 2).cpu().numpy()
+        err = rel_err(got, golden_ops["plane_sweep/" + name])
+        assert np.isfinite(got).all() and err <= tol, "plane_sweep_tc/%s terms=%d: %.3e" % (name, terms, err)
+
+
+@pytest.mark.parametrize("qcap", [512, 64])
+def test_plane_sweep_tensor_core_form_full_size_and_band_capacity(synth, qcap):
+    """BASELINE configs 2 / 3 shapes and a batch of clips with different poses against the fp32 gather kernel; qcap=64
+    forces tiny chunks and the direct path for planes whose band does not fit (same results either way)."""
+    import subprocess, sys, json, os
+    code = r"""
+import sys, json, numpy as np, torch
+sys.path[:0] = [%r, %r]
+import synth_data as synth
+from dvmvs import _ops as ops
+res = []
+for (B, h, w, D, M) in ((1, 128, 128, 64, 2), (1, 128, 160, 96, 4), (3, 64, 96, 64, 2)):
+    g = torch.Generator().manual_seed(D + B)
+    f1 = (torch.randn(B, h, w, 32, generator=g) * 4).cuda()
+    f2 = [(torch.randn(B, h, w, 32, generator=g) * 4).cuda() for _ in range(M)]
+    K = torch.from_numpy(synth.intrinsics(2 * h, 2 * w))[None].repeat(B, 1, 1).cuda(); K[:, 0:2, :] /= 2.0
+    pose1 = torch.stack([torch.from_numpy(synth.camera_pose(M + 3 * b)) for b in range(B)]).cuda()
+    pose2 = [torch.stack([torch.from_numpy(synth.camera_pose(M + 3 * b - k * (1 + b))) for b in range(B)]).cuda() for k in range(1, M + 1)]
+    base = ops.plane_sweep(f1, f2, pose1, pose2, K, 0.25, 20.0, D, True)
+    got = ops.plane_sweep_tc(ops.split_planes(f1), [ops.split_planes(t) for t in f2], pose1, pose2, K, 0.25, 20.0, D, terms=3)
+    res.append(float((got - base).abs().max() / base.abs().max()))
+print(json.dumps(res))
+""" % (REPO_DIR, os.path.join(REPO_DIR, "deep-video-mvs_b200"))
+    env = dict(os.environ, DVMVS_SWEEP_QCAP=str(qcap))        # read once per process by the library
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    errs = json.loads(out.stdout.strip().splitlines()[-1])
+    assert all(e <= 2e-5 for e in errs), errs
 
 
 def test_calculate_cost_volume_by_warping_is_single_frame_fusion(oracle, synth, cases):
