@@ -32,9 +32,77 @@ import torch  # noqa: E402
 H, W, D, M = 256, 256, 64, 2
 WORKLOAD = "fusionnet inference 256x256, 64 planes, 2 measurement frames, batch=%d clip(s)/GPU (BASELINE.json configs[1])"
 SWEEP_BYTES_PER_CLIP = ((1 + M) * 32 + D) * (H // 2) * (W // 2) * 4        # 10,485,760 B at c2
-# dram__bytes_read.sum + dram__bytes_write.sum of plane_sweep_c32_kernel at c2, B=1, from the committed ncu --set full
-# capture profiles/r01_plane_sweep_v5_ncu.md (6.68 MB read, 512 B written: the 4 MiB cost volume stays in L2)
-SWEEP_DRAM_TRAFFIC_PER_CLIP = 6684672 + 512
+CONV_FLOP_PER_KEYFRAME = 30.0e9                                             # 2 x 15.0 GMAC at c2
+# dram__bytes_read.sum + dram__bytes_write.sum PER CLIP of the sweep kernel from the committed ncu --set full capture named in
+# SWEEP_TRAFFIC_SOURCE (a profiler run cannot happen inside a timed bench; tools/summarize_ncu.py writes the summary)
+SWEEP_TRAFFIC_FILE = os.path.join(REPO, "profiles", "r02_sweep_tc_traffic.json")
+
+
+def sweep_traffic_per_clip():
+    try:
+        with open(SWEEP_TRAFFIC_FILE) as fh:
+            d = json.load(fh)
+        return float(d["dram_bytes_per_clip"]), d.get("source", os.path.basename(SWEEP_TRAFFIC_FILE))
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
+def workload_config(n_clips, weights_desc):
+    """The workload-defining part of the JSON line: identical for the GPU arm and the reference arm."""
+    return {"workload": WORKLOAD % n_clips, "clips_per_gpu": n_clips, "height": H, "width": W, "planes": D, "measurement_frames": M,
+            "weights": weights_desc, "inputs": "synthetic posed RGB stream (synth_data.make_clip, clip seed = global clip index)"}
+
+
+SHIPPED_FILES = ["0_feature_extractor", "1_feature_pyramid", "2_encoder", "3_lstm_fusion", "4_decoder"]
+TAGS = ["fe", "fpn", "cve", "lstm", "cvd"]
+
+
+def load_weights(which="auto"):
+    """tag -> state dict.  The reference's shipped fusionnet weights when they travelled with the snapshot (D = 64 is what
+    they were trained for; tests/golden/_ref_data, fetched by tools/fetch_fixtures.py), else seeded He-scaled random weights
+    of the same architecture (synth_data.make_state_dict, seed 7)."""
+    d = os.path.join(REPO, "tests", "golden", "_ref_data", "weights", "fusionnet")
+    if which in ("auto", "shipped") and all(os.path.isfile(os.path.join(d, f)) for f in SHIPPED_FILES):
+        return ({tag: torch.load(os.path.join(d, f), map_location="cpu", weights_only=True) for tag, f in zip(TAGS, SHIPPED_FILES)},
+                "reference's shipped fusionnet weights (dvmvs/fusionnet/weights)")
+    if which == "shipped":
+        raise RuntimeError("shipped weights not found under %s" % d)
+    return None, "random-init (seeded, He-scaled) reference architecture"
+
+
+def cpus_of_gpu(index):
+    """Logical CPUs NVML reports as local to GPU `index` (its NUMA node), or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        n = os.cpu_count() or 64
+        words = nv.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        return [c for c in cpus if c < n] or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def physical_core_cpus():
+    """One logical CPU per physical core, socket by socket (Linux sysfs); falls back to all logical CPUs."""
+    seen, out = set(), []
+    n = os.cpu_count() or 1
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        allowed = list(range(n))
+    for c in allowed:
+        base = "/sys/devices/system/cpu/cpu%d/topology/" % c
+        try:
+            key = (int(open(base + "physical_package_id").read()), int(open(base + "core_id").read()))
+        except Exception:  # noqa: BLE001
+            key = (0, c)
+        if key not in seen:
+            seen.add(key)
+            out.append((key, c))
+    out.sort()
+    return [c for _, c in out]
 
 
 def measured_peaks():
@@ -87,7 +155,7 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------- workload
 def make_inputs(n_clips, n_frames, rank):
     import synth_data as synth
-    clips = [synth.make_clip(1000 * rank + c, n_frames, H, W, M) for c in range(n_clips)]
+    clips = [synth.make_clip(100000 + 1000 * rank + c, n_frames, H, W, M) for c in range(n_clips)]
     return clips
 
 
@@ -111,17 +179,29 @@ def run_ours(args, rank, world, local_rank):
     from dvmvs import _ops as ops
     ops.set_conv_backend(args.backend, terms=args.tc_terms, stride2=True)
 
+    from dvmvs import sharding
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # the host thread that enqueues this rank's work stays on the cores of its GPU's NUMA node
+    numa_cpus = cpus_of_gpu(local_rank) if args.pin else None
+    if numa_cpus:
+        try:
+            os.sched_setaffinity(0, numa_cpus)
+        except Exception:  # noqa: BLE001
+            numa_cpus = None
     B = args.clips
     n_frames = args.warmup + args.steps
-    clips = make_inputs(B, n_frames, rank)
+    my_clips = sharding.clips_of_rank(B * world, rank, world)          # clip ids of this rank (round-robin over ranks)
+    clips = [synth.make_clip(c, n_frames, H, W, M) for c in my_clips]
 
-    # random-init weights of the reference architecture (no checkpoints offline): seeded, He-scaled (synth_data.py)
+    shipped, weights_desc = load_weights(args.weights)
     mods = {"fe": FeatureExtractor(), "fpn": FeatureShrinker(), "cve": CostVolumeEncoder(), "lstm": LSTMFusion(), "cvd": CostVolumeDecoder()}
     for tag, m in mods.items():
-        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
-        m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes, seed=7).items()}, strict=True)
+        if shipped is not None:
+            m.load_state_dict(shipped[tag], strict=True)
+        else:
+            shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes, seed=7).items()}, strict=True)
         m.to(dev).eval()
 
     log("modules built; staging %d frames" % n_frames)
@@ -148,11 +228,19 @@ def run_ours(args, rank, world, local_rank):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     pipe = None
+    engine_check = None
     if args.mode == "pipeline":
         pipe = pipeline.PipelinedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=args.stages)
         pred = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         with torch.no_grad():
             pipe.prime(*frames_dev[0])            # one-off graph captures, outside warm-up and timing
+            # the engine must reproduce the module call sequence: first keyframe (no recurrent state) through both
+            pipe.submit(*frames_dev[0], out=pred)
+            pipe.synchronize()
+            eager0, _ = pipeline.keyframe(mods, pipeline.KeyframeState(), *frames_dev[0], n_depth_levels=D)
+            engine_check = float((pred - eager0).abs().max())
+            assert engine_check <= 1e-5 * float(eager0.abs().max()), "pipelined engine deviates from the eager module sequence: %g" % engine_check
+            pipe.reset()
             for t in range(args.warmup):
                 pipe.submit(*frames_dev[t], out=pred)
             pipe.synchronize()
@@ -254,23 +342,44 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = e0.elapsed_time(e1)
     log("e2e arm done")
 
-    # ---------------- roofline of the dominant geometric kernel: fused plane sweep, timed alone
+    # ---------------- roofline of the dominant geometric kernel: the fused plane sweep the engine runs, timed alone
     from dvmvs import _ops as ops
-    f1 = torch.randn(B, H // 2, W // 2, 32, device=dev) * 4
-    f2 = [torch.randn(B, H // 2, W // 2, 32, device=dev) * 4 for _ in range(M)]
     ref, rpose, meas, mpose, K = frames_dev[0]
-    half_K = K.clone()
-    half_K[:, 0:2, :] /= 2.0
-    sw_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
-    for i in range(3):
-        ops.plane_sweep(f1, f2, rpose, mpose, half_K, 0.25, 20.0, D, True)
-    for a, b in sw_ev:
-        flush.zero_()
-        a.record()
-        ops.plane_sweep(f1, f2, rpose, mpose, half_K, 0.25, 20.0, D, True)
-        b.record()
-    torch.cuda.synchronize()
-    sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in sw_ev]))
+
+    def time_sweep(nb):
+        """CUDA-event time of one sweep launch over nb clips (L2 flushed between launches) + its error vs the fp32 gather kernel."""
+        g = torch.Generator(device="cpu").manual_seed(nb)
+        f1 = (torch.randn(nb, H // 2, W // 2, 32, generator=g) * 4).to(dev)
+        f2 = [(torch.randn(nb, H // 2, W // 2, 32, generator=g) * 4).to(dev) for _ in range(M)]
+        rp = rpose[:1].repeat(nb, 1, 1)
+        mp = [p_[:1].repeat(nb, 1, 1) for p_ in mpose]
+        hk = K[:1].repeat(nb, 1, 1).clone()
+        hk[:, 0:2, :] /= 2.0
+        use_tc = ops.sweep_uses_tc(True, 32, D, M)
+        if use_tc:
+            p1, p2 = ops.split_planes(f1), [ops.split_planes(t) for t in f2]
+            run = lambda: ops.plane_sweep_tc(p1, p2, rp, mp, hk, 0.25, 20.0, D, terms=ops.sweep_terms())
+        else:
+            run = lambda: ops.plane_sweep(f1, f2, rp, mp, hk, 0.25, 20.0, D, True)
+        base = ops.plane_sweep(f1, f2, rp, mp, hk, 0.25, 20.0, D, True)
+        err = float((run() - base).abs().max() / base.abs().max())
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for _ in range(3):
+            run()
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            run()
+            b.record()
+        torch.cuda.synchronize()
+        return float(np.median([a.elapsed_time(b) for a, b in evs])), err, ("plane_sweep_tc_kernel<%d>" % ops.sweep_terms()) if use_tc else "plane_sweep_c32_kernel"
+
+    sweep_ms, sweep_err, sweep_kernel = time_sweep(B)
+    sweep_points = {}
+    for nb in (8, 32):
+        if nb != B and args.extras:
+            ms_nb, _, _ = time_sweep(nb)
+            sweep_points["clips_%d" % nb] = {"ms_per_launch": ms_nb, "achieved_GBps": SWEEP_BYTES_PER_CLIP * nb / (ms_nb * 1e-3) / 1e9}
     log("roofline arm done: plane sweep %.3f ms" % sweep_ms)
 
     # ---------------- extra operating points (reported next to the headline, SURVEY.md 8d): strictly sequential latency
@@ -292,8 +401,7 @@ def run_ours(args, rank, world, local_rank):
                 lat.append(a.elapsed_time(b_))
             extras["sequential_latency_ms_per_keyframe"] = float(np.median(lat)) if lat else None
             del eng
-            EB = args.extra_clips
-            if EB > B:
+            for EB in sorted({int(v) for v in str(args.extra_clips).split(",") if int(v) > B}):
                 clips_b = make_inputs(EB, 12, rank)
                 fb = []
                 for t in range(12):
@@ -314,8 +422,27 @@ def run_ours(args, rank, world, local_rank):
                 pb.synchronize()
                 torch.cuda.synchronize()
                 ms = q0.elapsed_time(q1)
-                extras["batched"] = {"clips_per_gpu": EB, "frames_per_s_per_gpu": EB * 8 / (ms * 1e-3), "ms_per_step": ms / 8}
-                del pb, fb
+                fps_b = EB * 8 / (ms * 1e-3)
+                extras["batched_%d" % EB] = {"clips_per_gpu": EB, "frames_per_s_per_gpu": fps_b, "ms_per_step": ms / 8,
+                                             "conv_TFLOPs_algorithmic": fps_b * CONV_FLOP_PER_KEYFRAME / 1e12,
+                                             "finite": bool(torch.isfinite(outb).all())}
+                del pb, fb, outb
+                torch.cuda.empty_cache()
+            # the reference script's own call sequence (module forward()s one by one, M + 1 separate feature passes, host launches)
+            st_s = pipeline.KeyframeState()
+            lat_s = []
+            for t in range(min(n_frames, 14)):
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                w0 = time.perf_counter()
+                a.record()
+                _, st_s = pipeline.keyframe(mods, st_s, *frames_dev[t], n_depth_levels=D, batch_features=False)
+                b_.record()
+                torch.cuda.synchronize()
+                if t >= 4:
+                    lat_s.append((a.elapsed_time(b_), (time.perf_counter() - w0) * 1e3))
+            extras["script_sequence"] = {"ms_per_keyframe_device": float(np.median([x[0] for x in lat_s])),
+                                         "ms_per_keyframe_wall": float(np.median([x[1] for x in lat_s])),
+                                         "note": "run-testing.py:153-202 call sequence through the drop-in modules, eager (one host call per kernel)"}
             # BASELINE.json configs[2]: 320x256, 96 planes, 4 measurement frames (its own module set: aggregator0 has D+32 inputs)
             if args.mode == "pipeline":
                 from dvmvs.config import Config as _Config
@@ -416,68 +543,139 @@ def run_ours(args, rank, world, local_rank):
     total_frames = B * args.steps * world
     peaks, peak_src = measured_peaks()
     achieved = SWEEP_BYTES_PER_CLIP * B / (sweep_ms * 1e-3) / 1e9
+    traffic_per_clip, traffic_src = sweep_traffic_per_clip()
+    fps = total_frames / (dev_ms * 1e-3)
+    tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    conv_tf = fps / world * CONV_FLOP_PER_KEYFRAME / 1e12          # per GPU
+    dtype = "f32" if args.backend == "fp32" else ("f16+f32acc" if args.tc_terms == 1 else "f16x2+f32acc")
+    # final depth maps of every clip on every rank (clip order): the trivial gather of independent clips, outside the timed region
+    gathered = sharding.gather_clip_results({c: pred[i] for i, c in enumerate(my_clips)}, B * world, device=dev)
     result = {
-        "metric": "fusionnet depth frames/sec @256x256x64planes", "value": total_frames / (dev_ms * 1e-3), "unit": "frames/s",
+        "metric": "fusionnet depth frames/sec @256x256x64planes", "value": fps, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.backend == "fp32" else ("f16+f32acc" if args.tc_terms == 1 else "f16x2+f32acc"), "data": "synthetic",
-        "config": {"workload": WORKLOAD % B, "clips_per_gpu": B, "height": H, "width": W, "planes": D, "measurement_frames": M,
-                   "weights": "random-init (seeded) reference architecture", "mode": args.mode + (" (%d stages)" % args.stages if args.mode == "pipeline" else ""),
-                   "conv_backend": args.backend + ("" if args.backend == "fp32" else (" (tcgen05, fp16 operands, fp32 accumulate; parity 4e-5 synthetic / 1.1e-4 shipped weights vs 1e-3 budget, profiles/r01_terms_probe.jsonl)"
-                                                                                       if args.tc_terms == 1 else " (tcgen05, fp16-pair operands x3 terms, fp32 accumulate)")), "l2": ("per-step working set (weights 138 MB + activations) exceeds the 126 MB L2; steps run back to back (pipelined)"
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": workload_config(B, weights_desc),
+        "engine": {"mode": args.mode + (" (%d stages)" % args.stages if args.mode == "pipeline" else ""),
+                   "conv_backend": args.backend + ("" if args.backend == "fp32" else (" (tcgen05, fp16 operands, fp32 accumulate)" if args.tc_terms == 1
+                                                                                         else " (tcgen05, fp16-pair operands x3 terms, fp32 accumulate)")),
+                   "plane_sweep": sweep_kernel,
+                   "parity": "this exact configuration is held to <= 3.3e-4 rel-L1 on inverse depth vs the oracle / the shipped golden by "
+                             "tests/test_gpu_parity.py::test_benchmarked_configuration_* (budget 1e-3)",
+                   "engine_vs_eager_modules_max_abs_diff_first_keyframe": engine_check,
+                   "l2": ("per-step working set (weights 138 MB + activations) exceeds the 126 MB L2; steps run back to back (pipelined)"
                           if args.mode == "pipeline" else "flushed (256 MiB write) between timed steps"),
-                   "parallelism": "clip-sharded x%d, no data-path collective" % world, "host_loop_wall_ms_per_step": (wall1 - wall0) * 1e3 / args.steps,
-                   "host_enqueue_ms_per_step": ((wall_enq - wall0) * 1e3 / args.steps) if args.mode == "pipeline" else None},
+                   "parallelism": "clip-sharded x%d (dvmvs.sharding, round-robin), no data-path collective" % world,
+                   "host_thread_pinned_to_gpu_numa_cpus": len(numa_cpus) if numa_cpus else 0,
+                   "host_loop_wall_ms_per_step": (wall1 - wall0) * 1e3 / args.steps,
+                   "host_enqueue_ms_per_step": ((wall_enq - wall0) * 1e3 / args.steps) if args.mode == "pipeline" else None,
+                   "gathered_depth_checksum": float(sum(float(t.double().sum()) for t in gathered))},
         "clocks": clocks,
         "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": int(lt[0]),
         "operating_points": extras,
-        "roofline": {"kernel": "plane_sweep_c32_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": SWEEP_DRAM_TRAFFIC_PER_CLIP * B, "peak_source": peak_src, "ms_per_launch": sweep_ms,
-                     "algorithmic_bytes_per_launch": SWEEP_BYTES_PER_CLIP * B,
-                     "note": "64 FLOP per algorithmic byte and 512 B of L1 gather traffic per sample: bound by the L1 gather path / FFMA issue, not HBM (DESIGN.md section 6)"},
+        "roofline": {"kernel": sweep_kernel, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": (traffic_per_clip * B) if traffic_per_clip else None,
+                     "traffic_source": traffic_src, "peak_source": peak_src, "ms_per_launch": sweep_ms,
+                     "algorithmic_bytes_per_launch": SWEEP_BYTES_PER_CLIP * B, "rel_err_vs_fp32_gather_kernel": sweep_err,
+                     "batched": {k: dict(v, frac=v["achieved_GBps"] / peaks["hbm_gbs"]) for k, v in sweep_points.items()},
+                     "note": "correlate-then-interpolate on tcgen05: bound by shared-memory traffic and issue slots of the look-ups, not by HBM "
+                             "(64 FLOP per algorithmic byte; DESIGN.md section 6)"},
+        "roofline_conv": {"bound": "tensor", "achieved": conv_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": conv_tf / tensor_peak,
+                          "algorithmic_flop_per_keyframe": CONV_FLOP_PER_KEYFRAME, "peak_source": peak_src + " (sustained bf16)",
+                          "batched": {k: {"achieved": v["conv_TFLOPs_algorithmic"], "frac": v["conv_TFLOPs_algorithmic"] / tensor_peak}
+                                      for k, v in extras.items() if k.startswith("batched_")},
+                          "note": "whole conv stack of a keyframe (2 x MACs of SURVEY App. B) over the CUDA-event time of the pipelined step; "
+                                  "algorithmic FLOPs (1-term products)"},
     }
     return result
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arms
-def host_threads():
-    """Threads the CPU arm uses: torch's default intra-op pool (physical cores), capped -- oversubscribing SMT
-    siblings with OpenMP spin-waits makes the many tiny ops of the plane sweep crawl."""
-    return max(1, min(torch.get_num_threads(), 64))
-
-
-def cpu_baseline(n_frames, threads):
-    """The oracle (restatement of the reference's PyTorch-CPU path) on the host cores: a bounded sample of the same
-    workload (n_frames recurrent keyframes of ONE c2 clip, after one warm-up frame)."""
+def oracle_inputs(n_frames, weights_which="auto"):
+    """Weights (same choice as the GPU arm) and one c2 clip for the oracle-based baselines."""
     import synth_data as synth
     from oracle import dvmvs_oracle as oracle
-    torch.set_num_threads(threads)
-    log("cpu baseline: oracle on %d threads, %d frames" % (threads, n_frames))
-    shapes = oracle.state_dict_shapes(D)
-    w = {tag: {k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes[tag], seed=7).items()} for tag in shapes}
-    clip = synth.make_clip(0, n_frames + 1, H, W, M)
-    K = torch.from_numpy(clip["K"])[None]
-    st = oracle.FusionnetState()
+    w, desc = load_weights(weights_which)
+    if w is None:
+        shapes = oracle.state_dict_shapes(D)
+        w = {tag: {k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes[tag], seed=7).items()} for tag in shapes}
+    clip = synth.make_clip(0, n_frames, H, W, M)
+    return oracle, w, desc, clip
+
+
+def oracle_frames(oracle, w, clip, first, count, device="cpu", state=None):
+    """Runs `count` recurrent keyframes of the clip starting at `first`; returns (seconds per frame list, state)."""
+    K = torch.from_numpy(clip["K"])[None].to(device)
+    st = state if state is not None else oracle.FusionnetState()
     times = []
+    up = lambda a: torch.from_numpy(a)[None].to(device)
     with torch.no_grad():
-        for ref_i, meas_i in clip["frames"]:
+        for ref_i, meas_i in clip["frames"][first:first + count]:
+            if device != "cpu":
+                torch.cuda.synchronize()
             t0 = time.perf_counter()
-            _, st = oracle.fusionnet_step(w, st, torch.from_numpy(clip["images"][ref_i])[None], torch.from_numpy(clip["poses"][ref_i])[None],
-                                          [torch.from_numpy(clip["images"][j])[None] for j in meas_i],
-                                          [torch.from_numpy(clip["poses"][j])[None] for j in meas_i], K, n_depth_levels=D)
+            _, st = oracle.fusionnet_step(w, st, up(clip["images"][ref_i]), up(clip["poses"][ref_i]), [up(clip["images"][j]) for j in meas_i],
+                                          [up(clip["poses"][j]) for j in meas_i], K, n_depth_levels=D)
+            if device != "cpu":
+                torch.cuda.synchronize()
             times.append(time.perf_counter() - t0)
-            if sum(times) > 45.0 and len(times) >= 3:          # bounded sample
-                break
-    times = times[1:]
-    out = {"value": len(times) / sum(times), "unit": "frames/s", "cores": threads, "kind": "port",
-           "sample": "%d recurrent keyframes of one c2 clip (256x256, D=64, M=2) after 1 warm-up, torch %s CPU, %d threads"
-                     % (len(times), torch.__version__, threads)}
+    return times, st
+
+
+def best_thread_count(oracle, w, clip):
+    """The reference's PyTorch-CPU path scales poorly past one socket and collapses when SMT siblings spin in OpenMP barriers
+    (round 1: 0.78 frames/s with 64 threads on one box, 3.76 on another).  Try {8, 16, 32, physical cores} threads, each pinned to
+    that many physical cores (socket 0 first), on one keyframe after a warm-up keyframe; keep the fastest."""
+    cores = physical_core_cpus()
+    cand = sorted({n for n in (8, 16, 32, len(cores)) if 1 <= n <= len(cores)}) or [len(cores)]
+    trials = {}
+    for n in cand:
+        try:
+            os.sched_setaffinity(0, cores[:n])
+        except Exception:  # noqa: BLE001
+            pass
+        torch.set_num_threads(n)
+        t, _ = oracle_frames(oracle, w, clip, 0, 2)
+        trials[n] = t[1]
+        log("cpu threads %d: %.2f s per keyframe" % (n, t[1]))
+    best = min(trials, key=trials.get)
+    try:
+        os.sched_setaffinity(0, cores[:best])
+    except Exception:  # noqa: BLE001
+        pass
+    torch.set_num_threads(best)
+    return best, {str(k): round(v, 3) for k, v in trials.items()}, len(cores)
+
+
+def cpu_baseline(n_frames, weights_which="auto", budget_s=40.0):
+    """The oracle (restatement of the reference's PyTorch-CPU path) on the host cores: a bounded sample of the same workload --
+    up to n_frames recurrent keyframes of ONE c2 clip after one warm-up keyframe, stopping early once budget_s is spent."""
+    saved_aff = None
+    try:
+        saved_aff = os.sched_getaffinity(0)
+    except Exception:  # noqa: BLE001
+        pass
+    saved_threads = torch.get_num_threads()
+    oracle, w, desc, clip = oracle_inputs(n_frames + 1, weights_which)
+    threads, trials, n_phys = best_thread_count(oracle, w, clip)
+    log("cpu baseline: oracle on %d threads, up to %d frames" % (threads, n_frames))
+    times, st = oracle_frames(oracle, w, clip, 0, 1)
+    times = []
+    for t in range(1, n_frames + 1):
+        dt, st = oracle_frames(oracle, w, clip, t, 1, state=st)
+        times += dt
+        if sum(times) > budget_s and len(times) >= 2:
+            break
+    out = {"value": len(times) / sum(times), "unit": "frames/s", "cores": threads, "kind": "port", "frames_run": len(times),
+           "thread_trials_s_per_keyframe": trials, "physical_cores": n_phys, "weights": desc,
+           "sample": "%d recurrent keyframes of one c2 clip (256x256, D=64, M=2) after 1 warm-up, torch %s CPU, %d threads pinned to %d physical cores"
+                     % (len(times), torch.__version__, threads, threads)}
     try:        # SURVEY 8(d): the reference's cost_volume_fusion alone, beside the GPU kernel's roofline entry (never fatal)
         g = torch.Generator().manual_seed(0)
         f1 = torch.randn(1, 32, H // 2, W // 2, generator=g) * 4
         f2 = [torch.randn(1, 32, H // 2, W // 2, generator=g) * 4 for _ in range(M)]
         ref_i, meas_i = clip["frames"][0]
-        half_K = K.clone()
+        half_K = torch.from_numpy(clip["K"])[None].clone()
         half_K[:, 0:2, :] /= 2.0
         grid = oracle.get_warp_grid_for_cost_volume_calculation(W // 2, H // 2)
         poses = [torch.from_numpy(clip["poses"][j])[None] for j in meas_i]
@@ -492,23 +690,59 @@ def cpu_baseline(n_frames, threads):
                               "sample": "cost_volume_fusion of one c2 clip (128x128x32 features, D=64, M=2), best of 2 after 1 warm-up"}
     except Exception as e:  # noqa: BLE001
         out["plane_sweep"] = {"error": str(e)[:200]}
+    if saved_aff is not None:
+        try:
+            os.sched_setaffinity(0, saved_aff)
+        except Exception:  # noqa: BLE001
+            pass
+    torch.set_num_threads(saved_threads)
     return out
 
 
+def gpu_eager_baseline(n_frames=6, weights_which="auto"):
+    """SURVEY 8(d)'s second baseline: the reference algorithm as plain PyTorch eager ON THE B200 (the oracle port moved to
+    cuda: cuDNN convolutions, the D x M Python plane loop with its ~20 element-wise launches per plane, the host round trip
+    in the depth re-projection) -- what a user gets from the reference today on this GPU.  CUDA-event time per keyframe."""
+    try:
+        oracle, w, desc, clip = oracle_inputs(n_frames + 2, weights_which)
+        dev = "cuda"
+        wd = {tag: {k: v.to(dev) for k, v in sd.items()} for tag, sd in w.items()}
+        _, st = oracle_frames(oracle, wd, clip, 0, 2, device=dev)
+        evs = []
+        K = torch.from_numpy(clip["K"])[None].to(dev)
+        up = lambda a: torch.from_numpy(a)[None].to(dev)
+        with torch.no_grad():
+            for ref_i, meas_i in clip["frames"][2:2 + n_frames]:
+                args_ = (up(clip["images"][ref_i]), up(clip["poses"][ref_i]), [up(clip["images"][j]) for j in meas_i], [up(clip["poses"][j]) for j in meas_i])
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _, st = oracle.fusionnet_step(wd, st, *args_, K, n_depth_levels=D)
+                b.record()
+                torch.cuda.synchronize()
+                evs.append(a.elapsed_time(b))
+        ms = float(np.median(evs))
+        return {"value": 1e3 / ms, "unit": "frames/s", "ms_per_keyframe": ms, "kind": "port on cuda (torch eager / cuDNN, fp32, TF32 off)",
+                "frames_run": len(evs), "weights": desc}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:300]}
+
+
 def run_reference(args):
-    threads = host_threads()
-    per_step = 2
-    torch.set_num_threads(threads)
+    """The reference's own CPU implementation of the path (oracle port: the reference is pure PyTorch, nothing compiles), all the
+    host threads it can use (best of a small thread sweep), on the GPU arm's workload.  Runs warm-up + steps keyframes for real when
+    that fits ~2 minutes; otherwise as many as fit, and says how many."""
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: rank 0 is the only rank doing work here, give it the machine back
+    os.environ.pop("OMP_NUM_THREADS", None)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     t0 = time.perf_counter()
-    base = cpu_baseline(max(2, min(args.steps, 8) * per_step // 2), threads)
+    base = cpu_baseline(args.warmup + args.steps - 1, args.weights, budget_s=110.0)
     wall = time.perf_counter() - t0
     fps = base["value"]
-    base["value"] = fps
+    cfg = workload_config(1, base["weights"])
     return {"impl": "reference", "metric": "fusionnet depth frames/sec @256x256x64planes", "value": fps, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / fps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD % 1, "height": H, "width": W, "planes": D, "measurement_frames": M,
-                       "note": "reference's own PyTorch-CPU path (oracle port; the reference has no compiled code), wall %.1f s" % wall},
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "steps_run": base["frames_run"], "ms_per_step": 1e3 / fps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "engine": {"mode": "reference's own PyTorch-CPU path (oracle port; the reference has no compiled code)", "wall_s": wall},
             "cpu_baseline": base, "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
@@ -529,8 +763,12 @@ def main():
                          "<= 1.1e-4 rel-L1 on inverse depth, budget 1e-3); 3 = fp16 (hi, lo) pairs, three products (~1e-6)")
     ap.add_argument("--stages", type=int, default=5, choices=[2, 3, 4, 5], help="pipeline depth of --mode pipeline")
     ap.add_argument("--extras", type=int, default=1, help="also measure sequential latency and batched throughput (0 to skip)")
-    ap.add_argument("--extra-clips", type=int, default=8)
+    ap.add_argument("--extra-clips", default="8,32", help="clips per GPU of the batched operating points (comma separated)")
     ap.add_argument("--cpu-frames", type=int, default=6, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--weights", default="auto", choices=["auto", "shipped", "synthetic"],
+                    help="auto: the reference's shipped fusionnet weights when tests/golden/_ref_data holds them, else seeded random")
+    ap.add_argument("--pin", type=int, default=1, help="pin each rank's host thread to the CPUs local to its GPU (NVML affinity)")
+    ap.add_argument("--gpu-eager", type=int, default=1, help="also time the reference algorithm as PyTorch eager on the GPU (0 to skip)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
@@ -561,8 +799,16 @@ def main():
             os.close(saved_stdout)
     result = run_ours(args, rank, world, local_rank)
     if rank == 0:
+        if args.gpu_eager:
+            result["gpu_eager_baseline"] = gpu_eager_baseline(6, args.weights)
         if args.cpu_frames > 0:
-            result["cpu_baseline"] = cpu_baseline(args.cpu_frames, host_threads())
+            os.environ.pop("OMP_NUM_THREADS", None)
+            try:
+                os.sched_setaffinity(0, range(os.cpu_count() or 1))      # the GPU arm pinned this process to one NUMA node
+            except Exception:  # noqa: BLE001
+                pass
+            torch.set_num_threads(max(1, os.cpu_count() or 1))
+            result["cpu_baseline"] = cpu_baseline(args.cpu_frames, args.weights)
         print(json.dumps(result))
     if world > 1:
         import torch.distributed as dist

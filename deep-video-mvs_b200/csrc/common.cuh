@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/dvmvs_b200.h"
 
 namespace dvmvs {
@@ -64,6 +66,18 @@ inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bl
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// One-time per-DEVICE initialisation guard (function attributes such as the >48 KB dynamic shared-memory opt-in are per
+// device): returns true exactly once per (call site, current device); thread-safe.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};          // bit i: device i initialised (devices >= 64 re-run the init every time)
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const unsigned long long bit = 1ull << dev;
+    return (done.fetch_or(bit) & bit) == 0;
+  }
+};
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -261,10 +261,9 @@ __global__ void __launch_bounds__(256) conv_head_kernel(ConvParams p) {
 template <int KS, int STRIDE>
 static int launch_conv(const ConvParams& p, cudaStream_t s) {
   const size_t smem = (size_t)(CK * plane_stride(KS, STRIDE) + KS * KS * CK * TN) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     cudaFuncSetAttribute(conv2d_direct_kernel<KS, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
   }
   dim3 grid(p.tiles_x * p.tiles_y, (p.d.Cout + TN - 1) / TN, p.d.B * p.ksplit);
   launch_k(conv2d_direct_kernel<KS, STRIDE>, grid, dim3(kConvThreads), smem, s, p);
@@ -435,7 +434,8 @@ constexpr int kLstmWarps = 8;
 // ONCE, all loads in flight together, and stay in registers across the four reduction passes (the kernel sits on the
 // loop-carried critical path of the pipeline; with run-time loops it paid three serialised global-load phases).
 template <int PPW>
-__global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float* __restrict__ gates, const float* __restrict__ c_in,
+__global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float* __restrict__ gates, int n_parts, size_t part_stride,
+                                                                     const float* __restrict__ addend, const float* __restrict__ c_in,
                                                                      float* __restrict__ h_out, float* __restrict__ c_out, int hw, int C) {
   pdl_launch_dependents();
   pdl_wait();
@@ -444,7 +444,16 @@ __global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float
   const int c = blockIdx.x * 32 + lane;
   const int b = blockIdx.y;
   const float* g = gates + (size_t)b * hw * 4 * C;
+  const float* ad = addend ? addend + (size_t)b * hw * 4 * C : nullptr;
   const float inv_n = 1.f / (float)hw;
+  // gate pre-activations = sum of the n_parts split-K partial sums of the gate convolution, in split order (what
+  // conv_tc_finish_kernel computes), + the state-independent half `addend`: the finishing pass of the GEMM is this epilogue
+  auto pre = [&](size_t off) -> float {
+    float x = 0.f;
+    for (int sp = 0; sp < n_parts; ++sp) x += g[(size_t)sp * part_stride + off];
+    if (ad) x += __ldg(ad + off);
+    return x;
+  };
 
   auto block_sum = [&](float v) -> float {
     __syncthreads();
@@ -461,11 +470,11 @@ __global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float
   for (int j = 0; j < PPW; ++j) {
     const int p = warp + j * kLstmWarps;
     const bool ok = p < hw;
-    const float* gp = g + (size_t)(ok ? p : 0) * 4 * C;
-    vi[j] = ok ? gp[c] : 0.f;
-    vf[j] = ok ? gp[C + c] : 0.f;
-    vo[j] = ok ? gp[2 * C + c] : 0.f;
-    vg[j] = ok ? gp[3 * C + c] : 0.f;
+    const size_t gp = (size_t)(ok ? p : 0) * 4 * C;
+    vi[j] = ok ? pre(gp + c) : 0.f;
+    vf[j] = ok ? pre(gp + C + c) : 0.f;
+    vo[j] = ok ? pre(gp + 2 * C + c) : 0.f;
+    vg[j] = ok ? pre(gp + 3 * C + c) : 0.f;
     vc[j] = ok ? c_in[((size_t)b * hw + (ok ? p : 0)) * C + c] : 0.f;
   }
   // LayerNorm statistics of cc_g over the spatial positions (two-pass: mean, then centred variance)
@@ -613,20 +622,27 @@ extern "C" int dvmvs_dwconv2d(const float* x, const float* weight, const float* 
   return check_launch("dwconv_kernel");
 }
 
-extern "C" int dvmvs_lstm_gates(const float* gates, const float* c_in, float* h_out, float* c_out, int B, int h, int w, int C,
-                                dvmvs_stream_t stream) {
-  DVMVS_REQUIRE(gates && c_in && h_out && c_out, "lstm_gates: null pointer");
+extern "C" int dvmvs_lstm_gates_parts(const float* gate_parts, int n_parts, long long part_stride, const float* addend, const float* c_in,
+                                      float* h_out, float* c_out, int B, int h, int w, int C, dvmvs_stream_t stream) {
+  DVMVS_REQUIRE(gate_parts && c_in && h_out && c_out, "lstm_gates: null pointer");
   DVMVS_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && C % 32 == 0, "lstm_gates: bad shape (C must be a multiple of 32)");
+  DVMVS_REQUIRE(n_parts >= 1 && (n_parts == 1 || part_stride >= (long long)B * h * w * 4 * C), "lstm_gates: bad partial-sum layout");
   const int hw = h * w;
   const int ppw = (hw + kLstmWarps - 1) / kLstmWarps;
   DVMVS_REQUIRE(ppw <= 64, "lstm_gates: h*w=%d too large (bottleneck maps up to 512 positions)", hw);
   dim3 grid(C / 32, B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (ppw <= 2) launch_k(lstm_gates_kernel<2>, grid, dim3(32 * kLstmWarps), 0, st, gates, c_in, h_out, c_out, hw, C);
-  else if (ppw <= 8) launch_k(lstm_gates_kernel<8>, grid, dim3(32 * kLstmWarps), 0, st, gates, c_in, h_out, c_out, hw, C);
-  else if (ppw <= 16) launch_k(lstm_gates_kernel<16>, grid, dim3(32 * kLstmWarps), 0, st, gates, c_in, h_out, c_out, hw, C);
-  else launch_k(lstm_gates_kernel<64>, grid, dim3(32 * kLstmWarps), 0, st, gates, c_in, h_out, c_out, hw, C);
+  const size_t ps = (size_t)part_stride;
+  if (ppw <= 2) launch_k(lstm_gates_kernel<2>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
+  else if (ppw <= 8) launch_k(lstm_gates_kernel<8>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
+  else if (ppw <= 16) launch_k(lstm_gates_kernel<16>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
+  else launch_k(lstm_gates_kernel<64>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
   return check_launch("lstm_gates_kernel");
+}
+
+extern "C" int dvmvs_lstm_gates(const float* gates, const float* c_in, float* h_out, float* c_out, int B, int h, int w, int C,
+                                dvmvs_stream_t stream) {
+  return dvmvs_lstm_gates_parts(gates, 1, 0, nullptr, c_in, h_out, c_out, B, h, w, C, stream);
 }
 
 extern "C" int dvmvs_upsample2x(const float* x, float* y, int B, int H, int W, int C, dvmvs_stream_t stream) {

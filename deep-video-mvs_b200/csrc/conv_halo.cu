@@ -40,6 +40,7 @@ struct HaloParams {
   float* out_f32;              // [B][H][W][Cout] or null
   __half* out_blk;             // [2][B][Cout/8][H][W][8] or null
   __half* out_nhwc;            // [2][B][H][W][Cout] or null
+  int hi_only;                 // fp16 outputs: hi plane only
   int act;
   uint32_t a_bytes, w_bytes;   // per plane: halo tile bytes of one group, weight bytes of one (group, ky) stage
   unsigned long long* dbg;     // optional timeline dump: [cta][8] globaltimer ns at phase boundaries (profiling aid)
@@ -261,12 +262,12 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
         if (p.out_blk) {
           __half* o = p.out_blk + (((size_t)b * p.c8_out + (cbase >> 3)) * hw + (size_t)oy * p.Wout + ox) * 8;
           *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(hi);
-          *reinterpret_cast<uint4*>(o + plane_elems) = *reinterpret_cast<const uint4*>(lo);
+          if (!p.hi_only) *reinterpret_cast<uint4*>(o + plane_elems) = *reinterpret_cast<const uint4*>(lo);
         }
         if (p.out_nhwc) {
           __half* o = p.out_nhwc + pix * p.Cout + cbase;
           *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(hi);
-          *reinterpret_cast<uint4*>(o + nhwc_plane) = *reinterpret_cast<const uint4*>(lo);
+          if (!p.hi_only) *reinterpret_cast<uint4*>(o + nhwc_plane) = *reinterpret_cast<const uint4*>(lo);
         }
       }
     }
@@ -362,9 +363,8 @@ static int make_halo_map(CUtensorMap* map, const void* ptr, int B, int H, int W,
   cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)C8 * H * W * 16};
   cuuint32_t box[4] = {(cuuint32_t)halo_w * 8, (cuuint32_t)halo_h, (cuuint32_t)kc8, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = tensor_map_encoder()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = cached_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(blocked activation B=%d H=%d W=%d C8=%d halo %dx%d) failed: %d", B, H, W, C8, halo_w, halo_h, (int)r);
     return DVMVS_EINVAL;
@@ -374,11 +374,10 @@ static int make_halo_map(CUtensorMap* map, const void* ptr, int B, int H, int W,
 
 template <int BLOCK_N, int KSIZE, int KC, int TERMS>
 static int launch_halo(const HaloParams& p, dim3 grid, size_t smem, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, KSIZE, KC, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("conv_halo smem attribute: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
-    attr_set = true;
   }
   launch_k(conv_halo_kernel<BLOCK_N, KSIZE, KC, TERMS>, grid, dim3(kHaloThreads), smem, s, p);
   return check_launch("conv_halo_kernel");
@@ -449,6 +448,7 @@ extern "C" int dvmvs_conv2d_halo(const dvmvs_conv_halo_desc* d, dvmvs_stream_t s
   DVMVS_REQUIRE(!p.w_cat || (uintptr_t)p.w_cat % 16 == 0, "conv2d_halo: w_cat not 16-byte aligned");
   p.bias = d->bias; p.residual = d->residual; p.act = d->act;
   p.out_f32 = d->out_f32; p.out_blk = (__half*)d->out_blk; p.out_nhwc = (__half*)d->out_nhwc;
+  p.hi_only = d->out_hi_only ? 1 : 0;
   p.dbg = (unsigned long long*)g_halo_dbg;
   const int planes = d->terms > 1 ? 2 : 1;
   const size_t smem = 2 * (size_t)planes * p.a_bytes + kHaloWStages * (size_t)planes * p.w_bytes + 256 + 128;

@@ -21,6 +21,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "tc_ptx.cuh"
 
 namespace dvmvs {
@@ -52,6 +55,7 @@ struct TcParams {
   unsigned* tile_counters;    // fused finish: arrival counters, one per (pixel tile, n-block); zero before and after a launch
   int fused_finish;           // split-K: the last CTA to arrive for a tile reduces the partials in split order + epilogue
   int cluster_reduce;         // split-K splits form one thread-block cluster and reduce through distributed shared memory
+  int hi_only;                // fp16 outputs: write the hi plane only (every consumer runs 1-term products)
   int cat;                    // terms == 3 as two MMAs per K step: x_hi * [w_hi ; w_lo] (2*BLOCK_N columns) + x_lo * w_hi
   int num_stages, stage_bytes, a_bytes, w_bytes;   // smem ring geometry (runtime: sized by the widest K chunk in use)
 };
@@ -106,11 +110,11 @@ __device__ __forceinline__ void tc_emit8(const TcParams& p, float (&v)[8], int b
     }
     __half* oh = p.out_planes + pix * p.Cout + cbase;
     *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(oh + plane_stride) = *reinterpret_cast<const uint4*>(lo);
+    if (!p.hi_only) *reinterpret_cast<uint4*>(oh + plane_stride) = *reinterpret_cast<const uint4*>(lo);
     if (p.out_blk) {
       __half* ob = p.out_blk + ((((size_t)b * (p.Cout >> 3) + (cbase >> 3)) * p.Hout + oy) * p.Wout + ox) * 8;
       *reinterpret_cast<uint4*>(ob) = *reinterpret_cast<const uint4*>(hi);
-      *reinterpret_cast<uint4*>(ob + plane_stride) = *reinterpret_cast<const uint4*>(lo);
+      if (!p.hi_only) *reinterpret_cast<uint4*>(ob + plane_stride) = *reinterpret_cast<const uint4*>(lo);
     }
   }
 }
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
           if (p.out_planes) {
             const __half h = __float2half_rn(x);
             p.out_planes[pix * p.Cout + c] = h;
-            p.out_planes[plane_stride + pix * p.Cout + c] = __float2half_rn(x - __half2float(h));
+            if (!p.hi_only) p.out_planes[plane_stride + pix * p.Cout + c] = __float2half_rn(x - __half2float(h));
           }
         }
       }
@@ -421,11 +425,11 @@ __global__ void conv_tc_finish_kernel(TcParams p) {
     const __half h = __float2half_rn(x);
     const __half l = __float2half_rn(x - __half2float(h));
     p.out_planes[idx] = h;
-    p.out_planes[total + idx] = l;
+    if (!p.hi_only) p.out_planes[total + idx] = l;
     if (p.out_blk) {
       const size_t o = ((((size_t)b * (p.Cout >> 3) + (c >> 3)) * p.Hout + oy) * p.Wout + ox) * 8 + (c & 7);
       p.out_blk[o] = h;
-      p.out_blk[total + o] = l;
+      if (!p.hi_only) p.out_blk[total + o] = l;
     }
   }
 }
@@ -538,15 +542,57 @@ EncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 
+namespace {
+struct MapKeyAll {
+  unsigned long long w[16];
+  bool operator==(const MapKeyAll& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct MapKeyAllHash {
+  size_t operator()(const MapKeyAll& k) const {
+    unsigned long long h = 0xcbf29ce484222325ull;
+    for (int i = 0; i < 16; ++i) { h ^= k.w[i]; h *= 0x100000001b3ull; h ^= h >> 29; }
+    return (size_t)h;
+  }
+};
+std::mutex g_tm_mutex;
+std::unordered_map<MapKeyAll, CUtensorMap, MapKeyAllHash> g_tm_cache;
+}  // namespace
+
+CUresult cached_tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* ptr, const cuuint64_t* dims,
+                           const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle,
+                           CUtensorMapL2promotion promo) {
+  MapKeyAll key;
+  memset(&key, 0, sizeof(key));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  key.w[0] = (unsigned long long)(uintptr_t)ptr;
+  key.w[1] = ((unsigned long long)dtype << 48) | ((unsigned long long)rank << 40) | ((unsigned long long)swizzle << 32) | ((unsigned long long)promo << 24) |
+             (unsigned long long)(dev & 0xff);
+  for (int i = 0; i < rank && i < 5; ++i) {
+    key.w[2 + i] = dims[i];
+    key.w[7 + i] = (i + 1 < rank) ? strides[i] : 0;
+    key.w[12 + (i >> 1)] |= ((unsigned long long)box[i] | ((unsigned long long)estr[i] << 24)) << (32 * (i & 1));
+  }
+  std::lock_guard<std::mutex> lock(g_tm_mutex);
+  auto it = g_tm_cache.find(key);
+  if (it != g_tm_cache.end()) { *out = it->second; return CUDA_SUCCESS; }
+  CUresult r = tensor_map_encoder()(out, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) {
+    if (g_tm_cache.size() > 16384) g_tm_cache.clear();
+    g_tm_cache.emplace(key, *out);
+  }
+  return r;
+}
+
 static int make_act_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int Cs, int kchunk, int tile_w, int tile_h,
                         int stride) {
   cuuint64_t dims[4] = {(cuuint64_t)Cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
   cuuint32_t box[4] = {(cuuint32_t)kchunk, (cuuint32_t)((tile_w - 1) * stride + 1), (cuuint32_t)((tile_h - 1) * stride + 1), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = tensor_map_encoder()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, kchunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = cached_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ptr, dims, strides, box, estr,
+                                 kchunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(activation B=%d H=%d W=%d C=%d chunk=%d) failed: %d", B, H, W, Cs, kchunk, (int)r);
     return DVMVS_EINVAL;
@@ -559,9 +605,8 @@ static int make_w_map(CUtensorMap* map, const void* ptr, int rows, int ktot, int
   cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
   cuuint32_t box[2] = {(cuuint32_t)kchunk, (cuuint32_t)block_n};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = tensor_map_encoder()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, kchunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = cached_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr,
+                                 kchunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(weights rows=%d K=%d chunk=%d) failed: %d", rows, ktot, kchunk, (int)r);
     return DVMVS_EINVAL;
@@ -571,11 +616,10 @@ static int make_w_map(CUtensorMap* map, const void* ptr, int rows, int ktot, int
 
 template <int BLOCK_N>
 static int launch_tc(TcParams& p, dim3 grid, int kc_max, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess) { set_error("conv_tc smem attribute: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
-    attr_set = true;
   }
   // smem ring sized by the widest K chunk actually used; small stages => several CTAs co-reside per SM, which is what
   // hides the prologue / epilogue / TMA latency of these short tiles
@@ -596,10 +640,9 @@ static int launch_tc(TcParams& p, dim3 grid, int kc_max, cudaStream_t s) {
     const int z = (int)grid.z;
     bool ok = z <= 16 && kTileM * BLOCK_N * 4 <= stages * p.stage_bytes;
     if (ok && cluster_ok[z] == 0) {
-      static bool np_set = false;
-      if (!np_set) {
+      static PerDeviceOnce np_set;
+      if (np_set.first()) {
         cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        np_set = true;
       }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kMaxSmemBytes;   // worst case: 1 CTA per SM
@@ -636,7 +679,7 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   DVMVS_REQUIRE(d->terms == 1 || d->terms == 3, "conv2d_tc: terms=%d", d->terms);
   DVMVS_REQUIRE(d->B > 0 && d->Hin > 0 && d->Win > 0 && d->Cout > 0 && d->w_hi && (d->terms == 1 || d->w_lo),
                 "conv2d_tc: bad shape / null weights");
-  DVMVS_REQUIRE(d->out_f32 || d->out_planes, "conv2d_tc: no output");
+  DVMVS_REQUIRE(d->out_f32 || d->out_planes || d->defer_finish, "conv2d_tc: no output");
   DVMVS_REQUIRE(d->block_n == 32 || d->block_n == 64 || d->block_n == 128, "conv2d_tc: block_n=%d", d->block_n);
   DVMVS_REQUIRE(d->w_rows % d->block_n == 0 && d->w_rows >= d->Cout, "conv2d_tc: weight rows %d not a multiple of block_n", d->w_rows);
   DVMVS_REQUIRE(d->out_planes == nullptr || d->Cout % 8 == 0, "conv2d_tc: fp16-pair output needs Cout %% 8 == 0");
@@ -689,6 +732,7 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   p.out_blk = (__half*)d->out_blk;
   DVMVS_REQUIRE(!d->out_blk || (d->out_planes && d->Cout % 8 == 0), "conv2d_tc: out_blk needs out_planes and Cout %% 8 == 0");
   p.aux_mult = d->aux_mult; p.aux_base = d->aux_base; p.act = d->act;
+  p.hi_only = d->out_hi_only ? 1 : 0;
   cudaStream_t s = (cudaStream_t)stream;
   const int n_tiles = (d->Cout + d->block_n - 1) / d->block_n;
   const int ctas = p.tiles_x * p.tiles_y * d->B * n_tiles;
@@ -725,11 +769,45 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   else if (d->block_n == 64) rc = launch_tc<64>(p, grid, kc_max, s);
   else rc = launch_tc<128>(p, grid, kc_max, s);
   if (rc != DVMVS_OK) return rc;
+  if (d->defer_finish) {
+    // the caller's own epilogue kernel sums the split-K partial sums (dvmvs_lstm_gates_parts): only legal when this launch split
+    DVMVS_REQUIRE(p.ksplit > 1 && !p.cluster_reduce && !p.fused_finish, "conv2d_tc: defer_finish without a split-K launch (ask dvmvs_conv2d_tc_ksplit first)");
+    return DVMVS_OK;
+  }
   if (p.ksplit > 1 && !p.cluster_reduce && !p.fused_finish) {     // launch_tc clears cluster_reduce when it had to fall back to the workspace path
     launch_k(conv_tc_finish_kernel, dim3((unsigned)((out_elems + 255) / 256)), dim3(256), 0, s, p);
     return check_launch("conv_tc_finish_kernel");
   }
   return DVMVS_OK;
+}
+
+// Split count dvmvs_conv2d_tc will use for this descriptor (1 = no split): lets a caller that fuses the finishing pass into its own
+// epilogue (defer_finish) size its reads.  Mirrors the decision above.
+extern "C" int dvmvs_conv2d_tc_ksplit(const dvmvs_conv_tc_desc* d) {
+  if (!d || !(d->ksize == 1 || d->ksize == 3 || d->ksize == 5) || d->B <= 0) return 1;
+  static const bool alt_env = []() {
+    const char* a = getenv("DVMVS_CLUSTER_SPLITK");
+    const char* b = getenv("DVMVS_SPLITK_FUSED");
+    return (a && a[0] == '1') || (b && b[0] == '1');
+  }();
+  if (alt_env) return 1;                         // the experimental reductions finish inside the kernel
+  const int pad = (d->ksize - 1) / 2;
+  const int Hout = (d->Hin + 2 * pad - d->ksize) / d->stride + 1, Wout = (d->Win + 2 * pad - d->ksize) / d->stride + 1;
+  const int tile_w = (Wout <= 8 && Hout > 8) ? 8 : 16, tile_h = kTileM / tile_w;
+  const int tiles = ((Wout + tile_w - 1) / tile_w) * ((Hout + tile_h - 1) / tile_h);
+  const int n_tiles = (d->Cout + d->block_n - 1) / d->block_n;
+  const int ctas = tiles * d->B * n_tiles;
+  const int n_taps = d->ksize * d->ksize;
+  const long long counter_bytes = 16384;
+  const size_t out_elems = (size_t)d->B * Hout * Wout * d->Cout;
+  int ksplit = 1;
+  if (d->allow_split && d->workspace && d->workspace_bytes > counter_bytes && ctas < 74 && n_taps > 1) {
+    long long fit = (d->workspace_bytes - counter_bytes) / (long long)(out_elems * sizeof(float));
+    ksplit = (int)max(1LL, min((long long)min(n_taps, (148 + ctas - 1) / ctas), fit));
+    const int per = (n_taps + ksplit - 1) / ksplit;
+    ksplit = (n_taps + per - 1) / per;
+  }
+  return ksplit;
 }
 
 extern "C" int dvmvs_split_planes(const float* x, void* planes, int B, int H, int W, int C, int Cs, int upsample2x, int c_offset,

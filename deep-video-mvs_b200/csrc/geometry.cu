@@ -804,7 +804,7 @@ __global__ void depth_reproject_kernel(const float* __restrict__ cur_pose, const
 
 using namespace dvmvs;
 
-extern "C" int dvmvs_abi_version(void) { return 4; }
+extern "C" int dvmvs_abi_version(void) { return 5; }
 
 // Programmatic dependent launch for the launches that follow (process-wide): 1 on, 0 off, -1 back to the default
 // (on unless DVMVS_PDL=0).  What a launch was enqueued / captured with stays with it.
@@ -872,11 +872,10 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
   if (fast) {
     const int tiles = B * h * ((w + kPix - 1) / kPix);
     const size_t smem = (size_t)(kPix * 32 + M * D * 4 + kMaxMeas * 12 + kPix * D) * sizeof(float) + 2 * kGroup * kPix * sizeof(SweepTapParams);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
       cudaFuncSetAttribute(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       cudaFuncSetAttribute(plane_sweep_c32_kernel<DVMVS_SWEEP_SAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      attr_set = true;
     }
     DVMVS_REQUIRE(smem <= 96 * 1024, "plane_sweep: shared memory %zu too large", smem);
     // DVMVS_SWEEP_CTAS_PER_SM=n (1..3) pads the dynamic shared memory so that at most n CTAs of this kernel share an SM
@@ -890,11 +889,10 @@ extern "C" int dvmvs_plane_sweep_fused(const float* ref, const float* const* mea
     }
     static const int minb = []() { const char* e = getenv("DVMVS_SWEEP_MINB"); return e ? atoi(e) : 4; }();
     if (mode == DVMVS_SWEEP_DOT && (minb == 2 || minb == 3)) {
-      static bool attr2 = false;
-      if (!attr2) {
+      static PerDeviceOnce attr2;
+      if (attr2.first()) {
         cudaFuncSetAttribute(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr2 = true;
       }
       if (minb == 2) launch_k(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT, 2>, dim3(tiles), dim3(kSweepThreads), smem_launch, s, p);
       else launch_k(plane_sweep_c32_kernel<DVMVS_SWEEP_DOT, 3>, dim3(tiles), dim3(kSweepThreads), smem_launch, s, p);
@@ -936,10 +934,9 @@ extern "C" int dvmvs_plane_sweep_fused_h16(const float* ref, const void* const* 
   p.prefetch = 0;
   const int tiles = B * h * ((w + kPix - 1) / kPix);
   const size_t smem = (size_t)(kPix * 32 + M * D * 4 + kMaxMeas * 12 + kPix * D) * sizeof(float) + 2 * kGroup * kPix * sizeof(SweepPairParams);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     cudaFuncSetAttribute(plane_sweep_c32_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
   }
   DVMVS_REQUIRE(smem <= 96 * 1024, "plane_sweep_h16: shared memory %zu too large", smem);
   launch_k(plane_sweep_c32_h16_kernel, dim3(tiles), dim3(kSweepThreads), smem, (cudaStream_t)stream, p);
@@ -992,10 +989,9 @@ extern "C" int dvmvs_plane_sweep_backward(const float* ref, const float* const* 
   }
   const int tiles = B * h * ((w + kPix - 1) / kPix);
   const size_t smem = (size_t)(kPix * 32 + M * D * 4 + kMaxMeas * 12 + kPix * D) * sizeof(float) + kGroup * kPix * sizeof(SweepTapParams);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     cudaFuncSetAttribute(plane_sweep_backward_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
   }
   DVMVS_REQUIRE(smem <= 96 * 1024, "plane_sweep_backward: shared memory %zu too large", smem);
   launch_k(plane_sweep_backward_c32_kernel, dim3(tiles), dim3(kSweepThreads), smem, s, q);

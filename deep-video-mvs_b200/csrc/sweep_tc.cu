@@ -41,7 +41,6 @@
 #include <string.h>
 
 #include <mutex>
-#include <unordered_map>
 
 #include "tc_ptx.cuh"
 
@@ -51,7 +50,7 @@ constexpr int kStTileW = 16, kStTileH = 4, kStPix = kStTileW * kStTileH;     // 
 constexpr int kStConsumers = 512;       // warps 0..15: TMEM -> shared copy + look-ups
 constexpr int kStThreads = kStConsumers + 32;     // warp 16: planner + TMA producer + MMA issuer
 constexpr int kStRows = 64;             // band rows per chunk (circular slots: slot = y & 63)
-constexpr int kStBox = 32;              // band pixels per TMA box (one box = 32 rows of 64 B = four SWIZZLE_64B atoms)
+constexpr int kStBox = 32;              // band rows are fetched in runs of 32 pixels (2 KB, four SWIZZLE_64B atoms)
 constexpr int kStMaxMeas = 8;
 constexpr int kStMaxPlanes = 128;
 constexpr int kStMaxMD = 512;           // M * D (homography tables in shared memory)
@@ -69,7 +68,7 @@ struct StCfg {
 
 struct SweepTcParams {
   CUtensorMap ref_map[2];               // fp16 planes [B][h][w][32]: hi, lo; box {32, 16, 4, 1}
-  CUtensorMap meas_map[kStMaxMeas][2];  // box {32, 32, 1, 1}
+  CUtensorMap meas_map[kStMaxMeas][2];  // box {32, 32, 1, 1}: one 32-pixel run of a band row
   const __half* meas_planes[kStMaxMeas][2];   // raw pointers for the direct (fallback) path
   const __half* ref_planes[2];
   const float* pose2[kStMaxMeas];
@@ -80,9 +79,12 @@ struct SweepTcParams {
   int tiles_x, tiles_y;
   int qcap;                             // band capacity in pixels (multiple of 32)
   float depth[kStMaxPlanes];            // plane depths, computed on the host in double like the reference (utils.py:59-66)
+  long long* timeline;                  // development aid (tools/sweep_timeline.py): clock64 stamps of the first CTAs' phases, or null
 };
 
-// same algebra as geometry.cu sweep_matrices (utils.py:51-56): G = K R K^-1, Kt = K t
+// same algebra as geometry.cu sweep_matrices (utils.py:51-56): G = K R K^-1, Kt = K t.  The inverses are evaluated in double
+// (common.cuh): an fp32 cofactor inverse moves the sampling positions by ~1e-4 px, which the 2e-5 parity bound of the 3-term
+// mode does not admit (measured: golden test fails)
 __device__ __forceinline__ void st_matrices(const float* pose1, const float* pose2, const float* K, float* G, float* Kt) {
   float inv2[16], E[16];
   mat4_rigid_free_inverse(pose2, inv2);
@@ -98,19 +100,22 @@ __device__ __forceinline__ void st_matrices(const float* pose1, const float* pos
 }
 
 constexpr int kStMaxChunks = 48;
+constexpr int kStMaxRuns = 32;          // 1024 band pixels / 32
+constexpr int kStPlanGroup = 8;         // chunks verified at a time
 struct StChunk {         // one chunk of consecutive planes of one frame, planned in the prologue
-  short m, d0, nd, band, total_q, ylo;
+  short m, d0, nd, band, total_q, next_band;       // next_band: index of the next chunk with a band (or -1)
   short row_q[kStRows];            // q index of pixel x on the band row in slot (y & 63) = row_q + x
-  short xmn[kStRows];              // first band pixel of the row
-  unsigned char nb[kStRows];       // 32-pixel boxes of the row
+  short run_x[kStMaxRuns];         // band pixels [32 i, 32 i + 32) are the pixels x = run_x[i] .. + 31 of image row run_y[i]
+  short run_y[kStMaxRuns];
 };
 
 struct StSmem {          // fixed-size bookkeeping behind the big arrays
   float G[kStMaxMeas][12];
   StChunk chunk[kStMaxChunks];
-  int frame_n[kStMaxMeas], frame_fail[kStMaxMeas];
-  int n_chunks, any_fail;
-  unsigned long long bar_ref, bar_band, bar_mma, bar_tmem_empty;
+  int frame_n[kStMaxMeas], frame_fail[kStMaxMeas], frame_stuck[kStMaxMeas];
+  int plan[kStPlanGroup][2 * kStRows + 4];        // chunk verification scratch: row xmin[64], xmax[64], ylo, yhi, degenerate
+  int n_chunks, any_fail, first_band;
+  unsigned long long bar_ref, bar_go, bar_mma, bar_band;
   uint32_t tmem_slot;
 };
 
@@ -158,17 +163,23 @@ __device__ __forceinline__ float st_direct_sample(const SweepTcParams& p, int m,
 // estimated band pixels of a chunk of n planes: rows x 32-pixel boxes per row, from the displacement (dx, dy) of the tile
 // centre per plane.  Only a first guess -- the planner verifies the real band and halves the chunk when it does not fit.
 __device__ __forceinline__ float st_band_estimate(float n, float dx, float dy) {
-  const float rows = (float)(kStTileH + 3) + dy * n;
-  const float planes_per_row = fminf(n, (float)(kStTileH + 3) / fmaxf(dy, 1e-6f));
-  const float width = (float)(kStTileW + 3) + dx * planes_per_row;
+  const float rows = (float)(kStTileH + 2) + dy * n;
+  const float planes_per_row = fminf(n, (float)(kStTileH + 2) / fmaxf(dy, 1e-6f));
+  const float width = (float)(kStTileW + 1) + dx * planes_per_row;
   return rows * (float)kStBox * ceilf(width * (1.f / kStBox));
 }
+
+#define ST_STAMP(slot)                                                                                   \
+  do {                                                                                                   \
+    if (p.timeline && blockIdx.x < 8 && (threadIdx.x == 0)) p.timeline[blockIdx.x * 64 + (slot)] = clock64(); \
+  } while (0)
 
 template <int TERMS>
 __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __grid_constant__ SweepTcParams p) {
   using Cfg = StCfg<TERMS>;
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
+  ST_STAMP(0);
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_addr);
@@ -190,15 +201,15 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
   const int v0 = (t_in / p.tiles_x) * kStTileH, u0 = (t_in % p.tiles_x) * kStTileW;
   const int tw = min(kStTileW, p.w - u0), th = min(kStTileH, p.h - v0);      // valid extent of this tile
 
-  const uint32_t bar_ref = smem_u32(&sm->bar_ref), bar_band = smem_u32(&sm->bar_band), bar_mma = smem_u32(&sm->bar_mma);
-  const uint32_t bar_tmem_empty = smem_u32(&sm->bar_tmem_empty);
+  const uint32_t bar_ref = smem_u32(&sm->bar_ref), bar_go = smem_u32(&sm->bar_go), bar_mma = smem_u32(&sm->bar_mma);
+  const uint32_t bar_band = smem_u32(&sm->bar_band);
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.ref_map[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.meas_map[0][0]) : "memory");
-    mbar_init(bar_ref, 1);
     mbar_init(bar_band, 1);
+    mbar_init(bar_ref, 1);
+    mbar_init(bar_go, 1);
     mbar_init(bar_mma, 1);
-    mbar_init(bar_tmem_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (producer) {
@@ -207,12 +218,13 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();            // barrier objects initialised (thread 0) before anybody arms them; TMEM address published
   tc_fence_after();
-  const uint32_t tmem_base = sm->tmem_slot;
+  ST_STAMP(1);
   pdl_wait();
+  ST_STAMP(2);
 
-  // ---- reference tile (B operand) by TMA; pose algebra and per-plane geometry of ALL frames meanwhile (one pass, all threads)
+  // ---- reference tile (B operand) by TMA; pose algebra meanwhile
   if (producer && lane == 0) {
     mbar_expect_tx(bar_ref, (TERMS == 3 ? 2u : 1u) * kStPix * 64u);
     tma_load_4d(ref_addr, &p.ref_map[0], bar_ref, 0, u0, v0, b);
@@ -227,148 +239,204 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
     for (int i = 0; i < 3; ++i) sm->G[tid][9 + i] = Kt[i];
   }
   __syncthreads();
+  ST_STAMP(3);
+  const uint32_t tmem_base = sm->tmem_slot;
   const float sx = (float)(p.w - 1) / (float)p.w, sy = (float)(p.h - 1) / (float)p.h;      // align_corners "shrink" (App. A.1)
   const float wf = (float)p.w, hf = (float)p.h;
-  for (int i = tid; i < p.M * p.D; i += kStThreads) {
+  // ---- per-plane geometry of ALL frames: one thread per (frame, plane, tile corner), the four corners combine with shuffles
+  for (int i4 = tid; i4 < ((p.M * p.D * 4 + 31) & ~31); i4 += kStThreads) {
+    const int i = min(i4 >> 2, p.M * p.D - 1), c = i4 & 3;
     const int m = i / p.D, d = i - m * p.D;
     const float* G = sm->G[m];
     const float this_depth = p.depth[d];                                                     // utils.py:66
     const float4 kd = make_float4(G[9] / this_depth, G[10] / this_depth, G[11] / this_depth, 0.f);      // utils.py:68
-    s_kd[i] = kd;
     // bounding box of the tile's image on this plane: a homography with a denominator of one sign maps the (convex) tile
     // onto a convex quadrilateral, so the four corners bound every sample; +-1e-3 px absorbs fp32 rounding
-    float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
-    int pos = 0, neg = 0;
+    const float cu = (float)(u0 + ((c & 1) ? tw - 1 : 0)), cv = (float)(v0 + ((c >> 1) ? th - 1 : 0));
+    float xs, ys, den;
+    st_position(G, kd, cu, cv, sx, sy, wf, hf, xs, ys, den);
+    int pos = (den > 1e-6f), neg = (den < -1e-6f);
+    float xmn = xs, xmx = xs, ymn = ys, ymx = ys;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float cu = (float)(u0 + ((c & 1) ? tw - 1 : 0)), cv = (float)(v0 + ((c >> 1) ? th - 1 : 0));
-      float xs, ys, den;
-      st_position(G, kd, cu, cv, sx, sy, wf, hf, xs, ys, den);
-      pos += (den > 1e-6f);
-      neg += (den < -1e-6f);
-      xmn = fminf(xmn, xs); xmx = fmaxf(xmx, xs); ymn = fminf(ymn, ys); ymx = fmaxf(ymx, ys);
+    for (int o = 1; o < 4; o <<= 1) {
+      xmn = fminf(xmn, __shfl_xor_sync(0xffffffffu, xmn, o)); xmx = fmaxf(xmx, __shfl_xor_sync(0xffffffffu, xmx, o));
+      ymn = fminf(ymn, __shfl_xor_sync(0xffffffffu, ymn, o)); ymx = fmaxf(ymx, __shfl_xor_sync(0xffffffffu, ymx, o));
+      pos += __shfl_xor_sync(0xffffffffu, pos, o); neg += __shfl_xor_sync(0xffffffffu, neg, o);
     }
-    int4 bb;
-    bb.x = (int)floorf(xmn - 1e-3f); bb.y = (int)floorf(xmx + 1e-3f) + 1;
-    bb.z = (int)floorf(ymn - 1e-3f); bb.w = (int)floorf(ymx + 1e-3f) + 1;
-    if ((pos != 4 && neg != 4) || bb.w - bb.z >= kStRows) { bb.x = 1; bb.y = 0; }       // degenerate on this tile: direct path
-    s_box[i] = bb;
+    if (c == 0 && (i4 >> 2) < p.M * p.D) {
+      int4 bb;
+      bb.x = (int)floorf(xmn - 1e-3f); bb.y = (int)floorf(xmx + 1e-3f) + 1;
+      bb.z = (int)floorf(ymn - 1e-3f); bb.w = (int)floorf(ymx + 1e-3f) + 1;
+      if ((pos != 4 && neg != 4) || bb.w - bb.z >= kStRows) { bb.x = 1; bb.y = 0; }       // degenerate on this tile: direct path
+      s_kd[i] = kd;
+      s_box[i] = bb;
+    }
   }
-  if (tid < p.M) {
-    // first guess of the planes per chunk of frame tid from the motion of the tile centre between the first and the last plane
-    const float* G = sm->G[tid];
+  const int budget = max(1, kStMaxChunks / p.M);                  // first guess: an equal share of the chunk list per frame
+  if (warp < p.M) {
+    // first guess of the planes per chunk of frame `warp` from the motion of the tile centre between the first and the last
+    // plane: lane j tries j + 1 uniform chunks, the smallest count whose estimated band fits wins
+    const int m = warp;
+    const float* G = sm->G[m];
     const float uc = (float)u0 + 0.5f * (float)(tw - 1), vc = (float)v0 + 0.5f * (float)(th - 1);
     const float da = p.depth[0], db = p.depth[p.D - 1];
     float xa, ya, xb, yb, den;
     st_position(G, make_float4(G[9] / da, G[10] / da, G[11] / da, 0.f), uc, vc, sx, sy, wf, hf, xa, ya, den);
     st_position(G, make_float4(G[9] / db, G[10] / db, G[11] / db, 0.f), uc, vc, sx, sy, wf, hf, xb, yb, den);
     const float dx = fabsf(xb - xa) / (float)(p.D - 1), dy = fabsf(yb - ya) / (float)(p.D - 1);
-    // uniform chunks: the smallest number of chunks whose estimated band fits, within this frame's share of the chunk list
-    const int budget = max(1, kStMaxChunks / p.M);
-    int nch = 1;
-    while (nch < budget && st_band_estimate((float)((p.D + nch - 1) / nch), dx, dy) * 1.05f > (float)p.qcap) ++nch;
-    sm->frame_n[tid] = (p.D + nch - 1) / nch;
-    sm->frame_fail[tid] = 0;
+    const int nch_try = lane + 1;
+    const int n_try = (p.D + nch_try - 1) / nch_try;
+    const bool ok = nch_try >= budget || st_band_estimate((float)n_try, dx, dy) <= (float)p.qcap;
+    const unsigned fits_mask = __ballot_sync(0xffffffffu, ok);
+    const int nch = fits_mask ? __ffs(fits_mask) : min(budget, 32);
+    if (lane == 0) {
+      sm->frame_n[m] = (p.D + nch - 1) / nch;
+      sm->frame_fail[m] = 0;
+      sm->frame_stuck[m] = 0;
+    }
   }
+  if (tid == 0) sm->any_fail = 0;
   __syncthreads();
-  // ---- chunk plan: uniform chunks per frame, every chunk verified against the real per-plane boxes by one warp (lanes own
-  // the 64 circular row slots); a frame with a chunk that does not fit is re-planned with shorter chunks as long as its
-  // share of the chunk list allows -- what still does not fit then takes the direct path
-  const int min_n = (p.D + max(1, kStMaxChunks / p.M) - 1) / max(1, kStMaxChunks / p.M);
-  for (int round = 0; round < 10; ++round) {
-    if (tid == 0) {
-      int cnt = 0;
-      for (int m = 0; m < p.M; ++m) {
-        const int n = sm->frame_n[m];
-        for (int d0 = 0; d0 < p.D && cnt < kStMaxChunks; d0 += n) {
-          StChunk* ch = &sm->chunk[cnt++];
-          ch->m = (short)m; ch->d0 = (short)d0; ch->nd = (short)min(n, p.D - d0);
+  ST_STAMP(4);
+  // ---- chunk plan: uniform chunks per frame, every chunk verified against the real per-plane boxes: one thread per
+  // (chunk, plane) merges the plane's box into the chunk's 64 circular row slots (slot = y & 63) with shared-memory atomics,
+  // then one warp per chunk turns the rows into 32-pixel runs (prefix sum).  A frame with a chunk that does not fit is
+  // re-planned with shorter chunks as long as its share of the chunk list allows -- what still does not fit then takes the
+  // direct path.
+  int plan_rounds = 0;
+  while (true) {              // terminates: a failing frame strictly shortens its chunks until it is stuck, where nothing is flagged any more
+    ++plan_rounds;
+    int n_chunks = 0;
+    for (int m = 0; m < p.M; ++m) n_chunks += (p.D + sm->frame_n[m] - 1) / sm->frame_n[m];
+    for (int k0 = 0; k0 < n_chunks; k0 += kStPlanGroup) {
+      const int ng = min(kStPlanGroup, n_chunks - k0);
+      for (int i = tid; i < ng * (2 * kStRows + 4); i += kStThreads) {
+        const int j = i % (2 * kStRows + 4);
+        sm->plan[i / (2 * kStRows + 4)][j] = (j < kStRows || j == 2 * kStRows) ? INT_MAX : ((j == 2 * kStRows + 2) ? 0 : INT_MIN);
+      }
+      __syncthreads();
+      if (plan_rounds == 1 && k0 == 0) ST_STAMP(56);
+      for (int i = tid; i < ng * kStMaxPlanes; i += kStThreads) {
+        const int g = i / kStMaxPlanes, dd = i - g * kStMaxPlanes, k = k0 + g;
+        int m = 0, kk = k;
+        for (; m < p.M; ++m) {
+          const int c = (p.D + sm->frame_n[m] - 1) / sm->frame_n[m];
+          if (kk < c) break;
+          kk -= c;
+        }
+        const int n = sm->frame_n[m], d0 = kk * n, nd = min(n, p.D - d0);
+        if (dd >= nd) continue;
+        const int4 bb = s_box[m * p.D + d0 + dd];
+        int* pl_ = sm->plan[g];
+        if (bb.x > bb.y) { pl_[2 * kStRows + 2] = 1; continue; }       // degenerate plane in this chunk
+        atomicMin(&pl_[2 * kStRows], bb.z);
+        atomicMax(&pl_[2 * kStRows + 1], bb.w);
+        for (int y = bb.z; y <= bb.w; ++y) {
+          atomicMin(&pl_[y & (kStRows - 1)], bb.x);
+          atomicMax(&pl_[kStRows + (y & (kStRows - 1))], bb.y);
         }
       }
-      sm->n_chunks = cnt;
+      __syncthreads();
+      if (plan_rounds == 1 && k0 == 0) ST_STAMP(57);
+      if (warp < ng) {
+        const int k = k0 + warp;
+        int m = 0, kk = k;
+        for (; m < p.M; ++m) {
+          const int c = (p.D + sm->frame_n[m] - 1) / sm->frame_n[m];
+          if (kk < c) break;
+          kk -= c;
+        }
+        const int n = sm->frame_n[m], d0 = kk * n, nd = min(n, p.D - d0);
+        const int* pl_ = sm->plan[warp];
+        StChunk* ch = &sm->chunk[k];
+        const int xmn0 = pl_[2 * lane], xmx0 = pl_[kStRows + 2 * lane], xmn1 = pl_[2 * lane + 1], xmx1 = pl_[kStRows + 2 * lane + 1];
+        const int ylo = pl_[2 * kStRows], yhi = pl_[2 * kStRows + 1], degenerate = pl_[2 * kStRows + 2];
+        const int n0 = (!degenerate && xmx0 >= xmn0) ? (xmx0 - xmn0 + kStBox) / kStBox : 0;
+        const int n1 = (!degenerate && xmx1 >= xmn1) ? (xmx1 - xmn1 + kStBox) / kStBox : 0;
+        int incl = n0 + n1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int total_q = __shfl_sync(0xffffffffu, incl, 31) * kStBox;
+        const int r0 = incl - n0 - n1, r1 = r0 + n0;              // first 32-pixel run of the two rows
+        const bool fits = !degenerate && yhi - ylo + 1 <= kStRows && total_q <= p.qcap && total_q > 0;
+        if (fits) {
+          ch->row_q[2 * lane] = (short)(n0 ? r0 * kStBox - xmn0 : 0);
+          ch->row_q[2 * lane + 1] = (short)(n1 ? r1 * kStBox - xmn1 : 0);
+          const int y0 = ylo + ((2 * lane - ylo) & (kStRows - 1)), y1 = ylo + ((2 * lane + 1 - ylo) & (kStRows - 1));
+          for (int j = 0; j < n0; ++j) { ch->run_x[r0 + j] = (short)(xmn0 + kStBox * j); ch->run_y[r0 + j] = (short)y0; }
+          for (int j = 0; j < n1; ++j) { ch->run_x[r1 + j] = (short)(xmn1 + kStBox * j); ch->run_y[r1 + j] = (short)y1; }
+        }
+        if (lane == 0) {
+          ch->m = (short)m; ch->d0 = (short)d0; ch->nd = (short)nd;
+          ch->band = fits ? 1 : 0;
+          ch->total_q = (short)(fits ? total_q : 0);
+          if (!fits && !degenerate && !sm->frame_stuck[m] && nd > 1) { sm->frame_fail[m] = 1; sm->any_fail = 1; }      // shorter chunks may fit
+        }
+      }
+      __syncthreads();
+      if (plan_rounds == 1 && k0 == 0) ST_STAMP(58);
+    }
+    const int any_fail = sm->any_fail;
+    if (!any_fail) {
+      if (tid == 0) {          // link the band chunks
+        int next = -1;
+        for (int k = n_chunks - 1; k >= 0; --k) {
+          sm->chunk[k].next_band = (short)next;
+          if (sm->chunk[k].band) next = k;
+        }
+        sm->first_band = next;
+        sm->n_chunks = n_chunks;
+      }
+      break;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // shorten the chunks of the failing frames while the chunk list has room (frames share it); a frame that cannot
+      // shrink any further is stuck: its chunks that do not fit take the direct path
+      for (int m = 0; m < p.M; ++m) {
+        if (!sm->frame_fail[m]) continue;
+        sm->frame_fail[m] = 0;
+        const int n_new = max(1, (sm->frame_n[m] * 3) >> 2);
+        int total = 0;
+        for (int j = 0; j < p.M; ++j) { const int nj = (j == m) ? n_new : sm->frame_n[j]; total += (p.D + nj - 1) / nj; }
+        if (n_new < sm->frame_n[m] && total <= kStMaxChunks) sm->frame_n[m] = n_new;
+        else sm->frame_stuck[m] = 1;
+      }
       sm->any_fail = 0;
     }
     __syncthreads();
-    for (int k = warp; k < sm->n_chunks; k += kStThreads / 32) {
-      StChunk* ch = &sm->chunk[k];
-      const int m = ch->m, d0 = ch->d0, nd = ch->nd;
-      int xmn0 = INT_MAX, xmx0 = INT_MIN, xmn1 = INT_MAX, xmx1 = INT_MIN, ylo = INT_MAX, yhi = INT_MIN, degenerate = 0;
-#pragma unroll 4
-      for (int d = d0; d < d0 + nd; ++d) {
-        const int4 bb = s_box[m * p.D + d];
-        degenerate |= (bb.x > bb.y);
-        ylo = min(ylo, bb.z); yhi = max(yhi, bb.w);
-        const int span = bb.w - bb.z;
-        if (((2 * lane - bb.z) & (kStRows - 1)) <= span) { xmn0 = min(xmn0, bb.x); xmx0 = max(xmx0, bb.y); }
-        if (((2 * lane + 1 - bb.z) & (kStRows - 1)) <= span) { xmn1 = min(xmn1, bb.x); xmx1 = max(xmx1, bb.y); }
-      }
-      const int n0 = (!degenerate && xmx0 >= xmn0) ? (xmx0 - xmn0 + kStBox) / kStBox : 0;
-      const int n1 = (!degenerate && xmx1 >= xmn1) ? (xmx1 - xmn1 + kStBox) / kStBox : 0;
-      int incl = n0 + n1;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const int total_q = __shfl_sync(0xffffffffu, incl, 31) * kStBox;
-      const int q0 = (incl - n0 - n1) * kStBox, q1 = q0 + n0 * kStBox;
-      const bool fits = !degenerate && yhi - ylo + 1 <= kStRows && total_q <= p.qcap && total_q > 0;
-      if (fits) {
-        ch->row_q[2 * lane] = (short)(n0 ? q0 - xmn0 : 0);
-        ch->row_q[2 * lane + 1] = (short)(n1 ? q1 - xmn1 : 0);
-        ch->xmn[2 * lane] = (short)(n0 ? xmn0 : 0);
-        ch->xmn[2 * lane + 1] = (short)(n1 ? xmn1 : 0);
-        ch->nb[2 * lane] = (unsigned char)n0;
-        ch->nb[2 * lane + 1] = (unsigned char)n1;
-      }
-      if (lane == 0) {
-        ch->band = fits ? 1 : 0;
-        ch->total_q = (short)(fits ? total_q : 0);
-        ch->ylo = (short)(fits ? ylo : 0);
-        if (!fits && !degenerate && sm->frame_n[m] > min_n && nd > 1) { sm->frame_fail[m] = 1; sm->any_fail = 1; }      // shorter chunks may fit
-      }
-    }
-    __syncthreads();
-    if (!sm->any_fail) break;
-    __syncthreads();
-    if (tid < p.M && sm->frame_fail[tid]) {
-      sm->frame_n[tid] = max(min_n, (sm->frame_n[tid] * 3) >> 2);
-      sm->frame_fail[tid] = 0;
-    }
-    __syncthreads();
   }
+  __syncthreads();
+  ST_STAMP(5);
+  if (p.timeline && blockIdx.x < 8 && tid == 0) p.timeline[blockIdx.x * 64 + 59] = p.timeline[blockIdx.x * 64 + 0] + plan_rounds * 1000 + sm->n_chunks;
   const int n_chunks = sm->n_chunks;
 
   if (producer) {
-    // =============================== TMA producer + MMA issuer (one warp), one chunk ahead of the consumers ===============================
+    // =============================== TMA producer + MMA issuer: S = band . tile^T, one band chunk ahead of the look-ups ===============================
     const uint32_t hi_word = umma_hi_word(512u, 4u);                   // SBO = 8 rows x 64 B, SWIZZLE_64B
     const uint32_t idesc = (1u << 4) | ((uint32_t)(kStPix >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f32 += f16 x f16, K-major, N=64, M=128
     const uint32_t b_hi = umma_lo_word(ref_addr, 16), b_lo = umma_lo_word(ref_addr + kStPix * 64, 16);
     int n_band = 0;
-    for (int k = 0; k < n_chunks; ++k) {
+    for (int k = sm->first_band; k >= 0; k = sm->chunk[k].next_band) {
       const StChunk* ch = &sm->chunk[k];
-      if (ch->band != 1) continue;                                     // direct chunk: nothing to stage
-      const int m = ch->m, total_q = ch->total_q, ylo = ch->ylo;
-      // ---- band rows -> shared memory by TMA (the previous band chunk's MMAs must have consumed the band buffer)
+      const int total_q = ch->total_q, m = ch->m;
+      // ---- band rows -> shared memory by TMA, 2 KB runs; pixels outside the image are zero-filled by the TMA unit.  The band
+      // buffer is free as soon as the previous band chunk's MMAs have completed, i.e. before its look-ups even start.
       if (n_band > 0) mbar_wait(bar_mma, (uint32_t)((n_band - 1) & 1));
       if (lane == 0) mbar_expect_tx(bar_band, (uint32_t)total_q * (uint32_t)Cfg::kBandBytesPerQ);
       __syncwarp();
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int slot_r = 2 * lane + e;
-        const int nb = ch->nb[slot_r], xmn = ch->xmn[slot_r], qs = ch->row_q[slot_r] + xmn;
-        const int y = ylo + ((slot_r - ylo) & (kStRows - 1));
-        for (int j = 0; j < nb; ++j) {
-          const uint32_t dst = band_addr + (uint32_t)(qs + kStBox * j) * 64u;
-          tma_load_4d(dst, &p.meas_map[m][0], bar_band, 0, xmn + kStBox * j, y, b);
-          if (TERMS == 3) tma_load_4d(dst + (uint32_t)p.qcap * 64u, &p.meas_map[m][1], bar_band, 0, xmn + kStBox * j, y, b);
-        }
+      for (int run = lane; run * kStBox < total_q; run += 32) {
+        const uint32_t dst = band_addr + (uint32_t)run * 2048u;
+        tma_load_4d(dst, &p.meas_map[m][0], bar_band, 0, ch->run_x[run], ch->run_y[run], b);
+        if (TERMS == 3) tma_load_4d(dst + (uint32_t)p.qcap * 64u, &p.meas_map[m][1], bar_band, 0, ch->run_x[run], ch->run_y[run], b);
       }
       if (lane == 0) {
-        // ---- S = band . tile^T on the tensor cores
-        if (n_band == 0) mbar_wait(bar_ref, 0);
         mbar_wait(bar_band, (uint32_t)(n_band & 1));
-        if (n_band > 0) mbar_wait(bar_tmem_empty, (uint32_t)((n_band - 1) & 1));      // consumers drained the previous accumulators
+        // bar_go: arrival 0 = reference tile landed and pre-scaled, arrival n = accumulators of band chunk n-1 drained
+        mbar_wait(bar_go, (uint32_t)(n_band & 1));
         tc_fence_after();
         const int n_mt = (total_q + 127) >> 7;
         for (int mt = 0; mt < n_mt; ++mt) {
@@ -390,7 +458,7 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
       __syncwarp();
     }
   } else {
-    // =============================== consumers: TMEM -> S[q][p], then one thread per (pixel, plane) ===============================
+    // =============================== consumers: band rows -> smem (cp.async), TMEM -> S[q][p], look-ups ===============================
     const int pl = tid & (kStPix - 1);                 // pixel of this thread; planes d0 + (tid >> 6), + 8, ...
     const int pty = pl >> 4, ptx = pl & 15;
     const bool pix_valid = (ptx < tw) && (pty < th);
@@ -399,6 +467,21 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
     int n_band = 0, cur_m = -1;
     float b0 = 0.f, b1 = 0.f, b2 = 0.f;
     bool ref_ready = false;
+
+    // ---- the reference tile arrives by TMA.  1-term mode folds the 1/C of the dot-product cost (utils.py:82) into it: 2^-5 is exact
+    // in fp16 (features below 2e-3 go subnormal: 1e-7 of their range), so S = band . tile^T leaves the tensor core pre-scaled and
+    // fits fp16 with 32x headroom.  The 3-term mode keeps the tile as it is (its lo plane would go subnormal) and scales the sample.
+    mbar_wait(bar_ref, 0);
+    ref_ready = true;
+    if (TERMS == 1) {
+      __half2* rt = reinterpret_cast<__half2*>(base_ptr + band_bytes);
+      const __half2 sc = __floats2half2_rn(1.f / 32.f, 1.f / 32.f);
+      for (int i = tid; i < kStPix * 16; i += kStConsumers) rt[i] = __hmul2(rt[i], sc);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> visible to the tensor core's reads
+    consumer_barrier();
+    if (tid == 0) mbar_arrive(bar_go);
+    ST_STAMP(7);
     for (int k = 0; k < n_chunks; ++k) {
       const StChunk* ch = &sm->chunk[k];
       const int m = ch->m, d0 = ch->d0, nd = ch->nd, is_band = (ch->band == 1), total_q = ch->total_q;
@@ -411,44 +494,48 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
       }
       const float4* kdm = s_kd + m * p.D;
       if (is_band) {
+        ST_STAMP(8 + 6 * min(k, 8) + 0);
         mbar_wait(bar_mma, (uint32_t)(n_band & 1));
         ++n_band;
         tc_fence_after();
+        ST_STAMP(8 + 6 * min(k, 8) + 1);
+        const int nxt = ch->next_band;
+        ST_STAMP(8 + 6 * min(k, 8) + 2);
         // ---- TMEM lane = band pixel q, column = tile pixel p  ->  row q of S (all look-ups of the previous chunk are done:
         // consumer barrier at the end of the loop body)
         const int n_mt = (total_q + 127) >> 7;
         for (int mt = warp >> 2; mt < n_mt; mt += kStConsumers / 128) {
           const int q = mt * 128 + wq * 32 + lane;
+          float vals[64];
+          tmem_ld64(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * kStPix), vals);
+          if (q < total_q) {
+            if (TERMS == 1) {
+              uint4* dst = reinterpret_cast<uint4*>(S + (size_t)q * Cfg::kSPitchBytes);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float vals[32];
-            tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * kStPix + half * 32), vals);
-            if (q < total_q) {
-              if (TERMS == 1) {
-                uint4* dst = reinterpret_cast<uint4*>(S + (size_t)q * Cfg::kSPitchBytes + half * 64);
+              for (int j = 0; j < 8; ++j) {
+                __half2 h[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  __half2 h[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(vals[8 * j + 2 * e] * (1.f / 32.f), vals[8 * j + 2 * e + 1] * (1.f / 32.f));
-                  dst[j] = *reinterpret_cast<const uint4*>(h);
-                }
-              } else {
-                float4* dst = reinterpret_cast<float4*>(S + (size_t)q * Cfg::kSPitchBytes + half * 128);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(vals[8 * j + 2 * e], vals[8 * j + 2 * e + 1]);
+                dst[j] = *reinterpret_cast<const uint4*>(h);
               }
+            } else {
+              float4* dst = reinterpret_cast<float4*>(S + (size_t)q * Cfg::kSPitchBytes);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dst[j] = make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
             }
           }
         }
+        // accumulators drained (+ next band landed): the MMAs of the next band chunk run under this chunk's look-ups
+        ST_STAMP(8 + 6 * min(k, 8) + 3);
         tc_fence_before();
         consumer_barrier();
-        if (tid == 0) mbar_arrive(bar_tmem_empty);         // the producer may overwrite the accumulators
+        if (nxt >= 0 && tid == 0) mbar_arrive(bar_go);      // the next band chunk's MMAs may overwrite the accumulators
+        ST_STAMP(8 + 6 * min(k, 8) + 4);
         // ---- look-ups: four scalars per sample, no bounds tests (clamped positions, zero-filled band)
         if (pix_valid) {
           const short* row_q = ch->row_q;
           const int qmax = total_q - 2;
-#pragma unroll 2
+#pragma unroll 4
           for (int d = d0 + (tid >> 6); d < d0 + nd; d += kStConsumers / kStPix) {
             const float4 kd = kdm[d];
             const float q0 = b0 + kd.x, q1 = b1 + kd.y, q2 = b2 + kd.z;
@@ -470,14 +557,13 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
               s00 = sa[0]; s01 = sa[Cfg::kSPitchBytes / 4]; s10 = sb[0]; s11 = sb[Cfg::kSPitchBytes / 4];
             }
             float val = fmaf(s11, fx * fy, fmaf(s10, gx * fy, fmaf(s01, fx * gy, s00 * (gx * gy))));
-            if (TERMS == 3) val *= (1.f / 32.f);                          // utils.py:82 (/C); the fp16 S is stored pre-scaled
+            if (TERMS == 3) val *= (1.f / 32.f);                          // utils.py:82 (/C); at 1 term the reference tile is pre-scaled
             float* a = acc + d * kStAccPitch + pl;
             *a = (m == 0) ? val : *a + val;                               // summed over the measurement frames (utils.py:102)
           }
         }
       } else {
         // ---- direct path for these planes (band does not fit, or the homography is degenerate on the tile)
-        if (!ref_ready) { mbar_wait(bar_ref, 0); ref_ready = true; }
         if (pix_valid) {
           float f1[32];
           const size_t roff = (((size_t)b * p.h + v0 + pty) * p.w + u0 + ptx) * 32;
@@ -498,18 +584,26 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
         }
       }
       consumer_barrier();                                  // S is free again
+      ST_STAMP(8 + 6 * min(k, 8) + 5);
     }
     // ---- coalesced write-out: rows of the tile are contiguous [tw][D] spans of the channel-last cost volume
-    for (int ty = 0; ty < th; ++ty) {
-      float* o = p.out + (((size_t)b * p.h + v0 + ty) * p.w + u0) * p.D;
-      for (int i = tid; i < tw * p.D; i += kStConsumers) {
-        const int tx = i / p.D, d = i - tx * p.D;
-        o[i] = acc[d * kStAccPitch + ty * kStTileW + tx] / (float)p.M;      // utils.py:105-106
+    const bool pow2 = (p.M & (p.M - 1)) == 0;
+    const float m_f = (float)p.M, m_inv = 1.f / (float)p.M;             // x * (1/M) == x / M exactly when M is a power of two
+    for (int px = warp; px < th * kStTileW; px += kStConsumers / 32) {   // one warp per pixel: D consecutive floats
+      const int py = px >> 4, pxx = px & 15;
+      if (pxx >= tw) continue;
+      float* o = p.out + (((size_t)b * p.h + v0 + py) * p.w + u0 + pxx) * p.D;
+      const float* a = acc + px;
+      for (int d = lane; d < p.D; d += 32) {
+        const float v = a[d * kStAccPitch];
+        o[d] = pow2 ? v * m_inv : v / m_f;                                 // utils.py:105-106
       }
     }
   }
+  ST_STAMP(62);
   tc_fence_before();
   __syncthreads();
+  ST_STAMP(63);
   if (producer) {
     __syncwarp();
     tc_fence_after();
@@ -518,47 +612,30 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
 }
 
 // ----------------------------------------------------------------------------------------------- host side
-// Encoded tensor maps are cached per (pointer, shape, box): cuTensorMapEncodeTiled costs a few microseconds per map and a
-// sweep needs 2 (M + 1) of them; inside CUDA graphs the cost disappears, on the eager module path it is most of the call.
-struct MapKey {
-  const void* ptr;
-  int B, h, w, bw, bh;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && B == o.B && h == o.h && w == o.w && bw == o.bw && bh == o.bh; }
-};
-struct MapKeyHash {
-  size_t operator()(const MapKey& k) const {
-    size_t x = (size_t)k.ptr;
-    x ^= ((size_t)k.B * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.h << 20) ^ ((size_t)k.w << 36) ^ ((size_t)k.bw << 52) ^ ((size_t)k.bh << 58);
-    return x;
-  }
-};
-static std::mutex g_map_mutex;
-static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
-
 static int feature_map(CUtensorMap* out, const void* ptr, int B, int h, int w, int box_w, int box_h) {
-  MapKey key{ptr, B, h, w, box_w, box_h};
-  std::lock_guard<std::mutex> lock(g_map_mutex);
-  auto it = g_map_cache.find(key);
-  if (it != g_map_cache.end()) { *out = it->second; return DVMVS_OK; }
   cuuint64_t dims[4] = {32, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
   cuuint64_t strides[3] = {64, (cuuint64_t)w * 64, (cuuint64_t)h * w * 64};
   cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = tensor_map_encoder()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = cached_tensor_map(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   if (r != CUDA_SUCCESS) {
     set_error("plane_sweep_tc: cuTensorMapEncodeTiled(B=%d h=%d w=%d box=%dx%d) failed: %d", B, h, w, box_w, box_h, (int)r);
     return DVMVS_EINVAL;
   }
-  if (g_map_cache.size() > 4096) g_map_cache.clear();
-  g_map_cache.emplace(key, *out);
   return DVMVS_OK;
 }
 
 }  // namespace dvmvs
 
 using namespace dvmvs;
+
+static long long* g_timeline = nullptr;
+// development aid: device buffer of 8 x 64 long long that the next plane_sweep_tc launches fill with clock64 stamps (null: off)
+extern "C" int dvmvs_plane_sweep_tc_set_timeline(void* device_buffer) {
+  g_timeline = (long long*)device_buffer;
+  return DVMVS_OK;
+}
 
 extern "C" int dvmvs_plane_sweep_tc(const void* ref_hi, const void* ref_lo, const void* const* meas_hi_host, const void* const* meas_lo_host,
                                     const float* pose1, const float* const* pose2_host, const float* K, float* cost_out, int B, int h, int w,
@@ -598,6 +675,7 @@ extern "C" int dvmvs_plane_sweep_tc(const void* ref_hi, const void* ref_lo, cons
     p.pose2[m] = pose2_host[m];
   }
   p.pose1 = pose1; p.K = K; p.out = cost_out;
+  p.timeline = g_timeline;
   p.B = B; p.h = h; p.w = w; p.D = D; p.M = M;
   p.tiles_x = (w + kStTileW - 1) / kStTileW;
   p.tiles_y = (h + kStTileH - 1) / kStTileH;
@@ -617,13 +695,10 @@ extern "C" int dvmvs_plane_sweep_tc(const void* ref_hi, const void* ref_lo, cons
   DVMVS_REQUIRE(qcap >= 2 * kStBox, "plane_sweep_tc: no shared memory left for the band (D=%d, M=%d)", D, M);
   p.qcap = qcap;
   const size_t smem = fixed + (size_t)qcap * per_q;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  static bool attr_set[64] = {false};
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     cudaFuncSetAttribute(plane_sweep_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(plane_sweep_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set[dev] = true;
   }
   const int ctas = B * p.tiles_x * p.tiles_y;
   if (terms == 3) launch_k(plane_sweep_tc_kernel<3>, dim3(ctas), dim3(kStThreads), smem, (cudaStream_t)stream, p);

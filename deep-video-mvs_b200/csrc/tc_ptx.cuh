@@ -68,6 +68,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 64 consecutive accumulator columns of this warp's 32 lanes: both 32-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
+  uint32_t r[64];
+#define DVMVS_LD32(base, off)                                                                                                        \
+  asm volatile(                                                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                                      \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+      : "=r"(r[off + 0]), "=r"(r[off + 1]), "=r"(r[off + 2]), "=r"(r[off + 3]), "=r"(r[off + 4]), "=r"(r[off + 5]), "=r"(r[off + 6]),    \
+        "=r"(r[off + 7]), "=r"(r[off + 8]), "=r"(r[off + 9]), "=r"(r[off + 10]), "=r"(r[off + 11]), "=r"(r[off + 12]), "=r"(r[off + 13]), \
+        "=r"(r[off + 14]), "=r"(r[off + 15]), "=r"(r[off + 16]), "=r"(r[off + 17]), "=r"(r[off + 18]), "=r"(r[off + 19]),                 \
+        "=r"(r[off + 20]), "=r"(r[off + 21]), "=r"(r[off + 22]), "=r"(r[off + 23]), "=r"(r[off + 24]), "=r"(r[off + 25]),                 \
+        "=r"(r[off + 26]), "=r"(r[off + 27]), "=r"(r[off + 28]), "=r"(r[off + 29]), "=r"(r[off + 30]), "=r"(r[off + 31])                  \
+      : "r"(base))
+  DVMVS_LD32(taddr, 0);
+  DVMVS_LD32(taddr + 32u, 32);
+#undef DVMVS_LD32
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- thread-block clusters: barrier, rank, distributed-shared-memory loads (split-K reduction across the CTAs of a cluster)
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
@@ -140,5 +161,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn tensor_map_encoder();     // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency)
+
+// cuTensorMapEncodeTiled behind a process-wide cache keyed by every argument (pointer, shape, strides, box, swizzle, ...):
+// weight maps always hit, activation maps hit whenever the allocator hands the same buffer back (every call inside an
+// engine's warm-up, most calls of an eager keyframe loop).  An encode costs a few microseconds, a convolution launch needs up
+// to ten of them.  Thread-safe.  Returns CUDA_SUCCESS or the driver's error.
+CUresult cached_tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* ptr, const cuuint64_t* dims,
+                           const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle,
+                           CUtensorMapL2promotion promo);
 
 }  // namespace dvmvs

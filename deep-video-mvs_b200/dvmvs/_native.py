@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdvmvs_sm100.so")
 
 c_float_p = ctypes.c_void_p
-ABI_VERSION = 4      # dvmvs_abi_version() the descriptor mirrors below were written for; bump with every descriptor / signature change
+ABI_VERSION = 5      # dvmvs_abi_version() the descriptor mirrors below were written for; bump with every descriptor / signature change
 _lib = None
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_conv2d_halo", "dvmvs_split_blocked", "dvmvs_split_planes", "dvmvs_stem_conv", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
     "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw", "dvmvs_preprocess_rgb",
     "dvmvs_plane_sweep_backward", "dvmvs_hidden_warp_backward", "dvmvs_lstm_gates_backward", "dvmvs_depth_loss_forward",
-    "dvmvs_depth_loss_backward", "dvmvs_plane_sweep_fused_h16", "dvmvs_plane_sweep_tc",
+    "dvmvs_depth_loss_backward", "dvmvs_plane_sweep_fused_h16", "dvmvs_plane_sweep_tc", "dvmvs_lstm_gates_parts", "dvmvs_conv2d_tc_ksplit", "dvmvs_plane_sweep_tc_set_timeline",
 ]
 
 
@@ -56,6 +56,7 @@ class ConvTcDesc(ctypes.Structure):
         ("ksize", ctypes.c_int), ("stride", ctypes.c_int), ("act", ctypes.c_int),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_longlong),
         ("out_blk", ctypes.c_void_p),
+        ("out_hi_only", ctypes.c_int), ("defer_finish", ctypes.c_int),
     ]
 
 
@@ -86,6 +87,7 @@ class ConvHaloDesc(ctypes.Structure):
         ("B", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cout", ctypes.c_int),
         ("ksize", ctypes.c_int), ("act", ctypes.c_int),
         ("w_cat", ctypes.c_void_p),
+        ("out_hi_only", ctypes.c_int),
     ]
 
 
@@ -107,6 +109,7 @@ def lib():
         L.dvmvs_plane_sweep_generic.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
         L.dvmvs_plane_sweep_fused_h16.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, p]
         L.dvmvs_plane_sweep_tc.argtypes = [p, p, p, p, p, p, p, p, i, i, i, i, i, f, f, i, p]
+        L.dvmvs_plane_sweep_tc_set_timeline.argtypes = [p]
         L.dvmvs_hidden_warp.argtypes = [p, p, p, p, p, p, i, i, i, i, f, p]
         L.dvmvs_depth_reproject.argtypes = [p, p, p, p, p, p, i, i, i, p]
         L.dvmvs_conv2d.argtypes = [ctypes.POINTER(ConvDesc), p]
@@ -117,6 +120,8 @@ def lib():
         L.dvmvs_stem_conv.argtypes = [p, p, p, p, i, i, i, p]
         L.dvmvs_dwconv2d.argtypes = [p, p, p, p, p, i, i, i, i, i, i, i, p]
         L.dvmvs_lstm_gates.argtypes = [p, p, p, p, i, i, i, i, p]
+        L.dvmvs_lstm_gates_parts.argtypes = [p, i, ctypes.c_longlong, p, p, p, p, i, i, i, i, p]
+        L.dvmvs_conv2d_tc_ksplit.argtypes = [ctypes.POINTER(ConvTcDesc)]
         L.dvmvs_upsample2x.argtypes = [p, p, i, i, i, i, p]
         L.dvmvs_preprocess_rgb.argtypes = [p, i, i, i, i, i, i, p, i, i, i, f, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), p]
         L.dvmvs_nchw_to_nhwc.argtypes = [p, p, i, i, i, i, p]

@@ -21,6 +21,40 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _first_tensor(args):
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            return a
+        if isinstance(a, (list, tuple)):
+            t = _first_tensor(a)
+            if t is not None:
+                return t
+        f32 = getattr(a, "f32", None)            # Act
+        if isinstance(f32, torch.Tensor):
+            return f32
+        planes = getattr(a, "planes", None)
+        if isinstance(planes, torch.Tensor):
+            return planes
+    return None
+
+
+def on_tensor_device(fn):
+    """Native calls enqueue on the CURRENT device's current stream and allocate their outputs next to their inputs: when the
+    first tensor argument lives on another CUDA device than the current one (modules built on cuda:1 in a process whose
+    current device is cuda:0), run the call under torch.cuda.device(that device) -- stream, workspace and per-device kernel
+    attributes then all belong to the device the pointers are on."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        t = None if N.DRYRUN else _first_tensor(args)
+        if t is not None and t.is_cuda and t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapped
+
+
 _WORKSPACE = {}
 WORKSPACE_BYTES = 32 << 20
 
@@ -47,6 +81,7 @@ def require_cuda_f32(t, name):
     return t
 
 
+@on_tensor_device
 def to_nhwc(x, name="input"):
     """(B,C,H,W) logical tensor -> contiguous (B,H,W,C) tensor (zero-copy when already channels_last)."""
     require_cuda_f32(x, name)
@@ -69,6 +104,7 @@ def to_api(x_nhwc):
     return x_nhwc.permute(0, 3, 1, 2)
 
 
+@on_tensor_device
 def to_nchw_contiguous(x_nhwc):
     B, H, W, C = x_nhwc.shape
     y = torch.empty((B, C, H, W), dtype=torch.float32, device=x_nhwc.device)
@@ -112,6 +148,7 @@ class PackedDepthwise:
         self.bias = shift.to(torch.float32).contiguous()
 
 
+@on_tensor_device
 def conv2d(sources, pc, residual=None, residual_mode=N.RES_NONE, aux=None):
     """sources: list of (nhwc tensor, mode) with mode SRC_DIRECT / SRC_UPSAMPLE2X (tensor at half resolution).
     Returns out (B,Hout,Wout,Cout) [, aux_out] -- aux = (mult, base) emits 1/(mult*act(y)+base) as well."""
@@ -156,6 +193,7 @@ def conv2d(sources, pc, residual=None, residual_mode=N.RES_NONE, aux=None):
     return (out, aux_out) if aux is not None else out
 
 
+@on_tensor_device
 def stem_conv(image_nchw, pc):
     """MnasNet stem on the NCHW image (contiguous) -> channel-last (B, H/2, W/2, 32)."""
     B, C, H, W = image_nchw.shape
@@ -165,6 +203,7 @@ def stem_conv(image_nchw, pc):
     return y
 
 
+@on_tensor_device
 def dwconv2d(x, pd, want_f32=True, want_planes=False):
     """Returns y (fp32) by default; with want_planes also / only the fp16-pair planes: (y or None, planes)."""
     B, H, W, C = x.shape
@@ -179,6 +218,7 @@ def dwconv2d(x, pd, want_f32=True, want_planes=False):
     return (y, planes) if want_planes else y
 
 
+@on_tensor_device
 def plane_sweep(ref_nhwc, meas_nhwc_list, pose1, pose2_list, K, min_depth, max_depth, n_depth_levels, dot_product=True,
                 force_generic=False):
     B, h, w, C = ref_nhwc.shape
@@ -203,6 +243,7 @@ def plane_sweep(ref_nhwc, meas_nhwc_list, pose1, pose2_list, K, min_depth, max_d
     return out
 
 
+@on_tensor_device
 def plane_sweep_h16(ref_nhwc, meas_h16_list, pose1, pose2_list, K, min_depth, max_depth, n_depth_levels):
     """EXPERIMENTAL (opt-in, DVMVS_SWEEP_FP16=1): the fused plane sweep gathering fp16 measurement features -- (B,h,w,32)
     float16 tensors, e.g. the hi plane of a tensor-core convolution's output; dot-product cost only."""
@@ -222,6 +263,7 @@ def plane_sweep_h16(ref_nhwc, meas_h16_list, pose1, pose2_list, K, min_depth, ma
     return out
 
 
+@on_tensor_device
 def plane_sweep_tc(ref_planes, meas_planes_list, pose1, pose2_list, K, min_depth, max_depth, n_depth_levels, terms=3, out=None):
     """The fused plane sweep in its tensor-core form (correlate the epipolar band on tcgen05, then blend four scalars per
     sample; csrc/sweep_tc.cu).  ref_planes / meas_planes_list[m]: fp16 (hi, lo) planes of the 32-channel half-resolution
@@ -263,6 +305,7 @@ SWEEP_TC_MAX_PLANES = 128
 SWEEP_FP16 = _os_environ_get("DVMVS_SWEEP_FP16", "0") == "1"      # experimental, see plane_sweep_h16
 
 
+@on_tensor_device
 def preprocess_rgb(image_hwc, crop_x, crop_y, out_h, out_w, scale, mean, std, normalize=True, bgr=None, out=None):
     """Device pre-processing of one decoded frame (dataset_loader.py:260-263,322-334 + run-testing.py:127): image_hwc is a
     CUDA tensor (H,W,3), uint8 (as cv2.imread returns it: BGR unless bgr=False) or float32 (as load_image returns it: RGB
@@ -288,6 +331,7 @@ def preprocess_rgb(image_hwc, crop_x, crop_y, out_h, out_w, scale, mean, std, no
     return out
 
 
+@on_tensor_device
 def hidden_warp(h_nhwc, depth_b1hw, prev_pose, cur_pose, K, invalid_thresh):
     B, h, w, C = h_nhwc.shape
     depth = require_cuda_f32(depth_b1hw, "depth").contiguous()
@@ -303,6 +347,7 @@ def hidden_warp(h_nhwc, depth_b1hw, prev_pose, cur_pose, K, invalid_thresh):
     return out
 
 
+@on_tensor_device
 def depth_reproject(cur_pose, prev_pose, prev_depth, full_K, half_K, H, W):
     B = cur_pose.shape[0]
     args = [require_cuda_f32(t, n).contiguous() for t, n in ((cur_pose, "reference_pose"), (prev_pose, "measurement_pose"),
@@ -313,6 +358,7 @@ def depth_reproject(cur_pose, prev_pose, prev_depth, full_K, half_K, H, W):
     return out
 
 
+@on_tensor_device
 def lstm_gates(gates_nhwc, c_nhwc):
     B, h, w, C4 = gates_nhwc.shape
     C = C4 // 4
@@ -323,6 +369,7 @@ def lstm_gates(gates_nhwc, c_nhwc):
     return h_out, c_out
 
 
+@on_tensor_device
 def upsample2x(x_nhwc):
     B, H, W, C = x_nhwc.shape
     y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=x_nhwc.device)
@@ -335,6 +382,7 @@ def round_up(x, m):
     return (x + m - 1) // m * m
 
 
+@on_tensor_device
 def split_planes(x_nhwc, upsample=False):
     """fp32 (B,H,W,C) -> fp16 (hi, lo) planes (2,B,H',W',Cs), Cs = C rounded up to 8 (zero channels)."""
     B, H, W, C = x_nhwc.shape
@@ -346,6 +394,7 @@ def split_planes(x_nhwc, upsample=False):
     return planes
 
 
+@on_tensor_device
 def concat_planes(sources):
     """torch.cat([...], dim=channels) staged directly as ONE fp16-pair operand tensor: sources = [(fp32 nhwc, upsample)]."""
     shapes = [(t.shape[1] * (2 if up else 1), t.shape[2] * (2 if up else 1)) for t, up in sources]
@@ -406,6 +455,7 @@ class PackedConvTC:
         self.src_channels = list(src_channels)
 
 
+@on_tensor_device
 def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, want_f32=True, want_planes=True, terms=3,
               block_n=None, allow_split=True, blk_out=None):
     """sources: list of fp16-pair plane tensors (2,B,Hin,Win,Cs_i) matching ptc.src_stored.  Returns
@@ -469,6 +519,7 @@ def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, w
 
 
 # ================================================================================================ halo (blocked-layout) path
+@on_tensor_device
 def split_blocked(sources, only=None, into=None):
     """sources: [(fp32 nhwc tensor, upsample)] -> blocked fp16 pair planes (2, B, C8, H', W', 8) of their channel
     concatenation (torch.cat staged straight into the operand layout of conv_halo_kernel).  Every source starts on an
@@ -548,6 +599,7 @@ class PackedConvHalo:
         self.src_channels = list(src_channels)
 
 
+@on_tensor_device
 def conv2d_halo(sources_blk, ph, residual=None, terms=3, want_f32=True, want_blk=False, want_nhwc=True):
     """sources_blk: list of blocked plane tensors (2,B,C8_i,H,W,8).  Returns (f32 or None, blk or None, nhwc planes or None)."""
     d = N.ConvHaloDesc()
@@ -623,8 +675,8 @@ def set_precision_policy(policy=None):
         policy = {k.strip(): int(v) for k, v in (item.split("=") for item in policy.split(",") if item.strip())}
     policy = dict(policy or {})
     for k, v in policy.items():
-        if k not in ("fe", "fpn", "cve", "lstm", "cvd") or v not in (1, 3):
-            raise ValueError("precision policy: family in fe/fpn/cve/lstm/cvd, terms 1 or 3 (got %r=%r)" % (k, v))
+        if k not in ("fe", "fpn", "cve", "lstm", "cvd", "sweep") or v not in (1, 3):
+            raise ValueError("precision policy: family in fe/fpn/cve/lstm/cvd/sweep, terms 1 or 3 (got %r=%r)" % (k, v))
     _TERMS_POLICY = policy
 
 
@@ -659,10 +711,11 @@ def family_terms(family):
 class Act:
     """An activation inside a module: fp32 channel-last tensor and/or its fp16 (hi, lo) planes (created on demand,
     cached).  `up` planes = planes of the x2-bilinear-upsampled tensor (F.interpolate materialised for the TMA loader)."""
-    __slots__ = ("f32", "planes", "planes_up", "blk", "blk_up", "version")
+    __slots__ = ("f32", "planes", "planes_up", "blk", "blk_up", "version", "pair")
 
-    def __init__(self, f32=None, planes=None, blk=None):
+    def __init__(self, f32=None, planes=None, blk=None, pair=None):
         self.f32, self.planes, self.planes_up, self.blk, self.blk_up, self.version = f32, planes, None, blk, None, None
+        self.pair = pair          # (hi, lo) fp16 (B,H,W,C) tensors when the planes are a batch slice of a bigger tensor's planes
 
     @property
     def channels(self):
@@ -729,19 +782,65 @@ class Fork:
 
 
 def to_act(x, name="input"):
-    """API tensor (B,C,H,W) -> Act; re-uses the producer's Act (and its fp16 planes) when the tensor is the untouched
-    output of one of our modules."""
+    """API tensor (B,C,H,W) -> Act.  When the tensor is the untouched output of one of our modules (same storage, same
+    autograd version), the operand layouts the PRODUCER KERNEL emitted next to the fp32 values (fp16 pair planes, blocked
+    planes) come along; the Act handed back is a fresh object, so layouts derived later on demand (split kernels,
+    x2-upsampled planes) live and die with the consumer's call and are never cached on a tensor the caller can reach --
+    a CUDA-graph replay or an out-of-band write rewrites such a tensor without any notification.
+    Caveat: a write through `.data` does not bump the version either; call dvmvs._ops.invalidate(t) after
+    one, or the producer-emitted fp16 planes of `t` are stale."""
     a = getattr(x, "_dvmvs_act", None)
     if a is not None and a.f32.data_ptr() == x.data_ptr() and a.version == x._version and tuple(a.f32.shape) == (
             x.shape[0], x.shape[2], x.shape[3], x.shape[1]):
-        return a
+        return Act(a.f32, a.planes, a.blk, a.pair)
     return Act(to_nhwc(x, name))
 
 
 def act_to_api(a):
     t = to_api(a.f32)
-    a.version = t._version
-    t._dvmvs_act = a
+    keep = Act(a.f32, a.planes, a.blk, a.pair)  # what the producer emitted; nothing derived later is attached to it
+    keep.version = t._version
+    t._dvmvs_act = keep
+    return t
+
+
+def batch_slice(t, lo, hi):
+    """t[lo:hi] along the batch axis of an API tensor, keeping the fp16 (hi, lo) planes its producer emitted as views (the
+    engines run FeatureExtractor + FeatureShrinker once over the reference and measurement images stacked on the batch axis
+    and hand the slices to the plane sweep)."""
+    v = t[lo:hi]
+    a = getattr(t, "_dvmvs_act", None)
+    if a is not None and a.f32.data_ptr() == t.data_ptr() and a.version == t._version and a.planes is not None:
+        act = Act(a.f32[lo:hi], pair=(a.planes[0, lo:hi], a.planes[1, lo:hi]))
+        act.version = v._version
+        v._dvmvs_act = act
+    return v
+
+
+def act_pair(a):
+    """(hi, lo) fp16 planes of an Act as two contiguous (B,H,W,C) tensors (a split kernel runs when the producer emitted none)."""
+    if a.pair is not None:
+        return a.pair
+    p = a.get_planes()
+    return p[0], p[1]
+
+
+_SWEEP = _os_environ_get("DVMVS_SWEEP", "tc")      # "tc": tensor-core form of the plane sweep on the tc backend; "gather": always the fp32 gather kernel
+
+
+def sweep_uses_tc(dot_product, channels, n_depth_levels, n_meas):
+    return (_SWEEP == "tc" and _BACKEND == "tc" and dot_product and channels == 32 and 2 <= n_depth_levels <= SWEEP_TC_MAX_PLANES and
+            n_meas * n_depth_levels <= 512 and n_meas <= 8)
+
+
+def sweep_terms():
+    return _TERMS_POLICY.get("sweep", _TC_TERMS)
+
+
+def invalidate(t):
+    """Drops the operand layouts attached to an API tensor (after modifying it through `.data`)."""
+    if hasattr(t, "_dvmvs_act"):
+        del t._dvmvs_act
     return t
 
 

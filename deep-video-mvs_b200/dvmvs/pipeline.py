@@ -4,6 +4,7 @@ the script's loop body (bench.py, smoke test, examples).  It makes exactly the m
 makes, with the same keyword arguments."""
 import torch
 
+from . import _ops as ops
 from .utils import (cost_volume_fusion, get_non_differentiable_rectangle_depth_estimation,
                     get_warp_grid_for_cost_volume_calculation)
 
@@ -116,16 +117,16 @@ def feature_stage(mods, reference_image, reference_pose, measurement_images, mea
         stacked = torch.cat([reference_image] + [measurement_images[m] for m in todo], dim=0) if todo else reference_image
         a2, a4, a8, a16 = mods["fpn"](*mods["fe"](stacked))
         if todo:
-            f2, f4, f8, f16 = a2[:B], a4[:B], a8[:B], a16[:B]
+            f2, f4, f8, f16 = ops.batch_slice(a2, 0, B), a4[:B], a8[:B], a16[:B]
         else:
             f2, f4, f8, f16 = a2, a4, a8, a16
         for n, m in enumerate(todo):
-            meas_half[m] = a2[(n + 1) * B:(n + 2) * B]
+            meas_half[m] = ops.batch_slice(a2, (n + 1) * B, (n + 2) * B)
     elif batch_features and len(measurement_images) > 0:
         stacked = torch.cat([reference_image] + list(measurement_images), dim=0)
         a2, a4, a8, a16 = mods["fpn"](*mods["fe"](stacked))
-        f2, f4, f8, f16 = a2[:B], a4[:B], a8[:B], a16[:B]
-        meas_half = [a2[(m + 1) * B:(m + 2) * B] for m in range(len(measurement_images))]
+        f2, f4, f8, f16 = ops.batch_slice(a2, 0, B), a4[:B], a8[:B], a16[:B]
+        meas_half = [ops.batch_slice(a2, (m + 1) * B, (m + 2) * B) for m in range(len(measurement_images))]
     else:
         meas_half = []
         for im in measurement_images:
@@ -332,8 +333,8 @@ def _stage_sweep(mods, slot, fe_out, min_depth, max_depth, n_depth_levels):
         meas_half = [t.permute(0, 3, 1, 2) for t in slot["meas_half"]]
         slot["ref_half"] = f2                     # the engine copies it into the cache ring after the stage's graph
     else:
-        f2, f4, f8, f16 = a2[:B], a4[:B], a8[:B], a16[:B]
-        meas_half = [a2[(m + 1) * B:(m + 2) * B] for m in range(M)]
+        f2, f4, f8, f16 = ops.batch_slice(a2, 0, B), a4[:B], a8[:B], a16[:B]
+        meas_half = [ops.batch_slice(a2, (m + 1) * B, (m + 2) * B) for m in range(M)]
     half_K = slot["full_K"].clone()
     half_K[:, 0:2, :] = half_K[:, 0:2, :] / 2.0
     cv = cost_volume_fusion(image1=f2, image2s=meas_half, pose1=slot["ref_pose"], pose2s=slot["meas_poses"], K=half_K, warp_grid=None,
@@ -443,6 +444,22 @@ class PipelinedFusionnet:
     def reset(self):
         """TRACKING LOST / new clip: drops the recurrent state (the feature cache is keyed by frame id and stays valid)."""
         self._has_state = False
+
+    def load_state(self, lstm_state, previous_depth, previous_pose):
+        """Continue a clip whose first keyframes ran elsewhere (e.g. through the module calls with fewer measurement frames):
+        installs (h, c), the previous depth (B,1,H,W) and the previous pose as the recurrent state of the next submit().
+        Needs the static state buffers, i.e. prime() or one earlier keyframe."""
+        if self._static_state is None:
+            raise RuntimeError("load_state: call prime() (or submit one keyframe) first")
+        self.synchronize()
+        h, c, pd, pp = self._static_state
+        with torch.no_grad():
+            h.copy_(lstm_state[0])
+            c.copy_(lstm_state[1])
+            pd.copy_(previous_depth.reshape(pd.shape))
+            pp.copy_(previous_pose)
+        torch.cuda.current_stream(self.device).synchronize()
+        self._has_state = True
 
     # -- stage bodies -----------------------------------------------------------------------------------------------
     def _run_stage(self, i, slot, with_state):

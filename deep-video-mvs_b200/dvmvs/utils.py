@@ -43,6 +43,13 @@ def cost_volume_fusion(image1, image2s, pose1, pose2s, K, warp_grid, min_depth, 
                                       "inference only, utils.py:83-84)")
         from .training import plane_sweep_cost_volume
         return plane_sweep_cost_volume(image1, image2s, pose1, pose2s, K, min_depth, max_depth, n_depth_levels)
+    if ops.sweep_uses_tc(bool(dot_product), image1.shape[1], int(n_depth_levels), len(image2s)):
+        # tensor-core form (csrc/sweep_tc.cu): correlate the epipolar band on tcgen05, blend four scalars per sample.  Reads the
+        # fp16 (hi, lo) planes the FPN's output convolution emitted (a split kernel stages them for foreign tensors).
+        ref_pair = ops.act_pair(ops.to_act(image1, "image1"))
+        meas_pairs = [ops.act_pair(ops.to_act(t, "image2")) for t in image2s]
+        cost = ops.plane_sweep_tc(ref_pair, meas_pairs, pose1, pose2s, K, min_depth, max_depth, n_depth_levels, terms=ops.sweep_terms())
+        return ops.to_api(cost)
     ref = ops.to_nhwc(image1, "image1")
     if ops.SWEEP_FP16 and dot_product and ref.shape[-1] == 32 and ref.shape[2] >= 2:
         # experimental (DVMVS_SWEEP_FP16=1): gather the fp16 "hi" plane of the measurement features -- already there when they

@@ -88,6 +88,10 @@ int dvmvs_plane_sweep_tc(const void* ref_hi, const void* ref_lo, const void* con
                          const float* pose1, const float* const* pose2_host, const float* K, float* cost_out, int B, int h, int w,
                          int D, int M, float min_depth, float max_depth, int terms, dvmvs_stream_t stream);
 
+/* Development aid (tools/sweep_timeline.py): a device buffer of 8 x 64 int64 that subsequent dvmvs_plane_sweep_tc launches fill
+ * with clock64 stamps of the phases of their first eight CTAs; NULL switches it off. */
+int dvmvs_plane_sweep_tc_set_timeline(void* device_buffer);
+
 /* Pose-aware hidden-state warp with the invalid-depth mask fused.
  * Replaces dvmvs/utils.py:205-258 warp_frame_depth plus dvmvs/convlstm.py:30-41 (transformation =
  * inverse(previous_pose) @ current_pose; h[depth <= invalid_thresh] = 0).
@@ -163,9 +167,14 @@ typedef struct {
   long long workspace_bytes;
   void* out_blk;         /* optional: the same output also in the blocked layout [2][B][Cout/8][Hout][Wout][8] that
                             dvmvs_conv2d_halo consumes (needs out_planes) */
+  int out_hi_only;       /* fp16 outputs: write plane 0 (hi) only -- every consumer of this tensor runs 1-term products */
+  int defer_finish;      /* split-K launches only (dvmvs_conv2d_tc_ksplit > 1): leave the partial sums in the workspace
+                            ([ksplit][B][Hout][Wout][Cout] fp32 at workspace + 16384 bytes) and skip the finishing kernel --
+                            the caller's epilogue reduces them (dvmvs_lstm_gates_parts); no outputs are written */
 } dvmvs_conv_tc_desc;
 
 int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* desc_host, dvmvs_stream_t stream);
+int dvmvs_conv2d_tc_ksplit(const dvmvs_conv_tc_desc* desc_host);   /* the split count that call will use (1 = none) */
 
 /* ------------------------------------------------------------------------------------------------------
  * Stride-1 k x k convolution on tcgen05 without im2col amplification ("halo" implicit GEMM, csrc/conv_halo.cu): the
@@ -192,6 +201,7 @@ typedef struct {
   void* out_nhwc;
   int B, H, W, Cout, ksize, act;
   const void* w_cat;
+  int out_hi_only;       /* fp16 outputs: hi plane only */
 } dvmvs_conv_halo_desc;
 
 int dvmvs_conv2d_halo(const dvmvs_conv_halo_desc* desc_host, dvmvs_stream_t stream);
@@ -225,6 +235,14 @@ int dvmvs_dwconv2d(const float* x, const float* weight, const float* bias, float
  * variance, eps 1e-5, no affine; CELU alpha = 1. */
 int dvmvs_lstm_gates(const float* gates, const float* c_in, float* h_out, float* c_out, int B, int h, int w, int C,
                      dvmvs_stream_t stream);
+
+/* The same epilogue as the FINISHING PASS of the gate convolution (convlstm.py:43-59 in one step after the GEMM): the gate
+ * pre-activations are read as the sum, in split order, of the n_parts split-K partial sums a dvmvs_conv2d_tc launch with
+ * defer_finish left in its workspace (part i at gate_parts + i * part_stride elements, each [B][h][w][4*C]) plus `addend`
+ * ([B][h][w][4*C] or NULL: the state-independent half conv(W[:, :Cin], x)), then sigmoid / LayerNorm over (h,w) / CELU / state
+ * update.  n_parts = 1, addend = NULL is dvmvs_lstm_gates. */
+int dvmvs_lstm_gates_parts(const float* gate_parts, int n_parts, long long part_stride, const float* addend, const float* c_in,
+                           float* h_out, float* c_out, int B, int h, int w, int C, dvmvs_stream_t stream);
 
 /* x2 bilinear upsampling, align_corners=True (F.interpolate at dvmvs/fusionnet/model.py:59,114,293-294). */
 int dvmvs_upsample2x(const float* x, float* y, int B, int H, int W, int C, dvmvs_stream_t stream);

@@ -41,7 +41,7 @@ def bilinear_sample_zeros(image, xs, ys):
     B, C, H, W = image.shape
     x0 = torch.floor(xs)
     y0 = torch.floor(ys)
-    out = torch.zeros(B, C, *xs.shape[1:], dtype=image.dtype)
+    out = torch.zeros(B, C, *xs.shape[1:], dtype=image.dtype, device=image.device)
     flat = image.reshape(B, C, H * W)
     for dy in (0, 1):
         for dx in (0, 1):
@@ -70,11 +70,11 @@ def calculate_cost_volume_by_warping(image1, image2, pose1, pose2, K, warp_grid,
     t = E[:, 0:3, 3].unsqueeze(-1)
     Kt = K.bmm(t)                                             # :55
     G = K.bmm(R).bmm(torch.inverse(K))                        # :56
-    grid = warp_grid.unsqueeze(0).expand(B, -1, -1)
+    grid = warp_grid.to(image1.device).unsqueeze(0).expand(B, -1, -1)
     base = G.bmm(grid)                                        # :57  (B,3,h*w)
     inv_base = 1.0 / max_depth                                # :59
     inv_step = (1.0 / min_depth - 1.0 / max_depth) / (n_depth_levels - 1)   # :60
-    cost = torch.empty(B, n_depth_levels, h, w, dtype=torch.float32)
+    cost = torch.empty(B, n_depth_levels, h, w, dtype=torch.float32, device=image1.device)
     for i in range(n_depth_levels):
         this_depth = 1 / (inv_base + i * inv_step)            # :66
         q = base + Kt / this_depth                            # :68
@@ -96,7 +96,7 @@ def calculate_cost_volume_by_warping(image1, image2, pose1, pose2, K, warp_grid,
 def cost_volume_fusion(image1, image2s, pose1, pose2s, K, warp_grid, min_depth, max_depth, n_depth_levels,
                        device="cpu", dot_product=True):
     """dvmvs/utils.py:89-107 -- accumulate over measurement frames in list order, divide by M."""
-    fused = torch.zeros(image1.shape[0], n_depth_levels, image1.shape[2], image1.shape[3], dtype=torch.float32)
+    fused = torch.zeros(image1.shape[0], n_depth_levels, image1.shape[2], image1.shape[3], dtype=torch.float32, device=image1.device)
     for pose2, image2 in zip(pose2s, image2s):
         fused += calculate_cost_volume_by_warping(image1, image2, pose1, pose2, K, warp_grid, min_depth,
                                                   max_depth, n_depth_levels, device, dot_product)
@@ -107,7 +107,8 @@ def cost_volume_fusion(image1, image2s, pose1, pose2s, K, warp_grid, min_depth, 
 def _unproject(depth, K):
     """kornia 0.3.2 depth_to_3d(normalize_points=False): (B,1,H,W) -> (B,H,W,3)."""
     B, _, H, W = depth.shape
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=depth.device), torch.arange(W, dtype=torch.float32, device=depth.device),
+                            indexing="ij")
     fx, fy = K[:, 0, 0].view(B, 1, 1), K[:, 1, 1].view(B, 1, 1)
     cx, cy = K[:, 0, 2].view(B, 1, 1), K[:, 1, 2].view(B, 1, 1)
     d = depth[:, 0]
@@ -159,13 +160,13 @@ def get_non_differentiable_rectangle_depth_estimation(reference_pose_torch, meas
     valid = (pu >= 0) & (pv >= 0) & (pu < hw) & (pv < hh)                           # :137-139
     out = np.zeros((B, 1, hh, hw), dtype=np.float32)
     for b in range(B):
-        idx = (pv[b][valid[b]] * hw + pu[b][valid[b]]).numpy()
-        zs = z[b][valid[b]].numpy()
+        idx = (pv[b][valid[b]] * hw + pu[b][valid[b]]).cpu().numpy()       # the reference syncs to the host here too (utils.py:148)
+        zs = z[b][valid[b]].cpu().numpy()
         flat = np.full(hh * hw, -1.0, dtype=np.float32)
         np.maximum.at(flat, idx, zs)
         flat[flat < 0] = 0.0
         out[b, 0] = flat.reshape(hh, hw)
-    return torch.from_numpy(out)
+    return torch.from_numpy(out).to(previous_depth_torch.device)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -320,8 +321,8 @@ def lstm_fusion(sd, current_encoding, current_state, previous_pose, current_pose
     channel (biased variance, eps 1e-5, no affine); CELU alpha=1."""
     B, C, h, w = current_encoding.shape
     if current_state is None:
-        h_cur = torch.zeros(B, C, h, w)
-        c_cur = torch.zeros(B, C, h, w)
+        h_cur = torch.zeros(B, C, h, w, device=current_encoding.device)
+        c_cur = torch.zeros(B, C, h, w, device=current_encoding.device)
     else:
         h_cur, c_cur = current_state
     if previous_pose is not None:
@@ -437,7 +438,7 @@ def fusionnet_step(weights, state, reference_image, reference_pose, measurement_
                                                                full_K, half_K, W, H)  # :179-186
         de = F.interpolate(de, scale_factor=1.0 / 16.0, mode="nearest")               # :187-189
     else:
-        de = torch.zeros(B, 1, H // 32, W // 32)                                      # :191
+        de = torch.zeros(B, 1, H // 32, W // 32, device=reference_image.device)       # :191
     state.lstm_state = lstm_fusion(weights["lstm"], bottom, state.lstm_state, state.previous_pose, reference_pose, de, lstm_K)
     pred = cost_volume_decoder(weights["cvd"], reference_image, s0, s1, s2, s3, state.lstm_state[0], min_depth, max_depth)[0]
     state.previous_depth = pred.view(B, 1, H, W)                                      # :201

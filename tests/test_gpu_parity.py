@@ -621,6 +621,142 @@ def test_fusionnet_shipped_weights_tensor_core_backend_vs_shipped_golden(terms, 
         ops.set_conv_backend(old, terms=3)
 
 
+def _bench_frames(synth, clips, t, H, W, M):
+    """Batched device tensors for keyframe t of `clips` (what bench.py's stack_frame builds)."""
+    ref = np.stack([c["images"][c["frames"][t][0]] for c in clips])
+    rpose = np.stack([c["poses"][c["frames"][t][0]] for c in clips])
+    meas = [np.stack([c["images"][c["frames"][t][1][m]] for c in clips]) for m in range(M)]
+    mpose = [np.stack([c["poses"][c["frames"][t][1][m]] for c in clips]) for m in range(M)]
+    K = np.stack([c["K"] for c in clips])
+    return _cuda(ref), _cuda(rpose), [_cuda(x) for x in meas], [_cuda(x) for x in mpose], _cuda(K)
+
+
+@pytest.mark.parametrize("n_clips,n_frames", [(1, 12), (2, 6), (8, 3)])
+def test_benchmarked_configuration_vs_oracle(oracle, synth, n_clips, n_frames):
+    """EXACTLY what bench.py times: PipelinedFusionnet(n_stages=5) on the tcgen05 backend with fp16 operands (terms=1), config
+    c2 (256x256, 64 planes, 2 measurement frames), bench.py's seeded weights (seed 7) and clips (seed 1000 * rank + c), slots
+    re-used with the recurrent state carried -- against the CPU oracle run clip by clip.  n_clips > 1 = the `batched`
+    operating point and what every rank of the scaling run does."""
+    from dvmvs import _ops as ops
+    from dvmvs import pipeline
+    H, W, D, M = 256, 256, 64, 2
+    w = helpers.oracle_weights(oracle, synth, 7, n_depth_levels=D)
+    clips = [synth.make_clip(c, n_frames, H, W, M) for c in range(n_clips)]
+    old = ops.conv_backend()
+    ops.set_conv_backend("tc", terms=1, stride2=True)
+    try:
+        mods = helpers.build_product_modules(w, n_depth_levels=D)
+        pipe = pipeline.PipelinedFusionnet(mods, batch=n_clips, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=5)
+        outs = []
+        with torch.no_grad():
+            pipe.prime(*_bench_frames(synth, clips, 0, H, W, M))
+            for t in range(n_frames):
+                out = torch.empty((n_clips, H, W), dtype=torch.float32, device=DEV)
+                pipe.submit(*_bench_frames(synth, clips, t, H, W, M), out=out)
+                outs.append(out)
+            pipe.synchronize()
+        worst = 0.0
+        with torch.no_grad():
+            for c, clip in enumerate(clips):
+                st = oracle.FusionnetState()
+                K = T(clip["K"])[None]
+                for t, (ref_i, meas_i) in enumerate(clip["frames"]):
+                    gold, st = oracle.fusionnet_step(w, st, T(clip["images"][ref_i])[None], T(clip["poses"][ref_i])[None],
+                                                     [T(clip["images"][j])[None] for j in meas_i], [T(clip["poses"][j])[None] for j in meas_i],
+                                                     K, n_depth_levels=D)
+                    e = oracle.rel_l1_inverse_depth(outs[t][c:c + 1].cpu().numpy(), gold.numpy())
+                    worst = max(worst, e)
+                    assert e <= 3.3e-4, "clip %d keyframe %d: %.3e" % (c, t, e)
+        print("benchmarked configuration, %d clip(s) x %d keyframes: worst rel-L1(inverse depth) vs oracle %.2e" % (n_clips, n_frames, worst))
+    finally:
+        ops.set_conv_backend(old, terms=3)
+
+
+def test_benchmarked_configuration_shipped_weights_vs_shipped_golden():
+    """The bench engine (5-stage pipeline, tcgen05, fp16 operands) with the reference's shipped fusionnet weights on the
+    fixture scene (320x256, 64 planes, 1..3 measurement frames as the index file says) vs the reference's shipped golden."""
+    w = scene_fixture.load_shipped_weights("fusionnet")
+    if w is None:
+        pytest.skip("shipped weights not fetched (tools/fetch_fixtures.py needs /root/reference in the build container)")
+    from dvmvs import _ops as ops
+    from dvmvs import pipeline
+    from oracle import dvmvs_oracle as oracle
+    old = ops.conv_backend()
+    ops.set_conv_backend("tc", terms=1, stride2=True)
+    try:
+        mods = helpers.build_product_modules(w)
+        frames, full_K, gold = scene_fixture.load_scene()
+        M = len(frames[-1]["measurement_images"])
+        steady = [i for i, fr in enumerate(frames) if len(fr["measurement_images"]) == M]      # the engine is built for a fixed M
+        H, W = frames[0]["reference_image"].shape[-2:]
+        pipe = pipeline.PipelinedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_stages=5)
+        state = helpers.ProductState()
+        errs = []
+        with torch.no_grad():
+            args = lambda fr: (_cuda(fr["reference_image"])[None], _cuda(fr["reference_pose"])[None], [_cuda(x)[None] for x in fr["measurement_images"]],
+                               [_cuda(p)[None] for p in fr["measurement_poses"]], _cuda(full_K)[None])
+            pipe.prime(*args(frames[steady[0]]))
+            # the first keyframes of the clip have fewer measurement frames: script sequence for those, then hand the state over
+            for i in range(steady[0]):
+                pred, state = helpers.product_fusionnet_step(mods, state, *args(frames[i]))
+                errs.append(oracle.rel_l1_inverse_depth(pred[0].cpu().numpy(), gold[i]))
+            if steady[0] > 0:
+                pipe.load_state(state.lstm_state, state.previous_depth, state.previous_pose)
+            outs = []
+            for i in steady:
+                out = torch.empty((1, H, W), dtype=torch.float32, device=DEV)
+                pipe.submit(*args(frames[i]), out=out)
+                outs.append((i, out))
+            pipe.synchronize()
+        for i, out in outs:
+            errs.append(oracle.rel_l1_inverse_depth(out[0].cpu().numpy(), gold[i]))
+        print("bench engine + shipped weights vs shipped golden:", ["%.2e" % e for e in errs])
+        assert max(errs) <= 3.3e-4, errs
+    finally:
+        ops.set_conv_backend(old, terms=3)
+
+
+@pytest.mark.parametrize("backend,terms", [("tc", 1), ("tc", 3)])
+def test_engines_match_eager_keyframe_on_the_tensor_core_backend(oracle, synth, backend, terms):
+    """GraphedFusionnet and PipelinedFusionnet (2..5 stages, multi-stream, per-stream split-K scratch, PDL, operand planes
+    crossing stage boundaries) against eager keyframe() on the SAME backend, different inputs every keyframe: the kernels are
+    deterministic, so the engines must reproduce the eager results bit for bit."""
+    from dvmvs import _ops as ops
+    from dvmvs import pipeline
+    H, W, D, M = 64, 96, 64, 2
+    w = helpers.oracle_weights(oracle, synth, 11, n_depth_levels=D)
+    old = ops.conv_backend()
+    ops.set_conv_backend(backend, terms=terms, stride2=True)
+    try:
+        mods = helpers.build_product_modules(w, n_depth_levels=D)
+        clip = synth.make_clip(5, 7, H, W, M)
+        K = _cuda(clip["K"])[None]
+        st = pipeline.KeyframeState()
+        eng = pipeline.GraphedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D)
+        pipes = [pipeline.PipelinedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=ns)
+                 for ns in (2, 3, 5)]
+        expected, graphed, piped = [], [], [[] for _ in pipes]
+        with torch.no_grad():
+            for ref_i, meas_i in clip["frames"]:
+                args = (_cuda(clip["images"][ref_i])[None], _cuda(clip["poses"][ref_i])[None], [_cuda(clip["images"][j])[None] for j in meas_i],
+                        [_cuda(clip["poses"][j])[None] for j in meas_i], K)
+                a, st = pipeline.keyframe(mods, st, *args, n_depth_levels=D)
+                expected.append(a.clone())
+                graphed.append(eng.step(*args).clone())
+                for pi, pipe in enumerate(pipes):
+                    out = torch.empty((1, H, W), dtype=torch.float32, device=DEV)
+                    pipe.submit(*args, out=out)
+                    piped[pi].append(out)
+            for pipe in pipes:
+                pipe.synchronize()
+        for t, e in enumerate(expected):
+            assert torch.equal(graphed[t], e), "graph engine, keyframe %d: max diff %.3e" % (t, float((graphed[t] - e).abs().max()))
+            for pi in range(len(pipes)):
+                assert torch.equal(piped[pi][t], e), "pipeline %d, keyframe %d: max diff %.3e" % (pi, t, float((piped[pi][t] - e).abs().max()))
+    finally:
+        ops.set_conv_backend(old, terms=3)
+
+
 HALO_CASES = [
     # name, B, H, W, [(channels, upsampled)], Cout, k, residual, terms, tol
     ("k3_c32", 1, 40, 48, [(32, False)], 32, 3, False, 3, 2e-5),

@@ -1,4 +1,4 @@
-"""Copies the reference's shipped weight files (parity fixtures) from
+"""Copies the reference's shipped weight files (parity fixtures) and its test-driver scripts from
 /root/reference into tests/golden/_ref_data/ (git-ignored; travels to the GPU box with the snapshot).
 Run by __graft_entry__.build() in the build container; a no-op where /root/reference is absent."""
 import os
@@ -24,6 +24,17 @@ def fetch(verbose=True):
                 shutil.copyfile(s, d)
                 if verbose:
                     print("fetched", net, f)
+    # the reference's test drivers, verbatim, for the "runs unchanged" test (tests/test_gpu_reference_script.py): git-ignored like
+    # the weights, executed from there on the GPU box, never imported by the product
+    for net in ("fusionnet", "pairnet"):
+        dst = os.path.join(REPO, "tests", "golden", "_ref_data", "scripts", net)
+        os.makedirs(dst, exist_ok=True)
+        for f in ("run-testing.py", "run-testing-online.py"):
+            s = os.path.join(REF, "dvmvs", net, f)
+            if os.path.isfile(s):
+                shutil.copyfile(s, os.path.join(dst, f))
+                if verbose:
+                    print("fetched script", net, f)
     return True
 
 
