@@ -359,13 +359,20 @@ def depth_reproject(cur_pose, prev_pose, prev_depth, full_K, half_K, H, W):
 
 
 @on_tensor_device
-def lstm_gates(gates_nhwc, c_nhwc):
-    B, h, w, C4 = gates_nhwc.shape
-    C = C4 // 4
-    h_out = torch.empty((B, h, w, C), dtype=torch.float32, device=gates_nhwc.device)
+def lstm_gates(gates_nhwc, c_nhwc, parts=None, addend=None):
+    """ConvLSTM gate epilogue (convlstm.py:45-59).  gates_nhwc: (B,h,w,4C) gate pre-activations -- or, with parts=(workspace
+    tensor, byte offset, n_parts, part_stride), the split-K partial sums a deferred gate convolution left in its workspace: the
+    epilogue is then the finishing pass of that GEMM (sum of the parts in split order + `addend`, the state-independent half)."""
+    B, h, w, C = c_nhwc.shape
+    h_out = torch.empty((B, h, w, C), dtype=torch.float32, device=c_nhwc.device)
     c_out = torch.empty_like(h_out)
-    N.check(N.lib().dvmvs_lstm_gates(gates_nhwc.data_ptr(), c_nhwc.data_ptr(), h_out.data_ptr(), c_out.data_ptr(), B, h, w, C,
-                                     _stream()), "lstm_gates")
+    if parts is None:
+        N.check(N.lib().dvmvs_lstm_gates(gates_nhwc.data_ptr(), c_nhwc.data_ptr(), h_out.data_ptr(), c_out.data_ptr(), B, h, w, C,
+                                         _stream()), "lstm_gates")
+    else:
+        ws, offset, n_parts, stride = parts
+        N.check(N.lib().dvmvs_lstm_gates_parts(ws.data_ptr() + offset, int(n_parts), int(stride), addend.data_ptr() if addend is not None else None,
+                                               c_nhwc.data_ptr(), h_out.data_ptr(), c_out.data_ptr(), B, h, w, C, _stream()), "lstm_gates_parts")
     return h_out, c_out
 
 
@@ -457,7 +464,7 @@ class PackedConvTC:
 
 @on_tensor_device
 def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, want_f32=True, want_planes=True, terms=3,
-              block_n=None, allow_split=True, blk_out=None):
+              block_n=None, allow_split=True, blk_out=None, defer_finish=False):
     """sources: list of fp16-pair plane tensors (2,B,Hin,Win,Cs_i) matching ptc.src_stored.  Returns
     (out_f32 or None, out_planes or None[, aux_out])."""
     d = N.ConvTcDesc()
@@ -509,9 +516,20 @@ def conv2d_tc(sources, ptc, residual=None, residual_mode=N.RES_NONE, aux=None, w
         d.aux_mult, d.aux_base = aux
     d.B, d.Hin, d.Win, d.Cout = B, Hin, Win, ptc.cout
     d.ksize, d.stride, d.act = ptc.ksize, ptc.stride, ptc.act
+    ws = None
     if allow_split:
         ws = workspace(dev)
         d.workspace, d.workspace_bytes = ws.data_ptr(), WORKSPACE_BYTES
+    d.out_hi_only = 0 if lo_planes_needed() else 1
+    if defer_finish:
+        # split-K launch whose finishing pass the caller fuses into its own epilogue (ConvLSTM gates): partial sums stay in the workspace
+        k = N.lib().dvmvs_conv2d_tc_ksplit(ctypes.byref(d)) if (ws is not None and not N.DRYRUN) else 1
+        if k > 1 and residual is None and aux is None:
+            d.defer_finish = 1
+            d.out_f32 = d.out_planes = d.out_blk = None
+            N.check(N.lib().dvmvs_conv2d_tc(ctypes.byref(d), _stream()), "conv2d_tc(deferred finish)")
+            return ("parts", (ws, 16384, k, B * Hout * Wout * ptc.cout))
+        return None                 # this launch would not split: the caller runs the ordinary path
     N.check(N.lib().dvmvs_conv2d_tc(ctypes.byref(d), _stream()), "conv2d_tc")
     if aux is not None:
         return out_f32, out_planes, aux_out
@@ -626,6 +644,7 @@ def conv2d_halo(sources_blk, ph, residual=None, terms=3, want_f32=True, want_blk
     d.out_blk = out_blk.data_ptr() if want_blk else None
     d.out_nhwc = out_nhwc.data_ptr() if want_nhwc else None
     d.B, d.H, d.W, d.Cout, d.ksize, d.act = B, H, W, ph.cout, ph.ksize, ph.act
+    d.out_hi_only = 0 if lo_planes_needed() else 1
     N.check(N.lib().dvmvs_conv2d_halo(ctypes.byref(d), _stream()), "conv2d_halo")
     return out_f32, out_blk, out_nhwc
 
@@ -650,15 +669,26 @@ def set_conv_backend(name, terms=None, stride2=None):
     global _BACKEND, _TC_TERMS, _TC_STRIDE2
     if name not in ("fp32", "tc"):
         raise ValueError("backend must be 'fp32' or 'tc'")
+    global _TC_TERMS_BASE
     _BACKEND = name
     if terms is not None:
         _TC_TERMS = int(terms)
+        _TC_TERMS_BASE = int(terms)
     if stride2 is not None:
         _TC_STRIDE2 = bool(stride2)
 
 
 def conv_backend():
     return _BACKEND
+
+
+_TC_TERMS_BASE = _TC_TERMS          # the terms set_conv_backend chose (family_terms() changes _TC_TERMS while a module runs)
+
+
+def lo_planes_needed():
+    """fp16 lo planes are only read by 3-term products: when the base precision and every family policy are 1-term, producers
+    skip writing them (and never read them)."""
+    return _TC_TERMS_BASE == 3 or _TC_TERMS == 3 or any(v == 3 for v in _TERMS_POLICY.values())
 
 
 # Per-family operand precision of the tensor-core path: module family ("fe", "fpn", "cve", "lstm", "cvd") -> terms
@@ -884,6 +914,25 @@ class ConvLayer:
             act.get_blk_up()
         elif kind == "tc":
             act.get_planes(upsample=True)
+
+    def run_deferred(self, sources):
+        """Tensor-core path only, single source: launches the convolution WITHOUT its split-K finishing pass when it splits and
+        returns ("parts", (workspace, byte offset, n_parts, part_stride)); otherwise (no split / other path) returns None and the
+        caller uses run()."""
+        if not self.uses_tc() or self.pack_sources or len(sources) != 1:
+            return None
+        pc = self.pc
+        a0, m0 = sources[0]
+        hin = (a0.f32 if a0.f32 is not None else a0.planes[0]).shape[1]
+        win = (a0.f32 if a0.f32 is not None else a0.planes[0]).shape[2]
+        if m0 != N.SRC_DIRECT or self.uses_halo(hin, win, N.RES_NONE, None):
+            return None
+        if self._ptc is None:
+            self._ptc = PackedConvTC(pc, self.src_channels, pc.weight.device)
+        r = conv2d_tc([a0.get_planes()], self._ptc, terms=_TC_TERMS, want_f32=False, want_planes=False, defer_finish=True)
+        if isinstance(r, tuple) and len(r) == 2 and r[0] == "parts":
+            return r
+        return None
 
     def run(self, sources, residual=None, residual_mode=N.RES_NONE, aux=None, want_f32=True, want_planes=True, prestaged=None):
         """sources: list of (Act, mode).  Returns Act (or (Act, aux tensor)).  want_* only prune outputs of the

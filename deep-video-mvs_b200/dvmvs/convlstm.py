@@ -14,6 +14,9 @@ from . import _native as N
 from . import _ops as ops
 from ._base import NativeModule
 
+import os as _os
+_FUSED_GATES = _os.environ.get("DVMVS_FUSED_GATES", "1") == "1"      # gate epilogue as the finishing pass of the gate GEMM
+
 
 class MVSLayernormConvLSTMCell(NativeModule):
     def __init__(self, input_dim, hidden_dim, kernel_size, activation_function=None):
@@ -61,8 +64,13 @@ class MVSLayernormConvLSTMCell(NativeModule):
             h = ops.Act(ops.hidden_warp(h.f32, estimated_current_depth, previous_pose, current_pose, camera_matrix, 0.01))
         if fork is not None:
             fork.join()
-        gates = conv_h.run([(h, N.SRC_DIRECT)], residual=gx, residual_mode=N.RES_SAME, want_planes=False)
-        h_next, c_next = ops.lstm_gates(gates.f32, c)
+        # the finishing pass of the (split-K) gate GEMM IS the gate epilogue: partial sums + input half -> sigmoid / LN / CELU / state
+        deferred = conv_h.run_deferred([(h, N.SRC_DIRECT)]) if _FUSED_GATES else None
+        if deferred is not None:
+            h_next, c_next = ops.lstm_gates(None, c, parts=deferred[1], addend=gx.f32)
+        else:
+            gates = conv_h.run([(h, N.SRC_DIRECT)], residual=gx, residual_mode=N.RES_SAME, want_planes=False)
+            h_next, c_next = ops.lstm_gates(gates.f32, c)
         return ops.act_to_api(ops.Act(h_next)), ops.to_api(c_next)
 
     def init_hidden(self, batch_size, image_size):

@@ -631,12 +631,13 @@ def _bench_frames(synth, clips, t, H, W, M):
     return _cuda(ref), _cuda(rpose), [_cuda(x) for x in meas], [_cuda(x) for x in mpose], _cuda(K)
 
 
-@pytest.mark.parametrize("n_clips,n_frames", [(1, 12), (2, 6), (8, 3)])
+@pytest.mark.parametrize("n_clips,n_frames", [(1, 105), (2, 6), (8, 3)])
 def test_benchmarked_configuration_vs_oracle(oracle, synth, n_clips, n_frames):
     """EXACTLY what bench.py times: PipelinedFusionnet(n_stages=5) on the tcgen05 backend with fp16 operands (terms=1), config
     c2 (256x256, 64 planes, 2 measurement frames), bench.py's seeded weights (seed 7) and clips (seed 1000 * rank + c), slots
-    re-used with the recurrent state carried -- against the CPU oracle run clip by clip.  n_clips > 1 = the `batched`
-    operating point and what every rank of the scaling run does."""
+    re-used with the recurrent state carried -- against the CPU oracle run clip by clip.  (1, 105) is the bench's whole horizon
+    (--warmup 5 --steps 100 keyframes of clip 0); n_clips > 1 = the `batched` operating point and what every rank of the
+    scaling run does."""
     from dvmvs import _ops as ops
     from dvmvs import pipeline
     H, W, D, M = 256, 256, 64, 2
