@@ -38,10 +38,14 @@ CONV_FLOP_PER_KEYFRAME = 30.0e9                                             # SU
 SWEEP_TRAFFIC_FILE = os.path.join(REPO, "profiles", "r02_sweep_tc_traffic.json")
 
 
-def sweep_traffic_per_clip():
+def sweep_traffic_per_clip(n_clips=1):
     try:
         with open(SWEEP_TRAFFIC_FILE) as fh:
             d = json.load(fh)
+        by = d.get("by_clips", {})
+        if by:
+            k = min(by, key=lambda c: abs(int(c) - n_clips))
+            return (by[k]["dram_bytes_read"] + by[k]["dram_bytes_write"]) / float(k), d.get("source", "") + " (capture at %s clips)" % k
         return float(d["dram_bytes_per_clip"]), d.get("source", os.path.basename(SWEEP_TRAFFIC_FILE))
     except Exception:  # noqa: BLE001
         return None, None
@@ -442,7 +446,8 @@ def run_ours(args, rank, world, local_rank):
                     lat_s.append((a.elapsed_time(b_), (time.perf_counter() - w0) * 1e3))
             extras["script_sequence"] = {"ms_per_keyframe_device": float(np.median([x[0] for x in lat_s])),
                                          "ms_per_keyframe_wall": float(np.median([x[1] for x in lat_s])),
-                                         "note": "run-testing.py:153-202 call sequence through the drop-in modules, eager (one host call per kernel)"}
+                                         "note": "run-testing.py:153-202 call sequence through the drop-in modules (M + 1 separate feature passes, eleven module / utils calls per keyframe, "
+                                                 "each replaying its own auto-captured CUDA graph: dvmvs/_base.py)"}
             # BASELINE.json configs[2]: 320x256, 96 planes, 4 measurement frames (its own module set: aggregator0 has D+32 inputs)
             if args.mode == "pipeline":
                 from dvmvs.config import Config as _Config
@@ -543,7 +548,7 @@ def run_ours(args, rank, world, local_rank):
     total_frames = B * args.steps * world
     peaks, peak_src = measured_peaks()
     achieved = SWEEP_BYTES_PER_CLIP * B / (sweep_ms * 1e-3) / 1e9
-    traffic_per_clip, traffic_src = sweep_traffic_per_clip()
+    traffic_per_clip, traffic_src = sweep_traffic_per_clip(B)
     fps = total_frames / (dev_ms * 1e-3)
     tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     conv_tf = fps / world * CONV_FLOP_PER_KEYFRAME / 1e12          # per GPU

@@ -12,7 +12,7 @@ import torch
 
 from . import _native as N
 from . import _ops as ops
-from ._base import NativeModule, pack_cbr, pack_head
+from ._base import NativeModule, auto_graph, pack_cbr, pack_head
 from .config import Config
 from .convlstm import MVSLayernormConvLSTMCell
 from .layers import conv_layer, depth_layer_3x3
@@ -200,6 +200,7 @@ class FeatureExtractor(NativeModule):
             outs.append(x)
         return outs
 
+    @auto_graph
     @ops.family_terms("fe")
     def forward(self, image):
         B, C, H, W = image.shape
@@ -268,6 +269,7 @@ class FeatureShrinker(NativeModule):
         del keep
         return outs
 
+    @auto_graph
     @ops.family_terms("fpn")
     def forward(self, layer1, layer2, layer3, layer4, layer5):
         feats = [ops.to_act(t, "layer%d" % (i + 1)) for i, t in enumerate((layer1, layer2, layer3, layer4, layer5))]
@@ -304,6 +306,7 @@ class CostVolumeEncoder(NativeModule):
         out3 = self.encoder_block3.run(inp3)
         return inp0, inp1, inp2, inp3, out3
 
+    @auto_graph
     @ops.family_terms("cve")
     def forward(self, features_half, features_quarter, features_one_eight, features_one_sixteen, cost_volume):
         args = [ops.to_act(t, n) for t, n in ((features_half, "features_half"), (features_quarter, "features_quarter"),
@@ -371,6 +374,7 @@ class CostVolumeDecoder(NativeModule):
         _, depth1 = heads[4].run([(x, D)], aux=aux)
         return [t.squeeze(3) for t in (depth1, depth2, depth4, depth8, depth16)]
 
+    @auto_graph
     @ops.family_terms("cvd")
     def forward(self, image, skip0, skip1, skip2, skip3, bottom):
         args = [ops.to_act(t, n) for t, n in ((image, "image"), (skip0, "skip0"), (skip1, "skip1"), (skip2, "skip2"),
@@ -387,6 +391,7 @@ class LSTMFusion(NativeModule):
     def _pack(self):
         return ()
 
+    @auto_graph
     @ops.family_terms("lstm")
     def forward(self, current_encoding, current_state, previous_pose, current_pose, estimated_current_depth, camera_matrix,
                 input_gates=None):

@@ -669,7 +669,8 @@ def set_conv_backend(name, terms=None, stride2=None):
     global _BACKEND, _TC_TERMS, _TC_STRIDE2
     if name not in ("fp32", "tc"):
         raise ValueError("backend must be 'fp32' or 'tc'")
-    global _TC_TERMS_BASE
+    global _TC_TERMS_BASE, _CONFIG_EPOCH
+    _CONFIG_EPOCH += 1
     _BACKEND = name
     if terms is not None:
         _TC_TERMS = int(terms)
@@ -680,6 +681,14 @@ def set_conv_backend(name, terms=None, stride2=None):
 
 def conv_backend():
     return _BACKEND
+
+
+_CONFIG_EPOCH = 0
+
+
+def config_epoch():
+    """Bumped by every change of the backend / precision configuration (captured auto-graphs are keyed by it)."""
+    return _CONFIG_EPOCH
 
 
 _TC_TERMS_BASE = _TC_TERMS          # the terms set_conv_backend chose (family_terms() changes _TC_TERMS while a module runs)
@@ -700,7 +709,8 @@ _TERMS_POLICY = {}
 
 def set_precision_policy(policy=None):
     """policy: dict family -> 1 | 3, or None / {} to clear.  Also accepts "fe=1,fpn=1,cve=1" (DVMVS_TC_POLICY syntax)."""
-    global _TERMS_POLICY
+    global _TERMS_POLICY, _CONFIG_EPOCH
+    _CONFIG_EPOCH += 1
     if isinstance(policy, str):
         policy = {k.strip(): int(v) for k, v in (item.split("=") for item in policy.split(",") if item.strip())}
     policy = dict(policy or {})

@@ -5,6 +5,7 @@ makes, with the same keyword arguments."""
 import torch
 
 from . import _ops as ops
+from ._base import no_auto_graph
 from .utils import (cost_volume_fusion, get_non_differentiable_rectangle_depth_estimation,
                     get_warp_grid_for_cost_volume_calculation)
 
@@ -244,7 +245,7 @@ class GraphedFusionnet:
             self._capture_stream = torch.cuda.Stream(device=self.device)
         s = self._capture_stream        # same stream for warm-up and capture: per-stream scratch is allocated outside the graph
         s.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(s), torch.no_grad():
+        with torch.cuda.stream(s), torch.no_grad(), no_auto_graph():
             for _ in range(2):
                 pred, st = self._body(with_state)
         torch.cuda.current_stream(self.device).wait_stream(s)
@@ -504,7 +505,7 @@ class PipelinedFusionnet:
         saved = [t.clone() for t in self._static_state] if (i == last and self._static_state is not None) else None
         if i == last and not self._rec_pdl:
             _native.lib().dvmvs_set_programmatic_launch(0)
-        with torch.cuda.stream(stream), torch.no_grad():
+        with torch.cuda.stream(stream), torch.no_grad(), no_auto_graph():
             for _ in range(2):
                 res = self._run_stage(i, slot, with_state)
         stream.synchronize()

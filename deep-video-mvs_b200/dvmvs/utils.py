@@ -36,6 +36,18 @@ def cost_volume_fusion(image1, image2s, pose1, pose2s, K, warp_grid, min_depth, 
     tensors are never materialised.  Returns (B, D, h, w) fp32 (channels_last strides)."""
     image2s, pose2s = list(image2s), list(pose2s)
     _check_sweep_args(image1, image2s, pose2s)
+    if not (torch.is_grad_enabled() and any(t.requires_grad for t in [image1] + image2s)) and all(
+            getattr(t, "_dvmvs_act", None) is None for t in [image1] + image2s):
+        # foreign tensors (the script path): split kernels + sweep replayed as one CUDA graph (_base.graphed_call); tensors that
+        # carry their producer's fp16 planes go straight to the kernel (the engines capture that themselves)
+        from ._base import graphed_call
+        return graphed_call(("cost_volume_fusion",), _cost_volume_fusion, (image1, image2s, pose1, pose2s, K, float(min_depth), float(max_depth),
+                                                                            int(n_depth_levels), bool(dot_product)), {})
+    return _cost_volume_fusion(image1, image2s, pose1, pose2s, K, min_depth, max_depth, n_depth_levels, dot_product)
+
+
+def _cost_volume_fusion(image1, image2s, pose1, pose2s, K, min_depth, max_depth, n_depth_levels, dot_product):
+    device, warp_grid = image1.device, None
     if torch.is_grad_enabled() and any(t.requires_grad for t in [image1] + image2s):
         # training (run-training.py:231): same forward kernel, hand-written backward kernel (dvmvs/training.py, row f3)
         if not dot_product:
@@ -76,7 +88,9 @@ def get_non_differentiable_rectangle_depth_estimation(reference_pose_torch, meas
     H, W = int(original_height), int(original_width)
     if previous_depth_torch.numel() != B * H * W:
         raise ValueError("previous_depth_torch must hold B*H*W = %d values, got shape %s" % (B * H * W, tuple(previous_depth_torch.shape)))
-    return ops.depth_reproject(reference_pose_torch, measurement_pose_torch, previous_depth_torch, full_K_torch, half_K_torch, H, W)
+    from ._base import graphed_call
+    return graphed_call(("depth_reproject", H, W), lambda a, b, c, d, e: ops.depth_reproject(a, b, c, d, e, H, W),
+                        (reference_pose_torch, measurement_pose_torch, previous_depth_torch, full_K_torch, half_K_torch), {})
 
 
 def warp_frame_depth(image_src, depth_dst, src_trans_dst, camera_matrix, normalize_points=False, sampling_mode='bilinear'):
