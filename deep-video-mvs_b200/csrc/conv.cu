@@ -430,19 +430,26 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 constexpr int kLstmWarps = 8;
 
-// PPW = pixels per warp (ceil(h*w / kLstmWarps)), a template parameter so that each thread's gate / cell values are loaded
-// ONCE, all loads in flight together, and stay in registers across the four reduction passes (the kernel sits on the
-// loop-carried critical path of the pipeline; with run-time loops it paid three serialised global-load phases).
-template <int PPW>
+// A block owns CPB channels of one clip over all h*w positions (LayerNorm reduces over the positions): a warp covers CPB
+// channels x (32 / CPB) positions, so every load instruction reads (32 / CPB) contiguous 4*CPB-byte spans.  CPB = 32 is the wide
+// form (C/32 blocks per clip); CPB = 8 quadruples the number of blocks -- the kernel sits on the loop-carried critical path of
+// the pipeline and at batch 1 reads ~5 MB of split-K partial sums with C/32 = 16 blocks otherwise.
+// PPW = positions per thread, a template parameter so that each thread's gate / cell values are loaded ONCE, all loads in
+// flight together, and stay in registers across the four reduction passes.
+template <int PPW, int CPB>
 __global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float* __restrict__ gates, int n_parts, size_t part_stride,
                                                                      const float* __restrict__ addend, const float* __restrict__ c_in,
                                                                      float* __restrict__ h_out, float* __restrict__ c_out, int hw, int C) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float s_red[kLstmWarps * 32];
+  constexpr int kSub = 32 / CPB;                     // positions per warp pass
+  constexpr int kStride = kLstmWarps * kSub;         // positions per block pass
+  __shared__ float s_red[kLstmWarps * CPB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
+  const int cl = lane % CPB, sub = lane / CPB;
+  const int c = blockIdx.x * CPB + cl;
   const int b = blockIdx.y;
+  const int p0 = warp * kSub + sub;                  // this thread's positions: p0 + j * kStride
   const float* g = gates + (size_t)b * hw * 4 * C;
   const float* ad = addend ? addend + (size_t)b * hw * 4 * C : nullptr;
   const float inv_n = 1.f / (float)hw;
@@ -455,20 +462,22 @@ __global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float
     return x;
   };
 
-  auto block_sum = [&](float v) -> float {
+  auto block_sum = [&](float v) -> float {           // sum over all positions for this thread's channel
+#pragma unroll
+    for (int o = CPB; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
-    s_red[warp * 32 + lane] = v;
+    if (sub == 0) s_red[warp * CPB + cl] = v;
     __syncthreads();
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLstmWarps; ++i) t += s_red[i * 32 + lane];
+    for (int i = 0; i < kLstmWarps; ++i) t += s_red[i * CPB + cl];
     return t;
   };
 
   float vi[PPW], vf[PPW], vo[PPW], vg[PPW], vc[PPW];
 #pragma unroll
   for (int j = 0; j < PPW; ++j) {
-    const int p = warp + j * kLstmWarps;
+    const int p = p0 + j * kStride;
     const bool ok = p < hw;
     const size_t gp = (size_t)(ok ? p : 0) * 4 * C;
     vi[j] = ok ? pre(gp + c) : 0.f;
@@ -486,7 +495,7 @@ __global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float
 #pragma unroll
   for (int j = 0; j < PPW; ++j) {
     const float dlt = vg[j] - mean_g;
-    if (warp + j * kLstmWarps < hw) s += dlt * dlt;
+    if (p0 + j * kStride < hw) s += dlt * dlt;
   }
   const float rstd_g = rsqrtf(block_sum(s) * inv_n + 1e-5f);
   // c_next (pre-LN) = f*c + i*celu(LN(cc_g))
@@ -495,7 +504,7 @@ __global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float
   for (int j = 0; j < PPW; ++j) {
     const float ig = sigmoidf_(vi[j]), fg = sigmoidf_(vf[j]);
     const float gg = celu1((vg[j] - mean_g) * rstd_g);
-    vg[j] = (warp + j * kLstmWarps < hw) ? fg * vc[j] + ig * gg : 0.f;      // vg now holds c_next (pre-LN)
+    vg[j] = (p0 + j * kStride < hw) ? fg * vc[j] + ig * gg : 0.f;      // vg now holds c_next (pre-LN)
     s += vg[j];
   }
   const float mean_c = block_sum(s) * inv_n;
@@ -503,12 +512,12 @@ __global__ void __launch_bounds__(32 * kLstmWarps) lstm_gates_kernel(const float
 #pragma unroll
   for (int j = 0; j < PPW; ++j) {
     const float dlt = vg[j] - mean_c;
-    if (warp + j * kLstmWarps < hw) s += dlt * dlt;
+    if (p0 + j * kStride < hw) s += dlt * dlt;
   }
   const float rstd_c = rsqrtf(block_sum(s) * inv_n + 1e-5f);
 #pragma unroll
   for (int j = 0; j < PPW; ++j) {
-    const int p = warp + j * kLstmWarps;
+    const int p = p0 + j * kStride;
     if (p < hw) {
       const float cn = (vg[j] - mean_c) * rstd_c;
       c_out[((size_t)b * hw + p) * C + c] = cn;
@@ -628,15 +637,25 @@ extern "C" int dvmvs_lstm_gates_parts(const float* gate_parts, int n_parts, long
   DVMVS_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && C % 32 == 0, "lstm_gates: bad shape (C must be a multiple of 32)");
   DVMVS_REQUIRE(n_parts >= 1 && (n_parts == 1 || part_stride >= (long long)B * h * w * 4 * C), "lstm_gates: bad partial-sum layout");
   const int hw = h * w;
+  cudaStream_t st = (cudaStream_t)stream;
+  // few (clip, 32-channel) blocks: narrow blocks of 8 channels put four times as many CTAs on the reduction of the partial sums
+  const bool narrow = (B * (C / 32) < 74) && hw <= 8 * 4 * 16;
+  if (narrow) {
+    const int ppw = (hw + kLstmWarps * 4 - 1) / (kLstmWarps * 4);
+    dim3 grid(C / 8, B);
+    if (ppw <= 2) launch_k(lstm_gates_kernel<2, 8>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, (size_t)part_stride, addend, c_in, h_out, c_out, hw, C);
+    else if (ppw <= 4) launch_k(lstm_gates_kernel<4, 8>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, (size_t)part_stride, addend, c_in, h_out, c_out, hw, C);
+    else launch_k(lstm_gates_kernel<16, 8>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, (size_t)part_stride, addend, c_in, h_out, c_out, hw, C);
+    return check_launch("lstm_gates_kernel");
+  }
   const int ppw = (hw + kLstmWarps - 1) / kLstmWarps;
   DVMVS_REQUIRE(ppw <= 64, "lstm_gates: h*w=%d too large (bottleneck maps up to 512 positions)", hw);
   dim3 grid(C / 32, B);
-  cudaStream_t st = (cudaStream_t)stream;
   const size_t ps = (size_t)part_stride;
-  if (ppw <= 2) launch_k(lstm_gates_kernel<2>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
-  else if (ppw <= 8) launch_k(lstm_gates_kernel<8>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
-  else if (ppw <= 16) launch_k(lstm_gates_kernel<16>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
-  else launch_k(lstm_gates_kernel<64>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
+  if (ppw <= 2) launch_k(lstm_gates_kernel<2, 32>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
+  else if (ppw <= 8) launch_k(lstm_gates_kernel<8, 32>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
+  else if (ppw <= 16) launch_k(lstm_gates_kernel<16, 32>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
+  else launch_k(lstm_gates_kernel<64, 32>, grid, dim3(32 * kLstmWarps), 0, st, gate_parts, n_parts, ps, addend, c_in, h_out, c_out, hw, C);
   return check_launch("lstm_gates_kernel");
 }
 

@@ -434,15 +434,19 @@ def test_pipeline_keyframe_and_cuda_graph_engine_match_script_sequence(oracle, s
             assert oracle.rel_l1_inverse_depth(got.cpu().numpy(), e) <= 1e-6, "pipeline with %d stages" % (pi + 2)
 
 
-def test_feature_cache_reproduces_recomputed_features(oracle, synth):
+@pytest.mark.parametrize("backend,terms,tol", [("fp32", 3, 1e-5), ("tc", 3, 1e-5), ("tc", 1, 1e-4)])
+def test_feature_cache_reproduces_recomputed_features(oracle, synth, backend, terms, tol):
     """measurement features taken from the feature cache (keyed by frame id) instead of re-running
     FeatureExtractor + FeatureShrinker give the script sequence's depths -- eager keyframe() and the pipelined engine,
     cold cache (misses computed from the images), steady state (all hits, no measurement images passed) and FIFO
     eviction with the smallest legal capacity."""
     from dvmvs import pipeline
+    from dvmvs import _ops as ops
     H, W, D, M = 64, 96, 64, 2
     w = helpers.oracle_weights(oracle, synth, 13, n_depth_levels=D)
-    mods = helpers.build_product_modules(w, n_depth_levels=D)
+    old_backend = ops.conv_backend()
+    ops.set_conv_backend(backend, terms=terms, stride2=True)        # tc / 1 term: a different FeatureExtractor batch changes the split-K
+    mods = helpers.build_product_modules(w, n_depth_levels=D)      # summation order, and a 1-ulp fp32 difference can flip an fp16 operand
     clip = synth.make_clip(9, 7, H, W, M)
     K = _cuda(clip["K"])[None]
     st_a, st_b = helpers.ProductState(), pipeline.KeyframeState()
@@ -456,7 +460,7 @@ def test_feature_cache_reproduces_recomputed_features(oracle, synth):
                     [_cuda(clip["poses"][j])[None] for j in meas_i], K)
             a, st_a = helpers.product_fusionnet_step(mods, st_a, *args, n_depth_levels=D)
             b, st_b = pipeline.keyframe(mods, st_b, *args, n_depth_levels=D, cache=cache, reference_id=ref_i, measurement_ids=meas_i)
-            assert oracle.rel_l1_inverse_depth(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
+            assert oracle.rel_l1_inverse_depth(b.cpu().numpy(), a.cpu().numpy()) <= tol
             expected.append(a.cpu().numpy())
             for pi, pipe in enumerate(pipes):
                 out = torch.empty((1, H, W), dtype=torch.float32, device=DEV)
@@ -470,10 +474,11 @@ def test_feature_cache_reproduces_recomputed_features(oracle, synth):
     for pi, pipe in enumerate(pipes):
         assert pipe.cache.misses == M and pipe.cache.hits == M * (len(clip["frames"]) - 1)
         for e, got in zip(expected, piped[pi]):
-            assert oracle.rel_l1_inverse_depth(got.cpu().numpy(), e) <= 1e-5, "cached pipeline %d" % pi
+            assert oracle.rel_l1_inverse_depth(got.cpu().numpy(), e) <= tol, "cached pipeline %d" % pi
     # a miss without an image is an error, as is a cache-less engine handed ids
     with pytest.raises(ValueError):
         pipes[0].submit(args[0], args[1], [None] * M, args[3], K, reference_id=10 ** 6, measurement_ids=[10 ** 6 + 1, 10 ** 6 + 2])
+    ops.set_conv_backend(old_backend, terms=3)
 
 
 def test_online_engine_reproduces_shipped_golden_with_keyframe_buffer_and_feature_cache():

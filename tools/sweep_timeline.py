@@ -11,7 +11,7 @@ for _p in (REPO, os.path.join(REPO, "deep-video-mvs_b200")):
         sys.path.insert(0, _p)
 import torch  # noqa: E402
 
-NAMES = {0: "start", 1: "barriers+tmem", 2: "pdl_wait", 3: "matrices", 4: "geometry", 5: "plan", 6: "first loads issued", 7: "first band published", 56: "plan: scratch ready (round 1)", 57: "plan: boxes merged", 58: "plan: rows scanned", 59: "[rounds * 1000 + chunks]", 62: "write-out done", 63: "exit barrier"}
+NAMES = {0: "start", 1: "planner: start of first tile", 2: "consumers: waiting for the first tile's plan", 3: "matrices", 4: "geometry", 5: "planner: first tile planned", 6: "consumers: plan received", 7: "reference tile ready", 56: "plan: scratch ready (round 1)", 57: "plan: boxes merged", 58: "plan: rows scanned", 59: "[rounds * 1000 + chunks]", 62: "write-out done", 63: "exit barrier"}
 for k in range(9):
     for j, n in enumerate(("wait mma", "mma done", "next loads issued", "C1 done", "published", "look-ups done")):
         NAMES[8 + 6 * k + j] = "chunk %d: %s" % (k, n)
@@ -49,7 +49,7 @@ def main():
         t0 = int(row[0])
         print("CTA %d (cycles since its start; SM clock)" % cta)
         prev = 0
-        order = [0, 1, 2, 3, 4, 56, 57, 58, 5, 59] + list(range(6, 56)) + [62, 63]
+        order = [0, 1, 2, 5, 6, 7] + list(range(8, 56)) + [62]
         for slot in order:
             v = int(row[slot])
             if v == 0:
