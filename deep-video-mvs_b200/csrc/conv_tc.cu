@@ -31,7 +31,7 @@ namespace dvmvs {
 // ----------------------------------------------------------------------------------------------- parameters
 constexpr int kTcThreads = 192;
 constexpr int kTileM = 128;
-constexpr int kAStageBytes = kTileM * 128;   // one activation tile (64-channel chunk); 32-channel chunks use half
+
 
 struct TcParams {
   CUtensorMap a_map[3][2];    // [source][hi/lo]
@@ -52,9 +52,6 @@ struct TcParams {
   float aux_mult, aux_base;
   int act;
   float* workspace;           // split-K partial sums [ksplit][out elements]
-  unsigned* tile_counters;    // fused finish: arrival counters, one per (pixel tile, n-block); zero before and after a launch
-  int fused_finish;           // split-K: the last CTA to arrive for a tile reduces the partials in split order + epilogue
-  int cluster_reduce;         // split-K splits form one thread-block cluster and reduce through distributed shared memory
   int hi_only;                // fp16 outputs: write the hi plane only (every consumer runs 1-term products)
   int cat;                    // terms == 3 as two MMAs per K step: x_hi * [w_hi ; w_lo] (2*BLOCK_N columns) + x_lo * w_hi
   int num_stages, stage_bytes, a_bytes, w_bytes;   // smem ring geometry (runtime: sized by the widest K chunk in use)
@@ -290,12 +287,6 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
       if (!valid || cbase >= p.Cout) continue;
       if (vec8) {
         if (split) {
-          if (p.cluster_reduce) {   // partial tile -> own shared memory ([8-column group][row][8]); reduced across the cluster below
-            float4* st = reinterpret_cast<float4*>(base_ptr + ((size_t)(c0 >> 3) * kTileM + row) * 32);
-            st[0] = make_float4(v[0], v[1], v[2], v[3]);
-            st[1] = make_float4(v[4], v[5], v[6], v[7]);
-            continue;
-          }
           // partial sums of this tap range; conv_tc_finish_kernel reduces the splits in fixed order
           *reinterpret_cast<float4*>(wsp_row + cbase) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(wsp_row + cbase + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -322,71 +313,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
         }
       }
     }
-    if (split && p.fused_finish) __threadfence();      // this thread's partial sums are visible before the CTA signs in
     tc_fence_before();
-  }
-  if (p.fused_finish) {
-    // ---- split-K, fused finish: every split has published its fp32 partial tile; the LAST CTA to arrive for this
-    // (pixel tile, n-block) -- an atomic counter that cleans itself for the next launch -- sums the partials in split order
-    // (deterministic, same order as conv_tc_finish_kernel) and runs the epilogue.  Saves the finishing launch.
-    volatile uint32_t* last_flag = tmem_slot + 1;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned* slot = p.tile_counters + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-      const unsigned prev = atomicAdd(slot, 1u);
-      const bool last = prev + 1u == (unsigned)p.ksplit;
-      if (last) *slot = 0u;
-      *last_flag = last ? 1u : 0u;
-    }
-    __syncthreads();
-    if (*last_flag && warp >= 2) {
-      __threadfence();
-      const int q = warp & 3;
-      const int row = q * 32 + lane;
-      const int ty = row / p.tile_w, tx = row - ty * p.tile_w;
-      const int oy = oy0 + ty, ox = ox0 + tx;
-      if (oy < p.Hout && ox < p.Wout) {
-        const size_t pix = ((size_t)b * p.Hout + oy) * p.Wout + ox;
-        const size_t plane_stride = (size_t)p.B * p.Hout * p.Wout * p.Cout;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
-          const int cbase = n0 + c0;
-          if (cbase >= p.Cout) break;
-          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          const float* src = p.workspace + pix * p.Cout + cbase;
-          for (int sp = 0; sp < p.ksplit; ++sp, src += plane_stride) {
-            const float4 a0 = __ldcg(reinterpret_cast<const float4*>(src)), a1 = __ldcg(reinterpret_cast<const float4*>(src + 4));
-            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-          }
-          tc_emit8(p, v, b, oy, ox, cbase);
-        }
-      }
-    }
-  }
-  if (p.cluster_reduce) {
-    // split-K over the CTAs of this cluster (blockIdx.z): every CTA has parked its fp32 partial tile in its own shared
-    // memory; CTA `rank` now sums (row, 8-column) units rank, rank + z, ... over all peers in rank order (deterministic,
-    // same order as conv_tc_finish_kernel) through distributed shared memory and runs the epilogue on them.
-    cluster_sync_all();
-    if (warp >= 2) {
-      const uint32_t z = (uint32_t)p.ksplit, rank = cluster_ctarank();
-      const int units = kTileM * (BLOCK_N >> 3);
-      for (int u = (int)rank + (int)z * (int)(threadIdx.x - 64); u < units; u += (int)z * 128) {
-        const int g = u >> 7, r = u & (kTileM - 1);
-        const int ty = r / p.tile_w, tx = r - ty * p.tile_w;
-        const int oy = oy0 + ty, ox = ox0 + tx, cbase = n0 + g * 8;
-        if (oy >= p.Hout || ox >= p.Wout || cbase >= p.Cout) continue;
-        const uint32_t local = base + (uint32_t)(g * kTileM + r) * 32u;
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (uint32_t k = 0; k < z; ++k) {
-          const uint32_t remote = cluster_map_shared(local, k);
-          const float4 a0 = ld_cluster_f4(remote), a1 = ld_cluster_f4(remote + 16);
-          v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-        }
-        tc_emit8(p, v, b, oy, ox, cbase);
-      }
-    }
-    cluster_sync_all();      // no CTA may exit (and release its shared memory) while a peer still reads it
   }
   __syncthreads();
   if (warp == 1) {
@@ -633,35 +560,6 @@ static int launch_tc(TcParams& p, dim3 grid, int kc_max, cudaStream_t s) {
   stages = max(2, min(kMaxStages, stages));
   p.num_stages = stages;
   const int smem = stages * p.stage_bytes + overhead;
-  if (p.cluster_reduce) {
-    // the splits of one output tile (gridDim.z) form a cluster and reduce through distributed shared memory; needs the
-    // partial tile to fit in the (by then idle) stage ring and the cluster to be schedulable -- else the workspace path
-    static int cluster_ok[17] = {0};       // per cluster size: 0 unknown, 1 usable, -1 not
-    const int z = (int)grid.z;
-    bool ok = z <= 16 && kTileM * BLOCK_N * 4 <= stages * p.stage_bytes;
-    if (ok && cluster_ok[z] == 0) {
-      static PerDeviceOnce np_set;
-      if (np_set.first()) {
-        cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      }
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kMaxSmemBytes;   // worst case: 1 CTA per SM
-      cudaLaunchAttribute a[1];
-      a[0].id = cudaLaunchAttributeClusterDimension;
-      a[0].val.clusterDim.x = 1; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = (unsigned)z;
-      cfg.attrs = a; cfg.numAttrs = 1;
-      int n_clusters = 0;
-      cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, conv_tc_kernel<BLOCK_N>, &cfg);
-      cluster_ok[z] = (e == cudaSuccess && n_clusters > 0) ? 1 : -1;
-      if (e != cudaSuccess) cudaGetLastError();
-    }
-    ok = ok && cluster_ok[z] == 1;
-    if (ok) {
-      launch_k_cluster(conv_tc_kernel<BLOCK_N>, grid, dim3(kTcThreads), (size_t)smem, s, (unsigned)z, p);
-      return check_launch("conv_tc_kernel(cluster)");
-    }
-    p.cluster_reduce = 0;
-  }
   launch_k(conv_tc_kernel<BLOCK_N>, grid, dim3(kTcThreads), (size_t)smem, s, p);
   return check_launch("conv_tc_kernel");
 }
@@ -738,10 +636,8 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   const int ctas = p.tiles_x * p.tiles_y * d->B * n_tiles;
   p.ksplit = 1;
   const int n_taps = d->ksize * d->ksize;
-  // head of the workspace: arrival counters of the fused split-K finish (the owner zero-initialises the buffer once, the
-  // kernel leaves them zero); the partial sums follow
+  // the first 16 KiB of the workspace are reserved (historical: arrival counters); the partial sums follow
   const long long counter_bytes = 16384;
-  p.tile_counters = reinterpret_cast<unsigned*>(d->workspace);
   p.workspace = d->workspace ? reinterpret_cast<float*>(reinterpret_cast<char*>(d->workspace) + counter_bytes) : nullptr;
   const size_t out_elems = (size_t)d->B * p.Hout * p.Wout * d->Cout;
   if (d->allow_split && d->workspace && d->workspace_bytes > counter_bytes && ctas < 74 && n_taps > 1) {
@@ -753,17 +649,10 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   dim3 grid(p.tiles_x * p.tiles_y * d->B, n_tiles, p.ksplit);
   static const bool cat_env = []() { const char* e = getenv("DVMVS_TC_CAT"); return !(e && e[0] == '0'); }();
   p.cat = (d->terms == 3 && cat_env) ? 1 : 0;
-  // opt-in (DVMVS_CLUSTER_SPLITK=1): measured SLOWER than partials + finish kernel on B200 (c2 keyframe 1.52 vs 1.33 ms):
-  // clusters of 5 / 9 one-CTA-per-SM blocks must be co-scheduled inside a GPC, which costs more (extra waves, two
-  // cluster barriers) than the 21 short finish launches it removes.  Kept for the record and for larger split counts.
-  static const bool cluster_env = []() { const char* e = getenv("DVMVS_CLUSTER_SPLITK"); return e && e[0] == '1'; }();
-  p.cluster_reduce = (p.ksplit > 1 && cluster_env && d->Cout % 8 == 0) ? 1 : 0;
-  // opt-in (DVMVS_SPLITK_FUSED=1): measured SLOWER on B200 (c2: 1 110 vs 1 677 keyframes/s pipelined, 1.58 vs 1.14 ms sequential):
-  // the one CTA that finishes a tile walks ksplit x BLOCK_N/8 dependent L2 round trips with 128 threads, while the separate
-  // finishing kernel spreads the same reads over the whole GPU and overlaps the next kernel's prologue (PDL).
-  static const bool fused_env = []() { const char* e = getenv("DVMVS_SPLITK_FUSED"); return e && e[0] == '1'; }();
-  p.fused_finish = (p.ksplit > 1 && !p.cluster_reduce && fused_env && d->Cout % 8 == 0 &&
-                    (long long)grid.x * grid.y * (long long)sizeof(unsigned) <= counter_bytes) ? 1 : 0;
+  // Measured and removed (round 1, profiles/r01_bench_splitk_*.json): reducing the splits inside a thread-block cluster through
+  // distributed shared memory (1.52 vs 1.33 ms per keyframe: clusters of 5 / 9 one-CTA-per-SM blocks schedule worse than the 21
+  // short finishing launches they save) and a fused finish by the last-arriving CTA (1 110 vs 1 677 keyframes/s: one CTA walks
+  // ksplit x BLOCK_N/8 dependent L2 round trips where the finishing kernel spreads them over the GPU under the next prologue).
   int rc;
   if (d->block_n == 32) rc = launch_tc<32>(p, grid, kc_max, s);
   else if (d->block_n == 64) rc = launch_tc<64>(p, grid, kc_max, s);
@@ -771,10 +660,10 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   if (rc != DVMVS_OK) return rc;
   if (d->defer_finish) {
     // the caller's own epilogue kernel sums the split-K partial sums (dvmvs_lstm_gates_parts): only legal when this launch split
-    DVMVS_REQUIRE(p.ksplit > 1 && !p.cluster_reduce && !p.fused_finish, "conv2d_tc: defer_finish without a split-K launch (ask dvmvs_conv2d_tc_ksplit first)");
+    DVMVS_REQUIRE(p.ksplit > 1, "conv2d_tc: defer_finish without a split-K launch (ask dvmvs_conv2d_tc_ksplit first)");
     return DVMVS_OK;
   }
-  if (p.ksplit > 1 && !p.cluster_reduce && !p.fused_finish) {     // launch_tc clears cluster_reduce when it had to fall back to the workspace path
+  if (p.ksplit > 1) {
     launch_k(conv_tc_finish_kernel, dim3((unsigned)((out_elems + 255) / 256)), dim3(256), 0, s, p);
     return check_launch("conv_tc_finish_kernel");
   }
@@ -785,12 +674,6 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
 // epilogue (defer_finish) size its reads.  Mirrors the decision above.
 extern "C" int dvmvs_conv2d_tc_ksplit(const dvmvs_conv_tc_desc* d) {
   if (!d || !(d->ksize == 1 || d->ksize == 3 || d->ksize == 5) || d->B <= 0) return 1;
-  static const bool alt_env = []() {
-    const char* a = getenv("DVMVS_CLUSTER_SPLITK");
-    const char* b = getenv("DVMVS_SPLITK_FUSED");
-    return (a && a[0] == '1') || (b && b[0] == '1');
-  }();
-  if (alt_env) return 1;                         // the experimental reductions finish inside the kernel
   const int pad = (d->ksize - 1) / 2;
   const int Hout = (d->Hin + 2 * pad - d->ksize) / d->stride + 1, Wout = (d->Win + 2 * pad - d->ksize) / d->stride + 1;
   const int tile_w = (Wout <= 8 && Hout > 8) ? 8 : 16, tile_h = kTileM / tile_w;

@@ -29,7 +29,12 @@ class LossMeter(object):
 
 def calculate_loss(groundtruth, prediction):
     """losses.py:53-82 for one prediction scale: (l1, huber, l1_inv, l1_rel, valid_count) -- the four sums as 0-dim CUDA
-    tensors, the count as a python int (the reference's `valid_mask.nonzero().size()[0]` synchronises too)."""
+    tensors, the count as a python int (the reference's `valid_mask.nonzero().size()[0]` synchronises too).
+
+    NOT differentiable here: the sums are monitoring values (the fused kernel marks them non-differentiable).  The reference's
+    calculate_loss returns sums one can back-propagate through; in this package the optimizer loss comes from
+    update_losses(..., is_training=True) / dvmvs.training.multi_scale_depth_loss, which is what run-training.py:269-278 uses.  A
+    caller that builds its own loss from these sums gets `does not require grad` from autograd, not silent zeros."""
     _, sums = multi_scale_depth_loss([prediction], [1.0], groundtruth, "L1")
     return sums[0, 0], sums[0, 1], sums[0, 2], sums[0, 3], int(sums[0, 4].item())
 

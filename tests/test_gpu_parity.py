@@ -884,29 +884,3 @@ def test_device_preprocessing_feeds_the_network_like_the_host_path(oracle, synth
         a, _ = pipeline.keyframe(mods, pipeline.KeyframeState(), host[0], poses[0], host[1:], poses[1:], K, n_depth_levels=D)
         b, _ = pipeline.keyframe(mods, pipeline.KeyframeState(), dev[0], poses[0], dev[1:], poses[1:], K, n_depth_levels=D)
     assert oracle.rel_l1_inverse_depth(b.cpu().numpy(), a.cpu().numpy()) <= 1e-4     # host side may use IPP's coefficients (see above)
-
-
-def test_fused_split_k_finish_variant_matches():
-    """The opt-in fused split-K finish (DVMVS_SPLITK_FUSED=1: the last CTA to arrive for a tile reduces the partials in
-    split order and runs the epilogue, no finishing kernel; measured slower, off by default) must pass the tensor-core conv
-    cases too.  The switch is read once per process, so they run again in a child process."""
-    import os, subprocess, sys
-    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, DVMVS_SPLITK_FUSED="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(repo, "tests", "test_gpu_parity.py"), "-q", "-x", "-p", "no:cacheprovider",
-                        "-k", "conv2d_tc_vs_fp32_kernel_and_torch or (tensor_core_backend_vs_oracle and tiny)"], env=env, cwd=repo,
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-
-
-def test_cluster_split_k_variant_matches():
-    """The opt-in thread-block-cluster split-K (DVMVS_CLUSTER_SPLITK=1: partial tiles reduced through distributed shared
-    memory instead of the workspace + finish kernel) must give the same results; the switch is read once per process, so
-    the tensor-core conv cases run again in a child process."""
-    import os, subprocess, sys
-    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, DVMVS_CLUSTER_SPLITK="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(repo, "tests", "test_gpu_parity.py"), "-q", "-x", "-p", "no:cacheprovider",
-                        "-k", "conv2d_tc_vs_fp32_kernel_and_torch or tensor_core_backend_vs_oracle"], env=env, cwd=repo,
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
