@@ -647,6 +647,8 @@ def best_thread_count(oracle, w, clip):
         t, _ = oracle_frames(oracle, w, clip, 0, 2)
         trials[n] = t[1]
         log("cpu threads %d: %.2f s per keyframe" % (n, t[1]))
+        if t[1] > min(trials.values()):          # past the knee: more threads only add OpenMP barrier cost (64 threads: 1.2 - 60 s per keyframe)
+            break
     best = min(trials, key=trials.get)
     try:
         os.sched_setaffinity(0, cores[:best])
@@ -812,9 +814,9 @@ def main():
             os.close(saved_stdout)
     result = run_ours(args, rank, world, local_rank)
     if rank == 0:
-        if args.gpu_eager:
+        if args.gpu_eager and world == 1:
             result["gpu_eager_baseline"] = gpu_eager_baseline(6, args.weights)
-        if args.cpu_frames > 0:
+        if args.cpu_frames > 0 and world == 1:          # the CPU baseline is an N = 1 entry (the other ranks would idle through it)
             os.environ.pop("OMP_NUM_THREADS", None)
             try:
                 os.sched_setaffinity(0, range(os.cpu_count() or 1))      # the GPU arm pinned this process to one NUMA node
