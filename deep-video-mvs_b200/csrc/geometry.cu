@@ -804,7 +804,7 @@ __global__ void depth_reproject_kernel(const float* __restrict__ cur_pose, const
 
 using namespace dvmvs;
 
-extern "C" int dvmvs_abi_version(void) { return 5; }
+extern "C" int dvmvs_abi_version(void) { return 6; }
 
 // Programmatic dependent launch for the launches that follow (process-wide): 1 on, 0 off, -1 back to the default
 // (on unless DVMVS_PDL=0).  What a launch was enqueued / captured with stays with it.

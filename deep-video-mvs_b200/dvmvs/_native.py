@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdvmvs_sm100.so")
 
 c_float_p = ctypes.c_void_p
-ABI_VERSION = 5      # dvmvs_abi_version() the descriptor mirrors below were written for; bump with every descriptor / signature change
+ABI_VERSION = 6      # dvmvs_abi_version() the descriptor mirrors below were written for; bump with every descriptor / signature change
 _lib = None
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
@@ -20,7 +20,7 @@ LOSS_L1, LOSS_L1_INV, LOSS_L1_REL, LOSS_HUBER = 0, 1, 2, 3
 EXPORTED_SYMBOLS = [
     "dvmvs_abi_version", "dvmvs_set_programmatic_launch", "dvmvs_last_error_string", "dvmvs_kernel_launch_count", "dvmvs_plane_sweep_fused",
     "dvmvs_hidden_warp", "dvmvs_depth_reproject", "dvmvs_conv2d", "dvmvs_conv2d_tc", "dvmvs_conv2d_halo", "dvmvs_split_blocked", "dvmvs_split_planes", "dvmvs_stem_conv", "dvmvs_dwconv2d", "dvmvs_lstm_gates",
-    "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw", "dvmvs_preprocess_rgb",
+    "dvmvs_upsample2x", "dvmvs_nchw_to_nhwc", "dvmvs_nhwc_to_nchw", "dvmvs_preprocess_rgb", "dvmvs_tsdf_integrate",
     "dvmvs_plane_sweep_backward", "dvmvs_hidden_warp_backward", "dvmvs_lstm_gates_backward", "dvmvs_depth_loss_forward",
     "dvmvs_depth_loss_backward", "dvmvs_plane_sweep_fused_h16", "dvmvs_plane_sweep_tc", "dvmvs_lstm_gates_parts", "dvmvs_conv2d_tc_ksplit", "dvmvs_plane_sweep_tc_set_timeline",
 ]
@@ -126,6 +126,9 @@ def lib():
         L.dvmvs_preprocess_rgb.argtypes = [p, i, i, i, i, i, i, p, i, i, i, f, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), p]
         L.dvmvs_nchw_to_nhwc.argtypes = [p, p, i, i, i, i, p]
         L.dvmvs_nhwc_to_nchw.argtypes = [p, p, i, i, i, i, p]
+        d = ctypes.c_double
+        L.dvmvs_tsdf_integrate.argtypes = [p, p, p, i, i, i, ctypes.POINTER(ctypes.c_float), d, d, p, i, p, i, i, i,
+                                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double), d, p, p]
         L.dvmvs_plane_sweep_backward.argtypes = [p, p, p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
         L.dvmvs_hidden_warp_backward.argtypes = [p, p, p, p, p, p, i, i, i, i, f, p]
         L.dvmvs_lstm_gates_backward.argtypes = [p, p, p, p, p, p, i, i, i, i, p]

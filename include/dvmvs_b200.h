@@ -309,6 +309,25 @@ int dvmvs_depth_loss_backward(const float* const* preds_host, float* const* grad
 int dvmvs_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, dvmvs_stream_t stream);
 int dvmvs_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, dvmvs_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * TSDF fusion of the predicted depth maps: replaces TSDFVolume.integrate of the
+ * reference's sample-data/run-tsdf-reconstruction.py:220-323 -- both its inline pycuda kernel (:80-152) and the
+ * numba / numpy CPU path (:181-218, :283-323) it runs when pycuda is absent.  Arithmetic follows the CPU path
+ * (mixed float32 / float64) so that volumes are bit-identical to it.
+ *   tsdf_vol, weight_vol, color_vol : DEVICE fp32 [dim_x][dim_y][dim_z] (C order), updated in place; initial state
+ *                                     1 / 0 / 0 (:57-61).  color is folded b*65536 + g*256 + r.
+ *   vol_origin3   : HOST, 3 floats (:50)            voxel_size, trunc_margin (= 5 * voxel_size, :46) : doubles
+ *   color_im      : DEVICE [im_h][im_w][3] RGB, uint8 (color_is_u8 = 1) or fp32
+ *   depth_im      : DEVICE [im_h][im_w], fp32 or fp64 (depth_is_f64 = 1); 0 = invalid
+ *   intr4         : HOST fx, fy, cx, cy as the float32 values of cam_intr.astype(float32) (:197-199)
+ *   world_to_cam16: HOST, row-major float64 inv(cam_pose) (:285; the 4x4 inverse stays host logic as in the reference)
+ *   updated_count : optional DEVICE counter incremented by the number of voxels updated (NULL = none)          */
+int dvmvs_tsdf_integrate(float* tsdf_vol, float* weight_vol, float* color_vol, int dim_x, int dim_y, int dim_z,
+                         const float* vol_origin3, double voxel_size, double trunc_margin, const void* color_im,
+                         int color_is_u8, const void* depth_im, int depth_is_f64, int im_h, int im_w, const float* intr4,
+                         const double* world_to_cam16, double obs_weight, unsigned long long* updated_count,
+                         dvmvs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

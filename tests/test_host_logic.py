@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), "libdvmvs_sm100.so does not export %s" % sym
     assert sorted(N.EXPORTED_SYMBOLS) == declared
-    assert lib.dvmvs_abi_version() == N.ABI_VERSION == 5
+    assert lib.dvmvs_abi_version() == N.ABI_VERSION == 6
 
 
 def test_desc_structs_match_header_field_order():

@@ -1,0 +1,90 @@
+"""Times dvmvs.tsdf.TSDFVolume.integrate on a production-sized volume with CUDA events and puts it on
+the HBM roofline; the numpy oracle (the reference's CPU path restated) is timed beside it on one frame.
+
+    python tools/tsdf_bench.py [--voxel 0.04] [--frames 20] [--out profiles/r02_tsdf_bench.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "deep-video-mvs_b200"))
+sys.path.insert(0, os.path.join(REPO, "oracle"))
+
+
+def frame(i, h, w, rng):
+    yy, xx = np.mgrid[0:h, 0:w]
+    depth = (2.0 + 0.8 * np.sin(xx / 40.0 + i) * np.cos(yy / 30.0) + 0.01 * rng.rand(h, w)).astype(np.float32)
+    color = rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+    pose = np.eye(4)
+    c, s = np.cos(0.03 * i), np.sin(0.03 * i)
+    pose[:3, :3] = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+    pose[:3, 3] = [0.05 * i, -0.02 * i, 0.01 * i]
+    return color, depth, pose
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--voxel", type=float, default=0.04)
+    ap.add_argument("--frames", type=int, default=20)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    from dvmvs.tsdf import TSDFVolume
+    import tsdf_oracle
+    h, w = 256, 320
+    K = np.array([[250.0, 0, 160.3], [0, 251.0, 127.6], [0, 0, 1]])
+    bounds = np.array([[-4.0, 4.0], [-3.2, 3.2], [0.0, 4.8]])
+    rng = np.random.RandomState(5)
+    frames = [frame(i, h, w, rng) for i in range(a.frames)]
+    vol = TSDFVolume(bounds, a.voxel)
+    n_vox = int(np.prod(vol._vol_dim))
+    dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(d).cuda(), p) for c, d, p in frames]
+    for c, d, p in dev[:3]:
+        vol.integrate(c, d, K, p)
+    torch.cuda.synchronize()
+    before = vol.updated_voxels()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    times = []
+    for c, d, p in dev:                                          # resident inputs, L2 flushed between frames
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        vol.integrate(c, d, K, p)
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+    updated = (vol.updated_voxels() - before) / len(dev)
+    t = float(np.median(times))
+    t0 = time.perf_counter()                                     # host arrays: pinned upload + launch per frame
+    for c, d, p in frames:
+        vol.integrate(c, d, K, p)
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / len(frames)
+    orc = tsdf_oracle.TSDFVolume(bounds, a.voxel)
+    t0 = time.perf_counter()
+    orc.integrate(frames[0][0], frames[0][1], K, frames[0][2], 1.0)
+    t_cpu = time.perf_counter() - t0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 0) or 0) or None
+    alg = 24.0 * updated + h * w * 7
+    rec = {"kernel": "tsdf_integrate_kernel<u8,f32>", "voxels": n_vox, "vol_dim": [int(v) for v in vol._vol_dim], "image": [h, w],
+           "updated_voxels_per_frame": updated, "kernel_us": t * 1e6, "frames_per_s_resident": 1.0 / t,
+           "frames_per_s_host_inputs": 1.0 / t_e2e, "algorithmic_bytes": alg, "achieved_GBps": alg / t * 1e-9,
+           "swept_GBps_if_all_voxels_touched": 24.0 * n_vox / t * 1e-9, "peak_GBps": peak, "frac": (alg / t * 1e-9 / peak) if peak else None,
+           "cpu_oracle_s_per_frame": t_cpu, "speedup_vs_cpu_oracle": t_cpu / t}
+    print(json.dumps(rec))
+    if a.out:
+        json.dump(rec, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
