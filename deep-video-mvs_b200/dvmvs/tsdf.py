@@ -36,6 +36,8 @@ class TSDFVolume(object):
         self._vol_bnds = vol_bnds
         self._vol_origin = vol_bnds[:, 0].astype(np.float32)                           # :52
         self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
+            self.device = torch.device("cuda", torch.cuda.current_device())
         shape = tuple(int(d) for d in self._vol_dim)
         self._tsdf_vol = torch.ones(shape, dtype=torch.float32, device=self.device)     # :57-61
         self._weight_vol = torch.zeros(shape, dtype=torch.float32, device=self.device)
