@@ -12,10 +12,19 @@
 //   colour : float32 throughout, rintf, min(255, .) with NaN propagation as np.minimum
 // No multiply-add contraction anywhere a rounding would be skipped (explicit _rn intrinsics).
 //
+// Culling: 98 % of a room-sized volume is outside the frustum or the truncation band of any one frame, and the float64
+// projection (two double divisions) is what the kernel would spend its time on.  Each voxel is therefore first projected in
+// float32 (9 FMAs) and dropped when it is PROVABLY behind the camera or more than a pixel outside the image: the test uses
+// error bounds of the float32 evaluation computed on the host from the volume extent (eps), so a voxel the float64 path would
+// update is never dropped (tests compare whole volumes with the reference bit for bit).  Survivors take the exact path.
+//
 // HBM-bound: one thread per voxel, z fastest (the reference's C-order [x][y][z]) so a warp reads / writes 128 B rows of each
 // of the three volumes; voxels outside the frustum or the truncation band touch no volume memory at all.  Algorithmic bytes:
 // 24 B per UPDATED voxel (tsdf, weight, colour: read + write fp32) + the frame (4 B depth + 3..12 B colour per pixel, L2
 // resident).  The inverse pose, float32 intrinsics and trunc margin arrive by value in the launch parameters.
+#include <math.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dvmvs {
@@ -32,6 +41,10 @@ struct TsdfParams {
   double T[12];           // rows 0..2 of inv(cam_pose)
   double fx, fy, cx, cy;  // float32 intrinsics widened
   unsigned long long* updated;   // optional counter of updated voxels (nullptr = none)
+  float Tf[12];           // float32 copy of T for the conservative pre-test
+  float eps[3];           // bound on |float32 camera coordinate - float64 camera coordinate| per axis over the volume
+  float fxf, fyf, lo_x, hi_x, lo_y, hi_y;   // lo = cx + 1.5, hi = im_w + 1.5 - cx (one pixel of margin on each side)
+  int cull;
 };
 
 __device__ __forceinline__ float np_minimum(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
@@ -54,9 +67,25 @@ __global__ void __launch_bounds__(256) tsdf_integrate_kernel(TsdfParams p) {
     const int z = (int)(idx % p.dim_z);
     const long long xy = idx / p.dim_z;
     const int y = (int)(xy % p.dim_y), x = (int)(xy / p.dim_y);
-    const double wx = (double)__double2float_rn(__dadd_rn((double)p.origin[0], __dmul_rn(p.voxel_size, (double)x)));
-    const double wy = (double)__double2float_rn(__dadd_rn((double)p.origin[1], __dmul_rn(p.voxel_size, (double)y)));
-    const double wz = (double)__double2float_rn(__dadd_rn((double)p.origin[2], __dmul_rn(p.voxel_size, (double)z)));
+    const float wxf = __double2float_rn(__dadd_rn((double)p.origin[0], __dmul_rn(p.voxel_size, (double)x)));
+    const float wyf = __double2float_rn(__dadd_rn((double)p.origin[1], __dmul_rn(p.voxel_size, (double)y)));
+    const float wzf = __double2float_rn(__dadd_rn((double)p.origin[2], __dmul_rn(p.voxel_size, (double)z)));
+    bool candidate = true;
+    if (p.cull) {
+      const float X = fmaf(p.Tf[0], wxf, fmaf(p.Tf[1], wyf, fmaf(p.Tf[2], wzf, p.Tf[3])));
+      const float Y = fmaf(p.Tf[4], wxf, fmaf(p.Tf[5], wyf, fmaf(p.Tf[6], wzf, p.Tf[7])));
+      const float Z = fmaf(p.Tf[8], wxf, fmaf(p.Tf[9], wyf, fmaf(p.Tf[10], wzf, p.Tf[11])));
+      if (Z + p.eps[2] <= 0.f) candidate = false;                 // certainly behind the camera
+      else if (Z - p.eps[2] > 0.f) {                               // certainly in front: test the image borders with slack
+        const float ux = X * p.fxf, uy = Y * p.fyf;
+        const float sx = p.fxf * p.eps[0] + (fabsf(p.lo_x) + fabsf(p.hi_x)) * p.eps[2] + 1e-6f * (fabsf(ux) + (fabsf(p.lo_x) + fabsf(p.hi_x)) * Z);
+        const float sy = p.fyf * p.eps[1] + (fabsf(p.lo_y) + fabsf(p.hi_y)) * p.eps[2] + 1e-6f * (fabsf(uy) + (fabsf(p.lo_y) + fabsf(p.hi_y)) * Z);
+        // pixel < -1.5  <=>  X fx + (cx + 1.5) Z < 0 ;   pixel > w + 0.5  <=>  X fx - (w + 1.5 - cx) Z > 0  (with a pixel to spare)
+        if (ux + p.lo_x * Z < -sx || ux - p.hi_x * Z > sx || uy + p.lo_y * Z < -sy || uy - p.hi_y * Z > sy) candidate = false;
+      }
+    }
+    const double wx = (double)wxf, wy = (double)wyf, wz = (double)wzf;
+    if (candidate) {
     const double cxp = __fma_rn(p.T[3], 1.0, __fma_rn(p.T[2], wz, __fma_rn(p.T[1], wy, __dmul_rn(p.T[0], wx))));
     const double cyp = __fma_rn(p.T[7], 1.0, __fma_rn(p.T[6], wz, __fma_rn(p.T[5], wy, __dmul_rn(p.T[4], wx))));
     const double czp = __fma_rn(p.T[11], 1.0, __fma_rn(p.T[10], wz, __fma_rn(p.T[9], wy, __dmul_rn(p.T[8], wx))));
@@ -87,6 +116,7 @@ __global__ void __launch_bounds__(256) tsdf_integrate_kernel(TsdfParams p) {
         p.color[idx] = __fadd_rn(__fadd_rn(__fmul_rn(nb, 65536.f), __fmul_rn(ng, 256.f)), nr);
       }
     }
+    }
   }
   if (p.updated) {
     const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -116,6 +146,31 @@ extern "C" int dvmvs_tsdf_integrate(float* tsdf_vol, float* weight_vol, float* c
   for (int i = 0; i < 12; ++i) p.T[i] = world_to_cam16[i];
   p.fx = (double)intr4[0]; p.fy = (double)intr4[1]; p.cx = (double)intr4[2]; p.cy = (double)intr4[3];
   p.updated = updated_count;
+  // conservative float32 pre-test: per camera axis r, |fl32 evaluation - exact| <= 2^-20 * (sum_k |T[r][k]| max|w_k| + |T[r][3]|)
+  // (four roundings of 2^-24 each on the products / sums, plus 2^-24 relative on each float32 copy of T: 16x headroom)
+  double maxabs[3];
+  const int dims[3] = {dim_x, dim_y, dim_z};
+  for (int k = 0; k < 3; ++k) {
+    const double a = fabs((double)vol_origin3[k]), b = fabs((double)vol_origin3[k] + voxel_size * (double)dims[k]);
+    maxabs[k] = a > b ? a : b;
+  }
+  bool finite = true;
+  for (int r = 0; r < 3; ++r) {
+    double sum = fabs(p.T[4 * r + 3]);
+    for (int k = 0; k < 3; ++k) sum += fabs(p.T[4 * r + k]) * maxabs[k];
+    p.eps[r] = (float)(sum * 9.5367431640625e-07) + 1e-30f;
+    for (int k = 0; k < 4; ++k) {
+      p.Tf[4 * r + k] = (float)p.T[4 * r + k];
+      finite = finite && isfinite(p.Tf[4 * r + k]);
+    }
+    finite = finite && isfinite(p.eps[r]);
+  }
+  p.fxf = fabsf(intr4[0]); p.fyf = fabsf(intr4[1]);
+  p.lo_x = intr4[2] + 1.5f; p.hi_x = (float)im_w + 1.5f - intr4[2];
+  p.lo_y = intr4[3] + 1.5f; p.hi_y = (float)im_h + 1.5f - intr4[3];
+  // the border inequalities assume positive focal lengths; anything unusual (negative / non-finite) takes the exact path only
+  static const bool cull_env = []() { const char* e = getenv("DVMVS_TSDF_CULL"); return !(e && e[0] == '0'); }();
+  p.cull = (cull_env && finite && intr4[0] > 0.f && intr4[1] > 0.f && isfinite(intr4[2]) && isfinite(intr4[3])) ? 1 : 0;
   const dim3 grid((unsigned)((n + 255) / 256)), block(256);
   cudaStream_t s = (cudaStream_t)stream;
   if (color_is_u8) {

@@ -44,9 +44,27 @@ class TSDFVolume(object):
         self._color_vol = torch.zeros(shape, dtype=torch.float32, device=self.device)
         self._updated = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._origin_c = (ctypes.c_float * 3)(*[float(v) for v in self._vol_origin])
+        self._staging = {}
         self.gpu_mode = True
 
     # ---- the hot path -------------------------------------------------------------------------------------------------
+    def _upload(self, a, name):
+        """Host array -> device through a two-deep ring of pinned staging buffers owned by the volume (allocating pinned
+        memory per frame would cost more than the kernel); a slot is reused only after its previous copy has completed."""
+        key = (name, tuple(a.shape), a.dtype)
+        ring = self._staging.get(key)
+        if ring is None:
+            ring = self._staging[key] = {"next": 0, "slots": [
+                (torch.empty(a.shape, dtype=a.dtype).pin_memory(), torch.empty(a.shape, dtype=a.dtype, device=self.device), torch.cuda.Event())
+                for _ in range(2)]}
+        host, dev, done = ring["slots"][ring["next"]]
+        ring["next"] ^= 1
+        done.synchronize()
+        host.copy_(a)
+        dev.copy_(host, non_blocking=True)
+        done.record()
+        return dev
+
     def _to_device(self, a, allowed, name):
         if isinstance(a, np.ndarray):
             a = torch.from_numpy(np.ascontiguousarray(a))
@@ -55,24 +73,24 @@ class TSDFVolume(object):
         if a.dtype not in allowed:
             a = a.to(allowed[-1])
         if not a.is_cuda:
-            a = a.pin_memory().to(self.device, non_blocking=True) if torch.cuda.is_available() else a
-        elif a.device != self.device:
+            return self._upload(a, name)
+        if a.device != self.device:
             raise RuntimeError("TSDFVolume.integrate: %s lives on %s, the volume on %s" % (name, a.device, self.device))
         return a.contiguous()
 
     def integrate(self, color_im, depth_im, cam_intr, cam_pose, obs_weight=1.):
         """Integrate an RGB-D frame (:220-323).  color_im (H,W,3) RGB uint8 / float; depth_im (H,W) float32 / float64, 0 =
         invalid; cam_intr (3,3); cam_pose (4,4) camera-to-world; obs_weight: weight of this observation."""
-        depth = self._to_device(depth_im, (torch.float64, torch.float32), "depth_im")
-        color = self._to_device(color_im, (torch.uint8, torch.float32), "color_im")
-        if depth.dim() != 2 or tuple(color.shape) != (depth.shape[0], depth.shape[1], 3):
-            raise RuntimeError("TSDFVolume.integrate: expected depth (H,W) and colour (H,W,3), got %s and %s" % (tuple(depth.shape), tuple(color.shape)))
         intr = np.asarray(cam_intr.cpu() if isinstance(cam_intr, torch.Tensor) else cam_intr).astype(np.float32)      # :197
         pose = np.asarray(cam_pose.cpu() if isinstance(cam_pose, torch.Tensor) else cam_pose)
         inv = np.ascontiguousarray(np.linalg.inv(pose), dtype=np.float64)              # :285, host logic as in the reference
         intr4 = (ctypes.c_float * 4)(float(intr[0, 0]), float(intr[1, 1]), float(intr[0, 2]), float(intr[1, 2]))
         inv16 = (ctypes.c_double * 16)(*[float(v) for v in inv.reshape(-1)])
         with torch.cuda.device(self.device):
+            depth = self._to_device(depth_im, (torch.float64, torch.float32), "depth_im")
+            color = self._to_device(color_im, (torch.uint8, torch.float32), "color_im")
+            if depth.dim() != 2 or tuple(color.shape) != (depth.shape[0], depth.shape[1], 3):
+                raise RuntimeError("TSDFVolume.integrate: expected depth (H,W) and colour (H,W,3), got %s and %s" % (tuple(depth.shape), tuple(color.shape)))
             N.check(N.lib().dvmvs_tsdf_integrate(
                 self._tsdf_vol.data_ptr(), self._weight_vol.data_ptr(), self._color_vol.data_ptr(),
                 int(self._vol_dim[0]), int(self._vol_dim[1]), int(self._vol_dim[2]), self._origin_c, self._voxel_size,

@@ -110,3 +110,38 @@ def test_gpu_volume_at_production_size_equals_oracle():
     assert _same(tsdf, orc.tsdf) and _same(color_vol, orc.color)
     assert _same(vol.get_volume_tensors()[1].cpu().numpy(), orc.weight)
     assert vol.updated_voxels() == total and total > 100000
+
+
+def _rot(axis, angle):
+    axis = np.asarray(axis, dtype=np.float64) / np.linalg.norm(axis)
+    Kx = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(angle) * Kx + (1 - np.cos(angle)) * Kx @ Kx
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("offset", [0.0, 150.0])
+def test_gpu_frustum_cull_never_drops_a_voxel_the_reference_updates(offset):
+    """The kernel's float32 pre-test must be conservative: cameras INSIDE the volume, looking along every axis and obliquely
+    (many voxels on the image border and next to the camera plane), volume far from the origin (offset: float32 world
+    coordinates with 1e-5 m resolution), noisy depth.  Whole volumes equal the oracle's."""
+    from dvmvs.tsdf import TSDFVolume
+    rng = np.random.RandomState(23)
+    h, w = 96, 128
+    K = np.array([[100.0, 0, 63.5], [0, 100.0, 47.5], [0, 0, 1]])
+    bounds = np.array([[-2.0, 2.0], [-1.6, 1.6], [-2.0, 2.0]]) + offset
+    vol, orc = TSDFVolume(bounds, 0.04), tsdf_oracle.TSDFVolume(bounds, 0.04)
+    views = [([0, 1, 0], 0.0), ([0, 1, 0], np.pi / 2), ([0, 1, 0], np.pi), ([1, 0, 0], np.pi / 2), ([1, 0, 0], -np.pi / 2),
+             ([1, 1, 0], 0.7), ([1, 2, 3], 2.1), ([0, 0, 1], np.pi / 4)]
+    total = 0
+    for i, (axis, angle) in enumerate(views):
+        depth = (0.3 + 1.5 * rng.rand(h, w)).astype(np.float32)
+        color = rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        pose = np.eye(4)
+        pose[:3, :3] = _rot(axis, angle)
+        pose[:3, 3] = offset + rng.uniform(-0.5, 0.5, size=3)
+        vol.integrate(color, depth, K, pose, obs_weight=1.0 + i)
+        total += orc.integrate(color, depth, K, pose, 1.0 + i)
+    tsdf, color_vol = vol.get_volume()
+    assert _same(vol.get_volume_tensors()[1].cpu().numpy(), orc.weight)
+    assert _same(tsdf, orc.tsdf) and _same(color_vol, orc.color)
+    assert vol.updated_voxels() == total and total > 50000
