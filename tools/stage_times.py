@@ -1,43 +1,89 @@
-"""Stand-alone replay time of every (stage, slot 0) CUDA graph of PipelinedFusionnet at config c2 -- shows which stage
-bounds the pipelined throughput and how much of the gap to sum(stages) is contention.  GPU only."""
-import os, sys, json
-import numpy as np, torch
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "deep-video-mvs_b200"))
-import synth_data as synth
-from dvmvs import pipeline, _ops as ops
-from dvmvs.fusionnet.model import FeatureExtractor, FeatureShrinker, CostVolumeEncoder, LSTMFusion, CostVolumeDecoder
+"""Where does the pipelined engine's keyframe time go?  Builds bench.py's engine (PipelinedFusionnet, 5 stages, tensor-core
+backend, 1 product term, 256 x 256, M = 2, D = 64, seeded weights), then replays each stage's CUDA graph ALONE, back to
+back, and reports microseconds and kernel launches per stage beside the steady-state keyframe period of the whole pipeline.
+The last stage carries the loop dependence (ConvLSTM state + previous depth): the period cannot drop below its latency.
 
-H = W = 256; D = 64; M = 2; dev = torch.device("cuda", 0)
-ops.set_conv_backend("tc", terms=int(os.environ.get("DVMVS_TC_TERMS", "3")), stride2=True)
-mods = {"fe": FeatureExtractor(), "fpn": FeatureShrinker(), "cve": CostVolumeEncoder(), "lstm": LSTMFusion(), "cvd": CostVolumeDecoder()}
-for tag, m in mods.items():
-    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
-    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes, seed=7).items()}, strict=True)
-    m.to(dev).eval()
-clip = synth.make_clip(0, 12, H, W, M)
-T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-frames = [(T(clip["images"][r])[None], T(clip["poses"][r])[None], [T(clip["images"][j])[None] for j in m], [T(clip["poses"][j])[None] for j in m],
-           T(clip["K"])[None]) for r, m in clip["frames"]]
-res = {}
-for ns in [int(a) for a in (sys.argv[1:] or ["3", "5"])]:
-    eng = pipeline.PipelinedFusionnet(mods, batch=1, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=ns)
+    python tools/stage_times.py [--clips 1] [--stages 5] [--out profiles/r02_stage_times.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "deep-video-mvs_b200"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--clips", type=int, default=1)
+    ap.add_argument("--stages", type=int, default=5)
+    ap.add_argument("--reps", type=int, default=50)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    import bench
+    import synth_data as synth
+    from dvmvs import _ops as ops
+    from dvmvs import pipeline
+    from dvmvs.fusionnet.model import CostVolumeDecoder, CostVolumeEncoder, FeatureExtractor, FeatureShrinker, LSTMFusion
+    ops.set_conv_backend("tc", terms=1, stride2=True)
+    dev = torch.device("cuda", 0)
+    H, W, D, M = bench.H, bench.W, bench.D, bench.M
+    mods = {"fe": FeatureExtractor(), "fpn": FeatureShrinker(), "cve": CostVolumeEncoder(), "lstm": LSTMFusion(), "cvd": CostVolumeDecoder()}
+    for m in mods.values():
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(shapes, seed=7).items()}, strict=True)
+        m.to(dev).eval()
+    n_frames = 40
+    clips = [synth.make_clip(c, n_frames, H, W, M) for c in range(a.clips)]
+    frames = []
+    for t in range(n_frames):
+        ref, rpose, meas, mpose, K = bench.stack_frame(clips, t)
+        frames.append((torch.from_numpy(ref).to(dev), torch.from_numpy(rpose).to(dev), [torch.from_numpy(x).to(dev) for x in meas],
+                       [torch.from_numpy(p).to(dev) for p in mpose], torch.from_numpy(K).to(dev)))
+    eng = pipeline.PipelinedFusionnet(mods, batch=a.clips, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=a.stages)
+    out = torch.empty((a.clips, H, W), dtype=torch.float32, device=dev)
     with torch.no_grad():
-        for f in frames[:2 * ns + 2]:
-            eng.submit(*f)
-        eng.synchronize(); torch.cuda.synchronize()
-        slot = eng.slots[0]
-        per = []
-        for i in range(ns):
-            g = slot["graph"][i][True if i == ns - 1 else False]
-            s = eng.streams[i]
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(s):
-                for _ in range(5): g.replay()
-                a.record(s)
-                for _ in range(50): g.replay()
-                b.record(s)
+        eng.prime(*frames[0])
+        for t in range(8):
+            eng.submit(*frames[t], out=out)
+        eng.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(eng.stream_a)
+        for t in range(8, n_frames):
+            eng.submit(*frames[t], out=out)
+        e1.record(eng.stream_b)
+        eng.synchronize()
+        torch.cuda.synchronize()
+        period = e0.elapsed_time(e1) * 1e3 / (n_frames - 8)
+    stages = []
+    slot = eng.slots[0]
+    last = a.stages - 1
+    for i in range(a.stages):
+        g = slot["graph"][i][True if i == last else False]
+        s = eng.streams[i]
+        with torch.cuda.stream(s):
+            for _ in range(5):
+                g.replay()
             s.synchronize()
-            per.append(a.elapsed_time(b) / 50 * 1e3)
-        res[ns] = {"stage_us": [round(x, 1) for x in per], "sum_us": round(sum(per), 1), "kernels": eng._kernels}
-print(json.dumps(res))
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(s)
+            for _ in range(a.reps):
+                g.replay()
+            q1.record(s)
+            s.synchronize()
+        stages.append({"stage": i, "us_alone": q0.elapsed_time(q1) * 1e3 / a.reps, "launches": eng._kernels[i]})
+    rec = {"clips": a.clips, "n_stages": a.stages, "period_us_per_keyframe_batch": period, "keyframes_per_s": a.clips * 1e6 / period,
+           "sum_of_stages_us": sum(s["us_alone"] for s in stages), "stages": stages,
+           "launches_per_keyframe": eng.kernels_per_keyframe}
+    print(json.dumps(rec))
+    if a.out:
+        json.dump(rec, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
