@@ -558,6 +558,14 @@ static int launch_tc(TcParams& p, dim3 grid, int kc_max, cudaStream_t s) {
   const int budgets[3] = {74 * 1024, 112 * 1024, kMaxSmemBytes};
   for (int i = 0; i < 3 && stages < 3; ++i) stages = (budgets[i] - overhead) / p.stage_bytes;
   stages = max(2, min(kMaxStages, stages));
+  // ... but never more stages than this CTA has K chunks to load: a 1x1 layer over 32 channels has ONE.  The shared memory a
+  // CTA does not claim is what lets CTAs of OTHER streams' kernels (the software pipeline runs five) share the SM with it.
+  int chunks_per_tap = 0;
+  for (int i = 0; i < p.n_src; ++i) chunks_per_tap += p.src_chunks[i];
+  const int n_taps = p.ksize * p.ksize;
+  const int cta_chunks = ((n_taps + p.ksplit - 1) / p.ksplit) * chunks_per_tap;
+  static const bool tight_env = []() { const char* e = getenv("DVMVS_TC_TIGHT_SMEM"); return !(e && e[0] == '0'); }();
+  if (tight_env) stages = max(1, min(stages, cta_chunks));
   p.num_stages = stages;
   const int smem = stages * p.stage_bytes + overhead;
   launch_k(conv_tc_kernel<BLOCK_N>, grid, dim3(kTcThreads), (size_t)smem, s, p);

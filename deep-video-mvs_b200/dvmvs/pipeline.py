@@ -433,6 +433,10 @@ class PipelinedFusionnet:
         # DVMVS_PIPE_REC_PDL=0: capture the last stage without programmatic dependent launch (its early-launched CTAs then do
         # not sit on SMs waiting for their predecessor while other stages could use them) -- experiment switch
         self._rec_pdl = _os.environ.get("DVMVS_PIPE_REC_PDL", "1") == "1"
+        # DVMVS_PIPE_PDL=1: capture the stages WITH programmatic dependent launch.  Off by default: with several stage graphs in
+        # flight, early-launched CTAs that sit in griddepcontrol.wait hold shared memory / TMEM other stages' kernels could
+        # use (B200, 5 stages, 256 x 256: 508 us per keyframe without, 546 us with; a stage replayed alone gains only ~2 % from it)
+        self._pdl = _os.environ.get("DVMVS_PIPE_PDL", "0") == "1"
         if _os.environ.get("DVMVS_PIPE_SERIAL") == "1":        # debugging aid: all stages on one stream (no overlap)
             self.streams = [self.streams[0]] * n_stages
         self.stream_a, self.stream_b = self.streams[0], self.streams[-1]      # first / last stage (timing hooks)
@@ -503,7 +507,8 @@ class PipelinedFusionnet:
         stream = self.streams[i]
         torch.cuda.synchronize(self.device)
         saved = [t.clone() for t in self._static_state] if (i == last and self._static_state is not None) else None
-        if i == last and not self._rec_pdl:
+        pdl_off = (not self._pdl) or (i == last and not self._rec_pdl)
+        if pdl_off:
             _native.lib().dvmvs_set_programmatic_launch(0)
         with torch.cuda.stream(stream), torch.no_grad(), no_auto_graph():
             for _ in range(2):
@@ -527,7 +532,7 @@ class PipelinedFusionnet:
             else:
                 slot["out"][i] = res
         self._kernels[i] = _native.launch_count() - n0
-        if i == last and not self._rec_pdl:
+        if pdl_off:
             _native.lib().dvmvs_set_programmatic_launch(-1)
         slot["graph"][i][with_state if i == last else False] = g
         if saved is not None:

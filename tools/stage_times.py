@@ -53,9 +53,12 @@ def main():
             eng.submit(*frames[t], out=out)
         eng.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        import time
         e0.record(eng.stream_a)
+        h0 = time.perf_counter()
         for t in range(8, n_frames):
             eng.submit(*frames[t], out=out)
+        host_us = (time.perf_counter() - h0) * 1e6 / (n_frames - 8)       # enqueue cost only (no synchronisation inside)
         e1.record(eng.stream_b)
         eng.synchronize()
         torch.cuda.synchronize()
@@ -78,7 +81,7 @@ def main():
             s.synchronize()
         stages.append({"stage": i, "us_alone": q0.elapsed_time(q1) * 1e3 / a.reps, "launches": eng._kernels[i]})
     rec = {"clips": a.clips, "n_stages": a.stages, "period_us_per_keyframe_batch": period, "keyframes_per_s": a.clips * 1e6 / period,
-           "sum_of_stages_us": sum(s["us_alone"] for s in stages), "stages": stages,
+           "host_enqueue_us_per_submit": host_us, "sum_of_stages_us": sum(s["us_alone"] for s in stages), "stages": stages,
            "launches_per_keyframe": eng.kernels_per_keyframe}
     print(json.dumps(rec))
     if a.out:
