@@ -61,9 +61,11 @@ constexpr int kMaxStages = 8;
 constexpr int kBarrierBytes = 256;   // full[8] + empty[8] + tmem_full + TMEM slot + split-K flag
 constexpr int kMaxSmemBytes = 227 * 1024;
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool CAT>
 struct TcCfg {
-  static constexpr int kTmemCols = 2 * BLOCK_N;      // second half: the x_hi * w_lo product of the concatenated form
+  // CAT: second half = the x_hi * w_lo product of the concatenated three-term form.  The one-term / plain forms claim only
+  // BLOCK_N columns, so more CTAs (of this and of other streams' kernels) fit the SM's 512 columns.
+  static constexpr int kTmemCols = CAT ? 2 * BLOCK_N : BLOCK_N;
 };
 
 // bias / residual / activation and all requested output formats for 8 consecutive output channels of one pixel
@@ -116,9 +118,9 @@ __device__ __forceinline__ void tc_emit8(const TcParams& p, float (&v)[8], int b
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool CAT>
 __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_constant__ TcParams p) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, CAT>;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             if (p.terms > 1) {
               tma_load_4d(sb + off_a_lo, &p.a_map[s][1], full_bar(stage), ch * kc, ix, iy, b);
               // concatenated form: the lo tile directly follows the hi tile, so both read as ONE 2*BLOCK_N-row operand
-              tma_load_2d(sb + (p.cat ? off_w_hi + w_bytes : off_w_lo), &p.w_map[kind][1], full_bar(stage), wk, n0);
+              tma_load_2d(sb + (CAT ? off_w_hi + w_bytes : off_w_lo), &p.w_map[kind][1], full_bar(stage), wk, n0);
             }
             if (++stage == n_stages) { stage = 0; phase ^= 1u; }
           }
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             // lo words: (address >> 4) | LBO(=1) << 16; a K step of 16 fp16 = 32 bytes = +2
             const uint32_t a_hi = umma_lo_word(sb, 16), a_lo = umma_lo_word(sb + off_a_lo, 16);
             const uint32_t w_hi = umma_lo_word(sb + off_w_hi, 16), w_lo = umma_lo_word(sb + off_w_lo, 16);
-            if (p.cat) {
+            if (CAT) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (k < ksteps) {
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
       float v[8];
       tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (p.cat) {
+      if (CAT) {
         float u[8];
         tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c0), u);
 #pragma unroll
@@ -541,11 +543,11 @@ static int make_w_map(CUtensorMap* map, const void* ptr, int rows, int ktot, int
   return DVMVS_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool CAT>
 static int launch_tc(TcParams& p, dim3 grid, int kc_max, cudaStream_t s) {
   static PerDeviceOnce attr_set;
   if (attr_set.first()) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess) { set_error("conv_tc smem attribute: %s", cudaGetErrorString(e)); return DVMVS_ELAUNCH; }
   }
   // smem ring sized by the widest K chunk actually used; small stages => several CTAs co-reside per SM, which is what
@@ -568,7 +570,7 @@ static int launch_tc(TcParams& p, dim3 grid, int kc_max, cudaStream_t s) {
   if (tight_env) stages = max(1, min(stages, cta_chunks));
   p.num_stages = stages;
   const int smem = stages * p.stage_bytes + overhead;
-  launch_k(conv_tc_kernel<BLOCK_N>, grid, dim3(kTcThreads), (size_t)smem, s, p);
+  launch_k(conv_tc_kernel<BLOCK_N, CAT>, grid, dim3(kTcThreads), (size_t)smem, s, p);
   return check_launch("conv_tc_kernel");
 }
 
@@ -662,9 +664,15 @@ extern "C" int dvmvs_conv2d_tc(const dvmvs_conv_tc_desc* d, dvmvs_stream_t strea
   // short finishing launches they save) and a fused finish by the last-arriving CTA (1 110 vs 1 677 keyframes/s: one CTA walks
   // ksplit x BLOCK_N/8 dependent L2 round trips where the finishing kernel spreads them over the GPU under the next prologue).
   int rc;
-  if (d->block_n == 32) rc = launch_tc<32>(p, grid, kc_max, s);
-  else if (d->block_n == 64) rc = launch_tc<64>(p, grid, kc_max, s);
-  else rc = launch_tc<128>(p, grid, kc_max, s);
+  if (p.cat) {
+    if (d->block_n == 32) rc = launch_tc<32, true>(p, grid, kc_max, s);
+    else if (d->block_n == 64) rc = launch_tc<64, true>(p, grid, kc_max, s);
+    else rc = launch_tc<128, true>(p, grid, kc_max, s);
+  } else {
+    if (d->block_n == 32) rc = launch_tc<32, false>(p, grid, kc_max, s);
+    else if (d->block_n == 64) rc = launch_tc<64, false>(p, grid, kc_max, s);
+    else rc = launch_tc<128, false>(p, grid, kc_max, s);
+  }
   if (rc != DVMVS_OK) return rc;
   if (d->defer_finish) {
     // the caller's own epilogue kernel sums the split-K partial sums (dvmvs_lstm_gates_parts): only legal when this launch split

@@ -79,6 +79,7 @@ struct SweepTcParams {
   int B, h, w, D, M;
   int tiles_x, tiles_y;
   int qcap;                             // band capacity in pixels (multiple of 32)
+  int tmem_cols;                        // TMEM columns claimed: 64 per 128 band pixels of capacity, rounded up to a power of two
   float depth[kStMaxPlanes];            // plane depths, computed on the host in double like the reference (utils.py:59-66)
   long long* timeline;                  // development aid (tools/sweep_timeline.py): clock64 stamps of the first CTAs' phases, or null
 };
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (producer) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_slot)), "n"(Cfg::kTmemCols)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_slot)), "r"((uint32_t)p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -639,7 +640,7 @@ __global__ void __launch_bounds__(kStThreads, 1) plane_sweep_tc_kernel(const __g
   if (producer) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -726,6 +727,13 @@ extern "C" int dvmvs_plane_sweep_tc(const void* ref_hi, const void* ref_lo, cons
   if (qcap_env >= kStBox && qcap_env <= qcap) qcap = qcap_env & ~(kStBox - 1);
   DVMVS_REQUIRE(qcap >= 2 * kStBox, "plane_sweep_tc: no shared memory left for the band (D=%d, M=%d)", D, M);
   p.qcap = qcap;
+  {
+    const int need = ((qcap + 127) / 128) * kStPix;
+    int cols = 32;
+    while (cols < need) cols <<= 1;
+    p.tmem_cols = cols;
+    DVMVS_REQUIRE(cols <= (terms == 3 ? StCfg<3>::kTmemCols : StCfg<1>::kTmemCols), "plane_sweep_tc: band capacity %d needs %d TMEM columns", qcap, cols);
+  }
   const size_t smem = fixed + (size_t)qcap * per_q;
   static PerDeviceOnce attr_set;
   if (attr_set.first()) {

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--clips", type=int, default=1)
     ap.add_argument("--stages", type=int, default=5)
     ap.add_argument("--reps", type=int, default=50)
+    ap.add_argument("--pairs", type=int, default=0)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     import bench
@@ -80,9 +81,34 @@ def main():
             q1.record(s)
             s.synchronize()
         stages.append({"stage": i, "us_alone": q0.elapsed_time(q1) * 1e3 / a.reps, "launches": eng._kernels[i]})
+    pairs = []
+    if a.pairs:
+        # stage i and stage j replayed concurrently on their own streams: wall = max(alone) means they share the GPU freely,
+        # wall = sum(alone) means they serialise
+        graphs = [slot["graph"][i][True if i == last else False] for i in range(a.stages)]
+        for i in range(a.stages):
+            for j in range(i + 1, a.stages):
+                torch.cuda.synchronize()
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record()
+                eng.streams[i].wait_event(q0)
+                eng.streams[j].wait_event(q0)
+                for _ in range(a.reps):
+                    with torch.cuda.stream(eng.streams[i]):
+                        graphs[i].replay()
+                    with torch.cuda.stream(eng.streams[j]):
+                        graphs[j].replay()
+                torch.cuda.current_stream().wait_stream(eng.streams[i])
+                torch.cuda.current_stream().wait_stream(eng.streams[j])
+                q1.record()
+                torch.cuda.synchronize()
+                both = q0.elapsed_time(q1) * 1e3 / a.reps
+                ai, aj = stages[i]["us_alone"], stages[j]["us_alone"]
+                pairs.append({"pair": [i, j], "us_together": both, "max_alone": max(ai, aj), "sum_alone": ai + aj,
+                              "overlap": (ai + aj - both) / min(ai, aj)})
     rec = {"clips": a.clips, "n_stages": a.stages, "period_us_per_keyframe_batch": period, "keyframes_per_s": a.clips * 1e6 / period,
            "host_enqueue_us_per_submit": host_us, "sum_of_stages_us": sum(s["us_alone"] for s in stages), "stages": stages,
-           "launches_per_keyframe": eng.kernels_per_keyframe}
+           "launches_per_keyframe": eng.kernels_per_keyframe, "pairs": pairs}
     print(json.dumps(rec))
     if a.out:
         json.dump(rec, open(a.out, "w"), indent=1)
