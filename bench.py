@@ -448,6 +448,44 @@ def run_ours(args, rank, world, local_rank):
                                          "ms_per_keyframe_wall": float(np.median([x[1] for x in lat_s])),
                                          "note": "run-testing.py:153-202 call sequence through the drop-in modules (M + 1 separate feature passes, eleven module / utils calls per keyframe, "
                                                  "each replaying its own auto-captured CUDA graph: dvmvs/_base.py)"}
+            # the predicted depth maps fused into a TSDF volume (the reference's run-tsdf-reconstruction.py),
+            # 4 cm voxels over an 8 x 6.4 x 4.8 m room, frames at the network's resolution; device-resident and from host arrays
+            try:
+                from dvmvs.tsdf import TSDFVolume
+                rng_t = np.random.RandomState(5)
+                vol_t = TSDFVolume(np.array([[-4.0, 4.0], [-3.2, 3.2], [0.0, 4.8]]), 0.04, device=dev)
+                K_t = np.array([[0.78 * W, 0, W / 2.0], [0, 0.78 * W, H / 2.0], [0, 0, 1.0]])
+                fr_t = []
+                for i in range(16):
+                    yy, xx = np.mgrid[0:H, 0:W]
+                    dep = (2.0 + 0.8 * np.sin(xx / 40.0 + i) * np.cos(yy / 30.0)).astype(np.float32)
+                    col = rng_t.randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+                    pose_t = np.eye(4)
+                    pose_t[:3, 3] = [0.05 * i, -0.02 * i, 0.01 * i]
+                    fr_t.append((col, dep, pose_t))
+                dev_t = [(torch.from_numpy(c).to(dev), torch.from_numpy(d_).to(dev), p_) for c, d_, p_ in fr_t]
+                for c, d_, p_ in fr_t[:4] + dev_t[:4]:
+                    vol_t.integrate(c, d_, K_t, p_)
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(4):
+                    for c, d_, p_ in dev_t:
+                        vol_t.integrate(c, d_, K_t, p_)
+                t1.record()
+                torch.cuda.synchronize()
+                w0 = time.perf_counter()
+                for _ in range(4):
+                    for c, d_, p_ in fr_t:
+                        vol_t.integrate(c, d_, K_t, p_)
+                torch.cuda.synchronize()
+                extras["tsdf_fusion"] = {"voxels": int(np.prod(vol_t._vol_dim)), "frame": [H, W],
+                                         "frames_per_s_resident": 64.0 / (t0.elapsed_time(t1) * 1e-3),
+                                         "frames_per_s_host_frames": 64.0 / (time.perf_counter() - w0),
+                                         "note": "dvmvs.tsdf.TSDFVolume.integrate (one launch per frame, bit-identical to the reference's CPU path; tests/test_tsdf.py)"}
+                del vol_t, dev_t
+            except Exception as e:  # noqa: BLE001
+                extras["tsdf_fusion"] = {"error": repr(e)}
             # BASELINE.json configs[2]: 320x256, 96 planes, 4 measurement frames (its own module set: aggregator0 has D+32 inputs)
             if args.mode == "pipeline":
                 from dvmvs.config import Config as _Config
