@@ -324,23 +324,29 @@ def _stage_fe_tail(mods, slot, head):
     return mods["fe"].forward_tail(head)
 
 
-def _stage_sweep(mods, slot, fe_out, min_depth, max_depth, n_depth_levels):
-    """Feature pyramid + fused plane sweep."""
+def _sweep_from_pyramid(slot, pyramid, base, min_depth, max_depth, n_depth_levels):
+    """Fused plane sweep of ONE keyframe from a feature pyramid whose batch axis stacks [reference, measurement 1..M] x B clips
+    starting at row `base` (the lookahead engine's pyramid holds several keyframes)."""
     B = slot["ref_image"].shape[0]
     M = len(slot["meas_images"])
-    a2, a4, a8, a16 = mods["fpn"](*fe_out)
+    a2, a4, a8, a16 = pyramid
     if slot.get("meas_half") is not None:         # feature cache: batch = the reference frames only
         f2, f4, f8, f16 = a2, a4, a8, a16
         meas_half = [t.permute(0, 3, 1, 2) for t in slot["meas_half"]]
         slot["ref_half"] = f2                     # the engine copies it into the cache ring after the stage's graph
     else:
-        f2, f4, f8, f16 = ops.batch_slice(a2, 0, B), a4[:B], a8[:B], a16[:B]
-        meas_half = [ops.batch_slice(a2, (m + 1) * B, (m + 2) * B) for m in range(M)]
+        f2, f4, f8, f16 = ops.batch_slice(a2, base, base + B), a4[base:base + B], a8[base:base + B], a16[base:base + B]
+        meas_half = [ops.batch_slice(a2, base + (m + 1) * B, base + (m + 2) * B) for m in range(M)]
     half_K = slot["full_K"].clone()
     half_K[:, 0:2, :] = half_K[:, 0:2, :] / 2.0
     cv = cost_volume_fusion(image1=f2, image2s=meas_half, pose1=slot["ref_pose"], pose2s=slot["meas_poses"], K=half_K, warp_grid=None,
                             min_depth=min_depth, max_depth=max_depth, n_depth_levels=n_depth_levels, device=f2.device, dot_product=True)
     return (f2, f4, f8, f16, cv), half_K
+
+
+def _stage_sweep(mods, slot, fe_out, min_depth, max_depth, n_depth_levels):
+    """Feature pyramid + fused plane sweep."""
+    return _sweep_from_pyramid(slot, mods["fpn"](*fe_out), 0, min_depth, max_depth, n_depth_levels)
 
 
 def _stage_enc(mods, slot, swept):
@@ -637,7 +643,224 @@ class PipelinedFusionnet:
     def depth_of(self, t):
         return self.slots[t % self.n_stages]["depth"]
 
+    def flush(self):
+        """Nothing is ever held back by this engine (LookaheadFusionnet buffers keyframes; same call there launches them)."""
+
     def synchronize(self):
+        for s in self.streams:
+            s.synchronize()
+
+
+class LookaheadFusionnet:
+    """PipelinedFusionnet (5 stages) with the state-independent trunk batched over TIME: FeatureExtractor + FeatureShrinker run
+    once per group of `lookahead` consecutive keyframes -- (M + 1) x lookahead x B images in one pass -- instead of once per
+    keyframe.  Every keyframe still gets all of its M + 1 feature passes (nothing is cached or skipped: this is NOT the feature
+    cache of row f1); they are merely computed in a batch the GPU runs 2-3x more efficiently than batches of M + 1 = 3 images
+    (one-tile CTAs, launch-bound kernels at 8 x 8 .. 64 x 64 maps).  Plane sweep, cost-volume encoder and the loop-carried
+    ConvLSTM + decoder stage run per keyframe on slices of the group's pyramid, exactly as in PipelinedFusionnet.
+
+    Price: a keyframe's depth is available only after its group is complete (latency of up to `lookahead` - 1 further
+    submits) -- an offline / throughput engine, like the reference's run-testing.py loop over a recorded sequence.  submit()
+    buffers; flush() (also called by synchronize()) launches an incomplete group.  Same per-sample arithmetic as the other
+    engines; the only numerical difference is the split-K decision of a few convolutions, which depends on the batch (as with
+    any batched run: <= 1 ulp of fp32 in 3-term mode, rounding flips of the fp16 operands in 1-term mode; the parity tests hold
+    this engine to the same bounds against the oracle).
+
+        eng = LookaheadFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, lookahead=4)
+        for frame in stream:  eng.submit(*frame, out=pinned_host_tensor_or_None)
+        eng.synchronize()
+    """
+
+    n_stages = 5
+
+    def __init__(self, mods, batch, height, width, n_measurement_frames, min_depth=0.25, max_depth=20.0, n_depth_levels=64,
+                 device=None, lookahead=4, n_groups=2):
+        if lookahead < 1 or n_groups < 2:
+            raise ValueError("lookahead >= 1 and n_groups >= 2 required")
+        self.mods, self.B, self.H, self.W, self.M = mods, batch, height, width, n_measurement_frames
+        self.min_depth, self.max_depth, self.D = min_depth, max_depth, n_depth_levels
+        dev = device or next(mods["fe"].parameters()).device
+        self.device = dev
+        self.T, self.G = int(lookahead), int(n_groups)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        per_kf = (n_measurement_frames + 1) * batch
+        self.groups, self.kslots = [], []
+        for g in range(self.G):
+            images = z(self.T * per_kf, 3, height, width)
+            self.groups.append({"images": images, "head": None, "pyramid": None, "graph": [None, None],
+                                "done": [torch.cuda.Event(), torch.cuda.Event()], "readers_done": torch.cuda.Event()})
+            for j in range(self.T):
+                base = j * per_kf
+                self.kslots.append({"group": g, "base": base, "ref_image": images[base:base + batch],
+                                    "meas_images": [images[base + (m + 1) * batch:base + (m + 2) * batch] for m in range(n_measurement_frames)],
+                                    "ref_pose": z(batch, 4, 4), "full_K": z(batch, 3, 3),
+                                    "meas_poses": [z(batch, 4, 4) for _ in range(n_measurement_frames)],
+                                    "out": [None] * 5, "depth": z(batch, height, width), "graph": [dict() for _ in range(5)],
+                                    "done": [torch.cuda.Event() for _ in range(5)]})
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(5)]
+        self.stream_a, self.stream_b = self.streams[0], self.streams[-1]
+        self._static_state = None
+        self._has_state = False
+        self._gi, self._fill = 0, 0          # group counter, keyframes buffered in the open group
+        self._pending = []                   # (kslot index, with_state, out) of the open group
+        self._kslot_of = {}
+        self.t = 0
+        self._kernels = {"head": 0, "tail": 0, 2: 0, 3: 0, 4: 0}
+        self.kernels_per_keyframe = 0
+
+    def reset(self):
+        """New clip / tracking lost: the next submitted keyframe starts without recurrent state (buffered keyframes keep theirs)."""
+        self._has_state = False
+
+    # -- capture helpers ------------------------------------------------------------------------------------------------
+    def _graph_of(self, fn, stream, rec=False):
+        """Warm up `fn` twice on `stream`, capture it; returns (graph, result of the captured run, kernels launched)."""
+        from . import _native
+        torch.cuda.synchronize(self.device)
+        saved = [t.clone() for t in self._static_state] if (rec and self._static_state is not None) else None
+        _native.lib().dvmvs_set_programmatic_launch(0)          # see PipelinedFusionnet: PDL costs throughput with stages in flight
+        try:
+            with torch.cuda.stream(stream), torch.no_grad(), no_auto_graph():
+                for _ in range(2):
+                    res = fn()
+            stream.synchronize()
+            if rec and self._static_state is None:
+                pred, st = res
+                self._static_state = (st.lstm_state[0].clone(), st.lstm_state[1].clone(), st.previous_depth.clone(), st.previous_pose.clone())
+            g = torch.cuda.CUDAGraph()
+            n0 = _native.launch_count()
+            with torch.no_grad(), torch.cuda.graph(g, stream=stream):
+                res = fn(capturing=True) if rec else fn()
+            n = _native.launch_count() - n0
+        finally:
+            _native.lib().dvmvs_set_programmatic_launch(-1)
+        if saved is not None:
+            for dst, src in zip(self._static_state, saved):
+                dst.copy_(src)
+        torch.cuda.synchronize(self.device)
+        return g, res, n
+
+    def _rec_fn(self, ks, with_state):
+        def fn(capturing=False):
+            st = KeyframeState()
+            if with_state:
+                h, c, pd, pp = self._static_state
+                st.lstm_state, st.previous_depth, st.previous_pose = (h, c), pd, pp
+            enc, half_K = ks["out"][3]
+            pred, st = _stage_rec(self.mods, st, ks, enc, half_K)
+            if capturing:
+                h, c, pd, pp = self._static_state
+                ks["depth"].copy_(pred)
+                h.copy_(st.lstm_state[0])
+                c.copy_(st.lstm_state[1])
+                pd.copy_(st.previous_depth)
+                pp.copy_(ks["ref_pose"])
+            return pred, st
+        return fn
+
+    # -- steady state ---------------------------------------------------------------------------------------------------
+    def submit(self, reference_image, reference_pose, measurement_images, measurement_poses, full_K, out=None):
+        """Buffer keyframe t (inputs CPU-pinned or CUDA): its inputs are copied now, its stages are launched when its group of
+        `lookahead` keyframes is complete (or at flush() / synchronize()).  `out` as in PipelinedFusionnet.submit."""
+        g = self._gi % self.G
+        grp = self.groups[g]
+        ki = g * self.T + self._fill
+        ks = self.kslots[ki]
+        s0 = self.streams[0]
+        caller = torch.cuda.current_stream(self.device)
+        s0.wait_stream(caller)
+        for t_in in [reference_image, reference_pose, full_K] + list(measurement_images) + list(measurement_poses):
+            if t_in.is_cuda:
+                t_in.record_stream(s0)
+        if out is not None and out.is_cuda:
+            out.record_stream(self.streams[4])
+        with torch.cuda.stream(s0):
+            if self._fill == 0:
+                s0.wait_event(grp["readers_done"])       # the sweep stages of this group's previous use have read its pyramid / images
+            s0.wait_event(ks["done"][4])                 # this keyframe slot's previous use has left the pipeline
+            ks["ref_image"].copy_(reference_image, non_blocking=True)
+            ks["ref_pose"].copy_(reference_pose, non_blocking=True)
+            ks["full_K"].copy_(full_K, non_blocking=True)
+            for dst, src in zip(ks["meas_images"], measurement_images):
+                dst.copy_(src, non_blocking=True)
+            for dst, src in zip(ks["meas_poses"], measurement_poses):
+                dst.copy_(src, non_blocking=True)
+        self._pending.append((ki, self._has_state, out))
+        self._has_state = True
+        self._kslot_of[self.t] = ki
+        self._kslot_of.pop(self.t - 4 * self.T * self.G, None)
+        self._fill += 1
+        self.t += 1
+        if self._fill == self.T:
+            self.flush()
+        return self.t - 1
+
+    def flush(self):
+        """Launch the open group (complete or not): trunk over the group's image buffer, then sweep / encoder / recurrent
+        stage per buffered keyframe."""
+        if not self._pending:
+            return
+        g = self._gi % self.G
+        grp = self.groups[g]
+        s0, s1, s2, s3, s4 = self.streams
+        depth_args = (self.min_depth, self.max_depth, self.D)
+        with torch.cuda.stream(s0):
+            if grp["graph"][0] is None:
+                grp["graph"][0], grp["head"], self._kernels["head"] = self._graph_of(lambda: self.mods["fe"].forward_head(grp["images"]), s0)
+            grp["graph"][0].replay()
+            grp["done"][0].record(s0)
+        with torch.cuda.stream(s1):
+            s1.wait_event(grp["done"][0])
+            if grp["graph"][1] is None:
+                grp["graph"][1], grp["pyramid"], self._kernels["tail"] = self._graph_of(
+                    lambda: self.mods["fpn"](*self.mods["fe"].forward_tail(grp["head"])), s1)
+            grp["graph"][1].replay()
+            grp["done"][1].record(s1)
+        for ki, with_state, out in self._pending:
+            ks = self.kslots[ki]
+            with torch.cuda.stream(s2):
+                s2.wait_event(grp["done"][1])
+                if False not in ks["graph"][2]:
+                    def sweep_fn(ks=ks):
+                        _stage_side_inputs(ks)
+                        return _sweep_from_pyramid(ks, grp["pyramid"], ks["base"], *depth_args)
+                    ks["graph"][2][False], ks["out"][2], self._kernels[2] = self._graph_of(sweep_fn, s2)
+                ks["graph"][2][False].replay()
+                ks["done"][2].record(s2)
+            with torch.cuda.stream(s3):
+                s3.wait_event(ks["done"][2])
+                if False not in ks["graph"][3]:
+                    ks["graph"][3][False], ks["out"][3], self._kernels[3] = self._graph_of(lambda ks=ks: _stage_enc(self.mods, ks, ks["out"][2]), s3)
+                ks["graph"][3][False].replay()
+                ks["done"][3].record(s3)
+            with torch.cuda.stream(s4):
+                s4.wait_event(ks["done"][3])
+                if with_state not in ks["graph"][4]:
+                    ks["graph"][4][with_state], _, self._kernels[4] = self._graph_of(self._rec_fn(ks, with_state), s4, rec=True)
+                ks["graph"][4][with_state].replay()
+                if out is not None:
+                    out.copy_(ks["depth"], non_blocking=True)
+                ks["done"][4].record(s4)
+        grp["readers_done"].record(s2)
+        # launches per keyframe: the trunk's share of a full group + the per-keyframe stages
+        self.kernels_per_keyframe = (self._kernels["head"] + self._kernels["tail"]) / float(self.T) + self._kernels[2] + self._kernels[3] + self._kernels[4]
+        self._pending = []
+        self._fill = 0
+        self._gi += 1
+
+    def prime(self, reference_image, reference_pose, measurement_images, measurement_poses, full_K):
+        """Captures every graph (both variants of the recurrent stage for the slot the next clip starts in) with
+        2 x n_groups x lookahead throw-away keyframes, then resets the clip state."""
+        for _ in range(2 * self.G * self.T):
+            self.submit(reference_image, reference_pose, measurement_images, measurement_poses, full_K)
+        self.synchronize()
+        self.reset()
+
+    def depth_of(self, t):
+        return self.kslots[self._kslot_of[t]]["depth"]
+
+    def synchronize(self):
+        self.flush()
         for s in self.streams:
             s.synchronize()
 

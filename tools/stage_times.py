@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--stages", type=int, default=5)
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--pairs", type=int, default=0)
+    ap.add_argument("--lookahead", type=int, default=0, help="> 0: time LookaheadFusionnet(lookahead=N) instead and compare its depths with PipelinedFusionnet's")
+    ap.add_argument("--groups", type=int, default=2)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     import bench
@@ -46,6 +48,46 @@ def main():
         ref, rpose, meas, mpose, K = bench.stack_frame(clips, t)
         frames.append((torch.from_numpy(ref).to(dev), torch.from_numpy(rpose).to(dev), [torch.from_numpy(x).to(dev) for x in meas],
                        [torch.from_numpy(p).to(dev) for p in mpose], torch.from_numpy(K).to(dev)))
+    if a.lookahead > 0:
+        import time
+        ref_eng = pipeline.PipelinedFusionnet(mods, batch=a.clips, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=5)
+        la = pipeline.LookaheadFusionnet(mods, batch=a.clips, height=H, width=W, n_measurement_frames=M, n_depth_levels=D,
+                                         lookahead=a.lookahead, n_groups=a.groups)
+        n_cmp = 14
+        outs_a = [torch.empty((a.clips, H, W), device=dev) for _ in range(n_cmp)]
+        outs_b = [torch.empty((a.clips, H, W), device=dev) for _ in range(n_cmp)]
+        with torch.no_grad():
+            ref_eng.prime(*frames[0])
+            la.prime(*frames[0])
+            for t in range(n_cmp):
+                ref_eng.submit(*frames[t], out=outs_a[t])
+                la.submit(*frames[t], out=outs_b[t])
+            ref_eng.synchronize()
+            la.synchronize()
+            errs = [float((x - y).abs().sum() / x.abs().sum()) for x, y in zip(outs_a, outs_b)]
+            la.reset()
+            out = torch.empty((a.clips, H, W), dtype=torch.float32, device=dev)
+            for t in range(8):
+                la.submit(*frames[t], out=out)
+            la.synchronize()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(la.stream_a)
+            h0 = time.perf_counter()
+            for rep in range(3):
+                for t in range(8, n_frames):
+                    la.submit(*frames[t], out=out)
+            la.flush()
+            host_us = (time.perf_counter() - h0) * 1e6 / (3 * (n_frames - 8))
+            e1.record(la.stream_b)
+            la.synchronize()
+            torch.cuda.synchronize()
+            period = e0.elapsed_time(e1) * 1e3 / (3 * (n_frames - 8))
+        print(json.dumps({"engine": "LookaheadFusionnet", "lookahead": a.lookahead, "groups": a.groups, "clips": a.clips,
+                          "period_us_per_keyframe_batch": period, "keyframes_per_s": a.clips * 1e6 / period, "host_enqueue_us_per_submit": host_us,
+                          "launches_per_keyframe": la.kernels_per_keyframe, "kernels": {str(k): v for k, v in la._kernels.items()},
+                          "rel_l1_depth_vs_pipelined_engine_first_14_keyframes_max": max(errs), "finite": bool(torch.isfinite(out).all())}))
+        return
     eng = pipeline.PipelinedFusionnet(mods, batch=a.clips, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=a.stages)
     out = torch.empty((a.clips, H, W), dtype=torch.float32, device=dev)
     with torch.no_grad():
