@@ -845,13 +845,21 @@ def act_to_api(a):
 
 
 def batch_slice(t, lo, hi):
-    """t[lo:hi] along the batch axis of an API tensor, keeping the fp16 (hi, lo) planes its producer emitted as views (the
-    engines run FeatureExtractor + FeatureShrinker once over the reference and measurement images stacked on the batch axis
-    and hand the slices to the plane sweep)."""
+    """t[lo:hi] along the batch axis of an API tensor, keeping the operand layouts its producer emitted as views (the engines run
+    FeatureExtractor + FeatureShrinker once over the reference and measurement images stacked on the batch axis and hand the
+    slices to the plane sweep; LookaheadFusionnet runs the encoder over several keyframes and hands slices to the decoder).
+    The (hi, lo) pair planes always come along as two separate tensors (`pair`).  The stacked forms `planes` (2,B,H,W,C) and
+    `blk` (2,B,C/8,H,W,8) come along as strided views only while no kernel reads lo planes (1-term operands everywhere): the
+    kernels locate the lo plane at +B*H*W*C from the hi plane, which a batch slice of a bigger tensor does not satisfy; in
+    3-term configurations the consumer derives contiguous planes from the fp32 slice instead (one split launch)."""
     v = t[lo:hi]
     a = getattr(t, "_dvmvs_act", None)
     if a is not None and a.f32.data_ptr() == t.data_ptr() and a.version == t._version and a.planes is not None:
         act = Act(a.f32[lo:hi], pair=(a.planes[0, lo:hi], a.planes[1, lo:hi]))
+        if not lo_planes_needed():
+            act.planes = a.planes[:, lo:hi]
+            if a.blk is not None:
+                act.blk = a.blk[:, lo:hi]
         act.version = v._version
         v._dvmvs_act = act
     return v

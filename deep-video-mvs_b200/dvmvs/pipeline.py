@@ -652,19 +652,22 @@ class PipelinedFusionnet:
 
 
 class LookaheadFusionnet:
-    """PipelinedFusionnet (5 stages) with the state-independent trunk batched over TIME: FeatureExtractor + FeatureShrinker run
-    once per group of `lookahead` consecutive keyframes -- (M + 1) x lookahead x B images in one pass -- instead of once per
-    keyframe.  Every keyframe still gets all of its M + 1 feature passes (nothing is cached or skipped: this is NOT the feature
-    cache of row f1); they are merely computed in a batch the GPU runs 2-3x more efficiently than batches of M + 1 = 3 images
-    (one-tile CTAs, launch-bound kernels at 8 x 8 .. 64 x 64 maps).  Plane sweep, cost-volume encoder and the loop-carried
-    ConvLSTM + decoder stage run per keyframe on slices of the group's pyramid, exactly as in PipelinedFusionnet.
+    """Throughput engine with everything that does NOT depend on the recurrent state batched over TIME: FeatureExtractor,
+    FeatureShrinker, the plane sweep and the cost-volume encoder run once per group of `lookahead` consecutive keyframes
+    (lookahead x B "clips", each with its own poses and its own M measurement frames) instead of once per keyframe; only the
+    loop-carried stage (depth re-projection, ConvLSTM, decoder) runs keyframe by keyframe, on batch slices of the group's
+    encoder outputs.  Every keyframe still gets all of its M + 1 feature passes, its own cost volume and its own encoder pass
+    -- nothing is cached or skipped (this is NOT the feature cache of row f1); the state-independent work is merely issued in
+    batches the GPU runs far more efficiently than batches of one keyframe (at 8 x 8 .. 64 x 64 maps a single keyframe's
+    kernels are one-tile CTAs and launch-bound).  Five streams as in PipelinedFusionnet: trunk head | trunk tail + pyramid |
+    plane sweep | encoder | recurrent stage.
 
-    Price: a keyframe's depth is available only after its group is complete (latency of up to `lookahead` - 1 further
-    submits) -- an offline / throughput engine, like the reference's run-testing.py loop over a recorded sequence.  submit()
-    buffers; flush() (also called by synchronize()) launches an incomplete group.  Same per-sample arithmetic as the other
-    engines; the only numerical difference is the split-K decision of a few convolutions, which depends on the batch (as with
-    any batched run: <= 1 ulp of fp32 in 3-term mode, rounding flips of the fp16 operands in 1-term mode; the parity tests hold
-    this engine to the same bounds against the oracle).
+    Price: a keyframe's depth is available only after its group is complete (up to `lookahead` - 1 further submits) -- an
+    offline / throughput engine, like the reference's run-testing.py loop over a recorded sequence.  submit() buffers; flush()
+    (also called by synchronize()) launches an incomplete group.  Same per-sample arithmetic as the other engines; the only
+    numerical difference is the split-K decision of a few convolutions, which depends on the batch (as with any batched run:
+    <= 1 ulp of fp32 with 3-term operands, rounding flips of the fp16 operands in 1-term mode); the parity tests hold this
+    engine to the same bounds against the oracle.
 
         eng = LookaheadFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, lookahead=4)
         for frame in stream:  eng.submit(*frame, out=pinned_host_tensor_or_None)
@@ -674,7 +677,7 @@ class LookaheadFusionnet:
     n_stages = 5
 
     def __init__(self, mods, batch, height, width, n_measurement_frames, min_depth=0.25, max_depth=20.0, n_depth_levels=64,
-                 device=None, lookahead=4, n_groups=2):
+                 device=None, lookahead=4, n_groups=3):
         if lookahead < 1 or n_groups < 2:
             raise ValueError("lookahead >= 1 and n_groups >= 2 required")
         self.mods, self.B, self.H, self.W, self.M = mods, batch, height, width, n_measurement_frames
@@ -682,21 +685,25 @@ class LookaheadFusionnet:
         dev = device or next(mods["fe"].parameters()).device
         self.device = dev
         self.T, self.G = int(lookahead), int(n_groups)
+        TB = self.T * batch
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-        per_kf = (n_measurement_frames + 1) * batch
+        eye = lambda: torch.eye(4, dtype=torch.float32, device=dev).repeat(TB, 1, 1)
         self.groups, self.kslots = [], []
         for g in range(self.G):
-            images = z(self.T * per_kf, 3, height, width)
-            self.groups.append({"images": images, "head": None, "pyramid": None, "graph": [None, None],
-                                "done": [torch.cuda.Event(), torch.cuda.Event()], "readers_done": torch.cuda.Event()})
+            images = z((n_measurement_frames + 1) * TB, 3, height, width)      # [reference block | measurement 1 block | ...], TB rows each
+            K0 = torch.tensor([[float(width), 0.0, width / 2.0], [0.0, float(width), height / 2.0], [0.0, 0.0, 1.0]], device=dev).repeat(TB, 1, 1)
+            grp = {"images": images, "ref_image": images[:TB],
+                   "meas_images": [images[(m + 1) * TB:(m + 2) * TB] for m in range(n_measurement_frames)],
+                   "ref_pose": eye(), "full_K": K0, "meas_poses": [eye() for _ in range(n_measurement_frames)],   # sane until overwritten
+                   "head": None, "pyramid": None, "swept": None, "enc": None, "graph": [None] * 4,
+                   "done": [torch.cuda.Event() for _ in range(4)], "rec_done": torch.cuda.Event()}
+            self.groups.append(grp)
             for j in range(self.T):
-                base = j * per_kf
-                self.kslots.append({"group": g, "base": base, "ref_image": images[base:base + batch],
-                                    "meas_images": [images[base + (m + 1) * batch:base + (m + 2) * batch] for m in range(n_measurement_frames)],
-                                    "ref_pose": z(batch, 4, 4), "full_K": z(batch, 3, 3),
-                                    "meas_poses": [z(batch, 4, 4) for _ in range(n_measurement_frames)],
-                                    "out": [None] * 5, "depth": z(batch, height, width), "graph": [dict() for _ in range(5)],
-                                    "done": [torch.cuda.Event() for _ in range(5)]})
+                lo, hi = j * batch, (j + 1) * batch
+                self.kslots.append({"group": g, "lo": lo, "hi": hi, "ref_image": grp["ref_image"][lo:hi],
+                                    "meas_images": [mi[lo:hi] for mi in grp["meas_images"]], "ref_pose": grp["ref_pose"][lo:hi],
+                                    "full_K": grp["full_K"][lo:hi], "meas_poses": [mp[lo:hi] for mp in grp["meas_poses"]],
+                                    "depth": z(batch, height, width), "graph": dict(), "done": torch.cuda.Event()})
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(5)]
         self.stream_a, self.stream_b = self.streams[0], self.streams[-1]
         self._static_state = None
@@ -705,7 +712,7 @@ class LookaheadFusionnet:
         self._pending = []                   # (kslot index, with_state, out) of the open group
         self._kslot_of = {}
         self.t = 0
-        self._kernels = {"head": 0, "tail": 0, 2: 0, 3: 0, 4: 0}
+        self._kernels = [0] * 5
         self.kernels_per_keyframe = 0
 
     def reset(self):
@@ -740,14 +747,20 @@ class LookaheadFusionnet:
         torch.cuda.synchronize(self.device)
         return g, res, n
 
-    def _rec_fn(self, ks, with_state):
+    def _rec_fn(self, ks, grp, with_state):
+        lo, hi = ks["lo"], ks["hi"]
+
         def fn(capturing=False):
             st = KeyframeState()
             if with_state:
                 h, c, pd, pp = self._static_state
                 st.lstm_state, st.previous_depth, st.previous_pose = (h, c), pd, pp
-            enc, half_K = ks["out"][3]
-            pred, st = _stage_rec(self.mods, st, ks, enc, half_K)
+            enc, half_K = grp["enc"]
+            view = {"ref_image": ks["ref_image"], "ref_pose": ks["ref_pose"], "full_K": ks["full_K"], "ref_cl": grp["ref_cl"][lo:hi],
+                    "lstm_K": grp["lstm_K"][lo:hi]}
+            if grp.get("input_gates") is not None:
+                view["input_gates"] = grp["input_gates"][lo:hi]
+            pred, st = _stage_rec(self.mods, st, view, tuple(ops.batch_slice(e, lo, hi) for e in enc), half_K[lo:hi])
             if capturing:
                 h, c, pd, pp = self._static_state
                 ks["depth"].copy_(pred)
@@ -776,8 +789,7 @@ class LookaheadFusionnet:
             out.record_stream(self.streams[4])
         with torch.cuda.stream(s0):
             if self._fill == 0:
-                s0.wait_event(grp["readers_done"])       # the sweep stages of this group's previous use have read its pyramid / images
-            s0.wait_event(ks["done"][4])                 # this keyframe slot's previous use has left the pipeline
+                s0.wait_event(grp["rec_done"])           # every stage of this group's previous use has finished reading its buffers
             ks["ref_image"].copy_(reference_image, non_blocking=True)
             ks["ref_pose"].copy_(reference_pose, non_blocking=True)
             ks["full_K"].copy_(full_K, non_blocking=True)
@@ -796,54 +808,43 @@ class LookaheadFusionnet:
         return self.t - 1
 
     def flush(self):
-        """Launch the open group (complete or not): trunk over the group's image buffer, then sweep / encoder / recurrent
-        stage per buffered keyframe."""
+        """Launch the open group (complete or not): trunk, pyramid, plane sweep and encoder over the group's buffers, then the
+        recurrent stage for each buffered keyframe in order."""
         if not self._pending:
             return
-        g = self._gi % self.G
-        grp = self.groups[g]
+        grp = self.groups[self._gi % self.G]
         s0, s1, s2, s3, s4 = self.streams
         depth_args = (self.min_depth, self.max_depth, self.D)
-        with torch.cuda.stream(s0):
-            if grp["graph"][0] is None:
-                grp["graph"][0], grp["head"], self._kernels["head"] = self._graph_of(lambda: self.mods["fe"].forward_head(grp["images"]), s0)
-            grp["graph"][0].replay()
-            grp["done"][0].record(s0)
-        with torch.cuda.stream(s1):
-            s1.wait_event(grp["done"][0])
-            if grp["graph"][1] is None:
-                grp["graph"][1], grp["pyramid"], self._kernels["tail"] = self._graph_of(
-                    lambda: self.mods["fpn"](*self.mods["fe"].forward_tail(grp["head"])), s1)
-            grp["graph"][1].replay()
-            grp["done"][1].record(s1)
+
+        def run(i, stream, fn, key, after):
+            with torch.cuda.stream(stream):
+                if after is not None:
+                    stream.wait_event(after)
+                if grp["graph"][i] is None:
+                    grp["graph"][i], grp[key], self._kernels[i] = self._graph_of(fn, stream)
+                grp["graph"][i].replay()
+                grp["done"][i].record(stream)
+
+        def head_fn():
+            _stage_side_inputs(grp)                  # channel-last reference images + 1/32 intrinsics for the recurrent stage
+            return self.mods["fe"].forward_head(grp["images"])
+
+        run(0, s0, head_fn, "head", None)
+        run(1, s1, lambda: self.mods["fpn"](*self.mods["fe"].forward_tail(grp["head"])), "pyramid", grp["done"][0])
+        run(2, s2, lambda: _sweep_from_pyramid(grp, grp["pyramid"], 0, *depth_args), "swept", grp["done"][1])
+        run(3, s3, lambda: _stage_enc(self.mods, grp, grp["swept"]), "enc", grp["done"][2])
         for ki, with_state, out in self._pending:
             ks = self.kslots[ki]
-            with torch.cuda.stream(s2):
-                s2.wait_event(grp["done"][1])
-                if False not in ks["graph"][2]:
-                    def sweep_fn(ks=ks):
-                        _stage_side_inputs(ks)
-                        return _sweep_from_pyramid(ks, grp["pyramid"], ks["base"], *depth_args)
-                    ks["graph"][2][False], ks["out"][2], self._kernels[2] = self._graph_of(sweep_fn, s2)
-                ks["graph"][2][False].replay()
-                ks["done"][2].record(s2)
-            with torch.cuda.stream(s3):
-                s3.wait_event(ks["done"][2])
-                if False not in ks["graph"][3]:
-                    ks["graph"][3][False], ks["out"][3], self._kernels[3] = self._graph_of(lambda ks=ks: _stage_enc(self.mods, ks, ks["out"][2]), s3)
-                ks["graph"][3][False].replay()
-                ks["done"][3].record(s3)
             with torch.cuda.stream(s4):
-                s4.wait_event(ks["done"][3])
-                if with_state not in ks["graph"][4]:
-                    ks["graph"][4][with_state], _, self._kernels[4] = self._graph_of(self._rec_fn(ks, with_state), s4, rec=True)
-                ks["graph"][4][with_state].replay()
+                s4.wait_event(grp["done"][3])
+                if with_state not in ks["graph"]:
+                    ks["graph"][with_state], _, self._kernels[4] = self._graph_of(self._rec_fn(ks, grp, with_state), s4, rec=True)
+                ks["graph"][with_state].replay()
                 if out is not None:
                     out.copy_(ks["depth"], non_blocking=True)
-                ks["done"][4].record(s4)
-        grp["readers_done"].record(s2)
-        # launches per keyframe: the trunk's share of a full group + the per-keyframe stages
-        self.kernels_per_keyframe = (self._kernels["head"] + self._kernels["tail"]) / float(self.T) + self._kernels[2] + self._kernels[3] + self._kernels[4]
+                ks["done"].record(s4)
+        grp["rec_done"].record(s4)
+        self.kernels_per_keyframe = sum(self._kernels[:4]) / float(self.T) + self._kernels[4]      # a full group's share + the recurrent stage
         self._pending = []
         self._fill = 0
         self._gi += 1

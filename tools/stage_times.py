@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--pairs", type=int, default=0)
     ap.add_argument("--lookahead", type=int, default=0, help="> 0: time LookaheadFusionnet(lookahead=N) instead and compare its depths with PipelinedFusionnet's")
-    ap.add_argument("--groups", type=int, default=2)
+    ap.add_argument("--groups", type=int, default=3)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     import bench
@@ -85,7 +85,7 @@ def main():
             period = e0.elapsed_time(e1) * 1e3 / (3 * (n_frames - 8))
         print(json.dumps({"engine": "LookaheadFusionnet", "lookahead": a.lookahead, "groups": a.groups, "clips": a.clips,
                           "period_us_per_keyframe_batch": period, "keyframes_per_s": a.clips * 1e6 / period, "host_enqueue_us_per_submit": host_us,
-                          "launches_per_keyframe": la.kernels_per_keyframe, "kernels": {str(k): v for k, v in la._kernels.items()},
+                          "launches_per_keyframe": la.kernels_per_keyframe, "kernels": list(la._kernels),
                           "rel_l1_depth_vs_pipelined_engine_first_14_keyframes_max": max(errs), "finite": bool(torch.isfinite(out).all())}))
         return
     eng = pipeline.PipelinedFusionnet(mods, batch=a.clips, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=a.stages)
