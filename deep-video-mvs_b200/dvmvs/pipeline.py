@@ -704,7 +704,11 @@ class LookaheadFusionnet:
                                     "meas_images": [mi[lo:hi] for mi in grp["meas_images"]], "ref_pose": grp["ref_pose"][lo:hi],
                                     "full_K": grp["full_K"][lo:hi], "meas_poses": [mp[lo:hi] for mp in grp["meas_poses"]],
                                     "depth": z(batch, height, width), "graph": dict(), "done": torch.cuda.Event()})
-        self.streams = [torch.cuda.Stream(device=dev) for _ in range(5)]
+        # the recurrent stage's small kernels carry the loop dependence; on a high-priority stream their CTAs are dispatched
+        # ahead of the queued CTAs of the batched stages' big grids (DVMVS_LA_PRIO=0: all streams equal)
+        import os as _os
+        prio = _os.environ.get("DVMVS_LA_PRIO", "1") == "1"
+        self.streams = [torch.cuda.Stream(device=dev, priority=(-1 if (prio and i == 4) else 0)) for i in range(5)]
         self.stream_a, self.stream_b = self.streams[0], self.streams[-1]
         self._static_state = None
         self._has_state = False
