@@ -234,7 +234,11 @@ def run_ours(args, rank, world, local_rank):
     pipe = None
     engine_check = None
     if args.mode == "pipeline":
-        pipe = pipeline.PipelinedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=args.stages)
+        def make_engine(mods_, batch_, h_=H, w_=W, m_=M, d_=D):
+            if args.lookahead > 0:
+                return pipeline.LookaheadFusionnet(mods_, batch=batch_, height=h_, width=w_, n_measurement_frames=m_, n_depth_levels=d_, lookahead=args.lookahead)
+            return pipeline.PipelinedFusionnet(mods_, batch=batch_, height=h_, width=w_, n_measurement_frames=m_, n_depth_levels=d_, n_stages=args.stages)
+        pipe = make_engine(mods, B)
         pred = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         with torch.no_grad():
             pipe.prime(*frames_dev[0])            # one-off graph captures, outside warm-up and timing
@@ -242,8 +246,9 @@ def run_ours(args, rank, world, local_rank):
             pipe.submit(*frames_dev[0], out=pred)
             pipe.synchronize()
             eager0, _ = pipeline.keyframe(mods, pipeline.KeyframeState(), *frames_dev[0], n_depth_levels=D)
-            engine_check = float((pred - eager0).abs().max())
-            assert engine_check <= 1e-5 * float(eager0.abs().max()), "pipelined engine deviates from the eager module sequence: %g" % engine_check
+            engine_check = float((pred - eager0).abs().sum() / eager0.abs().sum())
+            # PipelinedFusionnet reproduces the module sequence bit for bit; LookaheadFusionnet re-associates a few split-K sums (batch)
+            assert engine_check <= (1e-4 if args.lookahead > 0 else 0.0) + 1e-7, "engine deviates from the eager module sequence: rel-L1 %g" % engine_check
             pipe.reset()
             for t in range(args.warmup):
                 pipe.submit(*frames_dev[t], out=pred)
@@ -258,6 +263,7 @@ def run_ours(args, rank, world, local_rank):
             p0.record(pipe.stream_a)
             for i in range(args.steps):
                 pipe.submit(*frames_dev[args.warmup + i], out=pred)
+            pipe.flush()                            # lookahead engine: launch an incomplete last group inside the timed region
             wall_enq = time.perf_counter()          # host side done enqueueing (the device may still be far behind)
             p1.record(pipe.stream_b)
             pipe.synchronize()
@@ -338,6 +344,8 @@ def run_ours(args, rank, world, local_rank):
         e0.record(pipe.stream_a if pipe is not None else torch.cuda.current_stream())
         for i in range(args.steps):
             state = e2e_step(args.warmup + i, state)
+        if pipe is not None:
+            pipe.flush()
         e1.record(pipe.stream_b if pipe is not None else torch.cuda.current_stream())
         if pipe is not None:
             pipe.synchronize()
@@ -506,7 +514,7 @@ def run_ours(args, rank, world, local_rank):
                     up = lambda a: torch.from_numpy(np.ascontiguousarray(a))[None].to(dev)
                     f3.append((up(clip3["images"][ref_i]), up(clip3["poses"][ref_i]), [up(clip3["images"][j]) for j in meas_i],
                                [up(clip3["poses"][j]) for j in meas_i], up(clip3["K"])))
-                p3 = pipeline.PipelinedFusionnet(mods3, batch=1, height=H3, width=W3, n_measurement_frames=M3, n_depth_levels=D3, n_stages=args.stages)
+                p3 = make_engine(mods3, 1, H3, W3, M3, D3)
                 out3 = torch.empty((1, H3, W3), dtype=torch.float32, device=dev)
                 p3.prime(*f3[0])
                 for t in range(4):
@@ -517,6 +525,7 @@ def run_ours(args, rank, world, local_rank):
                 r0.record(p3.stream_a)
                 for t in range(4, 16):
                     p3.submit(*f3[t], out=out3)
+                p3.flush()
                 r1.record(p3.stream_b)
                 p3.synchronize()
                 torch.cuda.synchronize()
@@ -524,11 +533,33 @@ def run_ours(args, rank, world, local_rank):
                 extras["config_c3_320x256_96planes_4frames"] = {"frames_per_s_per_gpu": 12 / (ms * 1e-3), "ms_per_step": ms / 12,
                                                                 "finite": bool(torch.isfinite(out3).all())}
                 del p3, mods3, f3
+            # the same stream through PipelinedFusionnet (5 stages, one keyframe per stage launch, results available keyframe by
+            # keyframe): what the headline engine's batching of the state-independent stages over time buys
+            if args.mode == "pipeline" and args.lookahead > 0:
+                pn = pipeline.PipelinedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=args.stages)
+                outn = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+                pn.prime(*frames_dev[0])
+                for t in range(args.warmup):
+                    pn.submit(*frames_dev[t], out=outn)
+                pn.synchronize()
+                torch.cuda.synchronize()
+                n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n0.record(pn.stream_a)
+                for t in range(args.warmup, n_frames):
+                    pn.submit(*frames_dev[t], out=outn)
+                n1.record(pn.stream_b)
+                pn.synchronize()
+                torch.cuda.synchronize()
+                ms_n = n0.elapsed_time(n1) / args.steps
+                extras["pipelined_%d_stages_no_lookahead" % args.stages] = {
+                    "frames_per_s_per_gpu": B * 1e3 / ms_n, "ms_per_step": ms_n, "launches_per_keyframe": pn.kernels_per_keyframe,
+                    "rel_l1_inverse_depth_vs_headline_last_keyframe": float(((1.0 / outn) - (1.0 / pred)).abs().sum() / (1.0 / pred).abs().sum())}
+                del pn
             # the other operand precision of the tensor path (fp16 (hi, lo) pairs, three products: ~fp32 accuracy)
             if args.backend == "tc" and args.mode == "pipeline":
                 other = 3 if args.tc_terms == 1 else 1
                 ops.set_conv_backend("tc", terms=other, stride2=True)
-                po = pipeline.PipelinedFusionnet(mods, batch=B, height=H, width=W, n_measurement_frames=M, n_depth_levels=D, n_stages=args.stages)
+                po = make_engine(mods, B)
                 outo = torch.empty((B, H, W), dtype=torch.float32, device=dev)
                 po.prime(*frames_dev[0])
                 for t in range(args.warmup):
@@ -539,6 +570,7 @@ def run_ours(args, rank, world, local_rank):
                 o0.record(po.stream_a)
                 for t in range(args.warmup, n_frames):
                     po.submit(*frames_dev[t], out=outo)
+                po.flush()
                 o1.record(po.stream_b)
                 po.synchronize()
                 torch.cuda.synchronize()
@@ -602,13 +634,15 @@ def run_ours(args, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": workload_config(B, weights_desc),
-        "engine": {"mode": args.mode + (" (%d stages)" % args.stages if args.mode == "pipeline" else ""),
+        "engine": {"mode": args.mode + ((" (LookaheadFusionnet: trunk, pyramid, plane sweep and encoder batched over groups of %d consecutive keyframes, "
+                                          "recurrent stage per keyframe; 5 streams)" % args.lookahead) if (args.mode == "pipeline" and args.lookahead > 0)
+                                         else (" (%d stages)" % args.stages if args.mode == "pipeline" else "")),
                    "conv_backend": args.backend + ("" if args.backend == "fp32" else (" (tcgen05, fp16 operands, fp32 accumulate)" if args.tc_terms == 1
                                                                                          else " (tcgen05, fp16-pair operands x3 terms, fp32 accumulate)")),
                    "plane_sweep": sweep_kernel,
                    "parity": "this exact configuration is held to <= 3.3e-4 rel-L1 on inverse depth vs the oracle / the shipped golden by "
                              "tests/test_gpu_parity.py::test_benchmarked_configuration_* (budget 1e-3)",
-                   "engine_vs_eager_modules_max_abs_diff_first_keyframe": engine_check,
+                   "engine_vs_eager_modules_rel_l1_first_keyframe": engine_check,
                    "l2": ("per-step working set (weights 138 MB + activations) exceeds the 126 MB L2; steps run back to back (pipelined)"
                           if args.mode == "pipeline" else "flushed (256 MiB write) between timed steps"),
                    "parallelism": "clip-sharded x%d (dvmvs.sharding, round-robin), no data-path collective" % world,
@@ -810,7 +844,10 @@ def main():
     ap.add_argument("--tc-terms", type=int, default=1, choices=[1, 3],
                     help="operand precision of the tcgen05 convolutions: 1 = fp16 operands, fp32 accumulate (default; measured "
                          "<= 1.1e-4 rel-L1 on inverse depth, budget 1e-3); 3 = fp16 (hi, lo) pairs, three products (~1e-6)")
-    ap.add_argument("--stages", type=int, default=5, choices=[2, 3, 4, 5], help="pipeline depth of --mode pipeline")
+    ap.add_argument("--stages", type=int, default=5, choices=[2, 3, 4, 5], help="pipeline depth of --mode pipeline (with --lookahead 0)")
+    ap.add_argument("--lookahead", type=int, default=4,
+                    help="--mode pipeline: keyframes per group of LookaheadFusionnet (state-independent stages batched over consecutive "
+                         "keyframes; every keyframe still gets all its feature passes); 0 = PipelinedFusionnet(--stages)")
     ap.add_argument("--extras", type=int, default=1, help="also measure sequential latency and batched throughput (0 to skip)")
     ap.add_argument("--extra-clips", default="8,32", help="clips per GPU of the batched operating points (comma separated)")
     ap.add_argument("--cpu-frames", type=int, default=6, help="frames of the bounded CPU-baseline sample")

@@ -723,6 +723,20 @@ class LookaheadFusionnet:
         """New clip / tracking lost: the next submitted keyframe starts without recurrent state (buffered keyframes keep theirs)."""
         self._has_state = False
 
+    def load_state(self, lstm_state, previous_depth, previous_pose):
+        """As PipelinedFusionnet.load_state: continue a clip whose first keyframes ran elsewhere."""
+        if self._static_state is None:
+            raise RuntimeError("load_state: call prime() (or submit one keyframe) first")
+        self.synchronize()
+        h, c, pd, pp = self._static_state
+        with torch.no_grad():
+            h.copy_(lstm_state[0])
+            c.copy_(lstm_state[1])
+            pd.copy_(previous_depth.reshape(pd.shape))
+            pp.copy_(previous_pose)
+        torch.cuda.current_stream(self.device).synchronize()
+        self._has_state = True
+
     # -- capture helpers ------------------------------------------------------------------------------------------------
     def _graph_of(self, fn, stream, rec=False):
         """Warm up `fn` twice on `stream`, capture it; returns (graph, result of the captured run, kernels launched)."""
