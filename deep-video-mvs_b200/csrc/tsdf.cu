@@ -64,9 +64,18 @@ __global__ void __launch_bounds__(256) tsdf_integrate_kernel(TsdfParams p) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool hit = false;
   if (idx < n) {
-    const int z = (int)(idx % p.dim_z);
-    const long long xy = idx / p.dim_z;
-    const int y = (int)(xy % p.dim_y), x = (int)(xy / p.dim_y);
+    int x, y, z;
+    if (n <= 0xffffffffLL) {       // 32-bit index arithmetic (64-bit division is emulated: it was most of this kernel's time)
+      const unsigned i = (unsigned)idx, xy = i / (unsigned)p.dim_z;
+      z = (int)(i - xy * (unsigned)p.dim_z);
+      x = (int)(xy / (unsigned)p.dim_y);
+      y = (int)(xy - (unsigned)x * (unsigned)p.dim_y);
+    } else {
+      z = (int)(idx % p.dim_z);
+      const long long xy = idx / p.dim_z;
+      y = (int)(xy % p.dim_y);
+      x = (int)(xy / p.dim_y);
+    }
     const float wxf = __double2float_rn(__dadd_rn((double)p.origin[0], __dmul_rn(p.voxel_size, (double)x)));
     const float wyf = __double2float_rn(__dadd_rn((double)p.origin[1], __dmul_rn(p.voxel_size, (double)y)));
     const float wzf = __double2float_rn(__dadd_rn((double)p.origin[2], __dmul_rn(p.voxel_size, (double)z)));
