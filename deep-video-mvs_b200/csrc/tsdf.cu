@@ -12,13 +12,15 @@
 //   colour : float32 throughout, rintf, min(255, .) with NaN propagation as np.minimum
 // No multiply-add contraction anywhere a rounding would be skipped (explicit _rn intrinsics).
 //
-// Culling: 98 % of a room-sized volume is outside the frustum or the truncation band of any one frame; one thread per voxel
-// spends the launch issuing instructions for voxels that cannot be touched (measured: 23 M warp instructions, issue slots 75 %
-// busy, 32 us for 3.84 M voxels).  A thread therefore owns a run of 8 consecutive z voxels and first projects the run's two END
-// POINTS in float32 (9 FMAs each): the run is dropped when it is PROVABLY behind the camera or more than a pixel outside one
-// image border -- the tests use error bounds of the float32 evaluation computed on the host from the volume extent (eps), so a
-// voxel the float64 path would update is never dropped (tests compare whole volumes with the reference bit for bit).  Voxels
-// of surviving runs take the exact path.
+// Culling: 98 % of a room-sized volume is outside the frustum or the truncation band of any one frame.  A thread owns a run of
+// 8 consecutive z voxels and first projects the run's two END POINTS in float32 (9 FMAs each): the run is dropped when it is
+// PROVABLY behind the camera or more than a pixel outside one image border -- the tests use error bounds of the float32
+// evaluation computed on the host from the volume extent (eps), so a voxel the float64 path would update is never dropped
+// (tests compare whole volumes with the reference bit for bit).  Voxels of surviving runs take the exact path.
+// Measured (B200, 3.84 M voxels, 320 x 256 frame, 80 k voxels updated): 29.7 us per launch; one thread per voxel with a
+// per-voxel pre-test: 31.7 us, 23 M warp instructions, issue slots 75 % busy (profiles/r02_tsdf_ncu_per_voxel_kernel.md).  What
+// remains is the exact float64 projection (two double divisions) of the ~20 % of voxels inside the frustum, nine tenths of
+// which then fail the truncation test; a conservative depth pre-test against a coarse max-depth image is the next step.
 //
 // Memory: volumes are the reference's C-order [x][y][z]; a thread's run is 32 contiguous bytes of each volume (one sector), a
 // warp's runs are contiguous.  Voxels outside the frustum or the truncation band touch no volume memory at all.  Algorithmic
