@@ -708,6 +708,8 @@ class LookaheadFusionnet:
         # ahead of the queued CTAs of the batched stages' big grids (DVMVS_LA_PRIO=0: all streams equal)
         import os as _os
         prio = _os.environ.get("DVMVS_LA_PRIO", "1") == "1"
+        self._foreach = _os.environ.get("DVMVS_LA_FOREACH", "1") == "1" and hasattr(torch, "_foreach_copy_")
+        self._rec_pdl = _os.environ.get("DVMVS_LA_REC_PDL", "0") == "1"       # experiment: PDL inside the recurrent stage's graph only
         self.streams = [torch.cuda.Stream(device=dev, priority=(-1 if (prio and i == 4) else 0)) for i in range(5)]
         self.stream_a, self.stream_b = self.streams[0], self.streams[-1]
         self._static_state = None
@@ -743,7 +745,7 @@ class LookaheadFusionnet:
         from . import _native
         torch.cuda.synchronize(self.device)
         saved = [t.clone() for t in self._static_state] if (rec and self._static_state is not None) else None
-        _native.lib().dvmvs_set_programmatic_launch(0)          # see PipelinedFusionnet: PDL costs throughput with stages in flight
+        _native.lib().dvmvs_set_programmatic_launch(1 if (rec and self._rec_pdl) else 0)   # see PipelinedFusionnet: PDL costs throughput with stages in flight
         try:
             with torch.cuda.stream(stream), torch.no_grad(), no_auto_graph():
                 for _ in range(2):
@@ -781,11 +783,13 @@ class LookaheadFusionnet:
             pred, st = _stage_rec(self.mods, st, view, tuple(ops.batch_slice(e, lo, hi) for e in enc), half_K[lo:hi])
             if capturing:
                 h, c, pd, pp = self._static_state
-                ks["depth"].copy_(pred)
-                h.copy_(st.lstm_state[0])
-                c.copy_(st.lstm_state[1])
-                pd.copy_(st.previous_depth)
-                pp.copy_(ks["ref_pose"])
+                dsts = [ks["depth"], h, c, pd, pp]
+                srcs = [pred, st.lstm_state[0], st.lstm_state[1], st.previous_depth.reshape(pd.shape), ks["ref_pose"]]
+                if self._foreach:        # one multi-tensor launch instead of five copy kernels at the end of the loop-carried chain
+                    torch._foreach_copy_(dsts, [s_.reshape(d_.shape) for d_, s_ in zip(dsts, srcs)])
+                else:
+                    for d_, s_ in zip(dsts, srcs):
+                        d_.copy_(s_)
             return pred, st
         return fn
 
