@@ -708,8 +708,11 @@ class LookaheadFusionnet:
         # ahead of the queued CTAs of the batched stages' big grids (DVMVS_LA_PRIO=0: all streams equal)
         import os as _os
         prio = _os.environ.get("DVMVS_LA_PRIO", "1") == "1"
-        self._foreach = _os.environ.get("DVMVS_LA_FOREACH", "1") == "1" and hasattr(torch, "_foreach_copy_")
-        self._rec_pdl = _os.environ.get("DVMVS_LA_REC_PDL", "0") == "1"       # experiment: PDL inside the recurrent stage's graph only
+        # measured switches, both off (B200, c2, lookahead 4: 2 396 keyframes/s as is): DVMVS_LA_FOREACH=1 writes the recurrent state
+        # back with one multi-tensor copy instead of five copy kernels (2 410: inside run-to-run noise); DVMVS_LA_REC_PDL=1 captures
+        # the recurrent stage's graph with programmatic dependent launch (2 321: slower, as for the other stages)
+        self._foreach = _os.environ.get("DVMVS_LA_FOREACH", "0") == "1" and hasattr(torch, "_foreach_copy_")
+        self._rec_pdl = _os.environ.get("DVMVS_LA_REC_PDL", "0") == "1"
         self.streams = [torch.cuda.Stream(device=dev, priority=(-1 if (prio and i == 4) else 0)) for i in range(5)]
         self.stream_a, self.stream_b = self.streams[0], self.streams[-1]
         self._static_state = None
