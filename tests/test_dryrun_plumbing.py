@@ -76,6 +76,31 @@ for backend in ("fp32", "tc"):
     enc, half_K = pipeline._stage_enc(mods, slot, pipeline._stage_sweep(mods, slot, fe, 0.25, 20.0, D))
     pred, _ = pipeline._stage_rec(mods, pipeline.KeyframeState(), slot, enc, half_K)
     assert tuple(pred.shape) == (1, H, W)
+    # LookaheadFusionnet's composition: trunk / pyramid / sweep / encoder over a GROUP of keyframes (block layout: all reference
+    # images, then all first measurement images, ...), recurrent stage per keyframe on batch slices of the group's outputs
+    for terms in (1, 3):
+        ops.set_conv_backend(backend, terms=terms, stride2=True)
+        TB = len(clip["frames"])
+        blocks = [[T(clip["images"][r])[None] for r, _ in clip["frames"]]] + [[T(clip["images"][ms[m]])[None] for _, ms in clip["frames"]] for m in range(M)]
+        images = torch.cat([torch.cat(b, dim=0) for b in blocks], dim=0)
+        grp = {"images": images, "ref_image": images[:TB], "meas_images": [images[(m + 1) * TB:(m + 2) * TB] for m in range(M)],
+               "ref_pose": torch.cat([T(clip["poses"][r])[None] for r, _ in clip["frames"]]), "full_K": T(clip["K"])[None].repeat(TB, 1, 1),
+               "meas_poses": [torch.cat([T(clip["poses"][ms[m]])[None] for _, ms in clip["frames"]]) for m in range(M)]}
+        pipeline._stage_side_inputs(grp)
+        pyramid = mods["fpn"](*mods["fe"].forward_tail(mods["fe"].forward_head(grp["images"])))
+        assert pyramid[0].shape[0] == (M + 1) * TB
+        enc, half_K = pipeline._stage_enc(mods, grp, pipeline._sweep_from_pyramid(grp, pyramid, 0, 0.25, 20.0, D))
+        assert enc[4].shape[0] == TB and grp["input_gates"].shape[0] == TB
+        st = pipeline.KeyframeState()
+        for j in range(TB):
+            sl = tuple(ops.batch_slice(e, j, j + 1) for e in enc)
+            a = getattr(sl[0], "_dvmvs_act", None)
+            if backend == "tc" and a is not None and a.pair is not None:
+                assert (a.planes is not None) == (terms == 1), "stacked plane views travel with a batch slice only while no lo plane is read"
+            view = {"ref_image": grp["ref_image"][j:j + 1], "ref_pose": grp["ref_pose"][j:j + 1], "full_K": grp["full_K"][j:j + 1],
+                    "ref_cl": grp["ref_cl"][j:j + 1], "lstm_K": grp["lstm_K"][j:j + 1], "input_gates": grp["input_gates"][j:j + 1]}
+            pred, st = pipeline._stage_rec(mods, st, view, sl, half_K[j:j + 1])
+            assert tuple(pred.shape) == (1, H, W)
 print("dryrun ok")
 """
 
