@@ -177,6 +177,7 @@ def test_hidden_warp_vs_reference_golden(synth, cases, golden_ops):
 
 def test_reprojection_vs_reference_golden(synth, cases, golden_ops):
     from dvmvs.utils import get_non_differentiable_rectangle_depth_estimation
+    counts = {}
     for name, c in cases.REPROJECT_CASES.items():
         inp = cases.reproject_inputs(synth, c)
         out = get_non_differentiable_rectangle_depth_estimation(_cuda(inp["reference_pose"]), _cuda(inp["measurement_pose"]),
@@ -184,8 +185,19 @@ def test_reprojection_vs_reference_golden(synth, cases, golden_ops):
                                                                 _cuda(inp["half_K"]), c["W"], c["H"]).cpu().numpy()
         gold = golden_ops["reproject/" + name]
         assert out.shape == gold.shape
-        mismatch = np.mean(np.abs(out - gold) > 1e-5 * np.maximum(1.0, np.abs(gold)))
-        assert mismatch <= 2e-3, "reproject/%s: %.4f%% pixels differ" % (name, 100 * mismatch)
+        differ = np.abs(out - gold) > 1e-5 * np.maximum(1.0, np.abs(gold))
+        # a differing pixel would be a rounding tie of the scatter target (a source point 1e-7 from a .5 pixel boundary landing in
+        # the neighbouring cell under fp32 re-association).  Measured on B200 (round 2): 0 of 16 384 (c2) and 0 of 2 048 (batch)
+        # half-resolution pixels differ -- the bound is two tie flips per case, not a ratio that could hide dozens.
+        counts[name] = {"pixels": int(differ.size), "differing": int(differ.sum())}
+        print("reproject/%s: %d of %d half-resolution pixels differ from the reference golden" % (name, int(differ.sum()), differ.size))
+        assert int(differ.sum()) <= 2, "reproject/%s: %d of %d pixels differ" % (name, int(differ.sum()), differ.size)
+    import json
+    import os
+    out_dir = os.path.join(REPO_DIR, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "r02_reproject_mismatch_counts.json"), "w") as fh:
+            json.dump(counts, fh, indent=1)
 
 
 def test_reprojection_is_idempotent_under_identity(synth):
