@@ -637,7 +637,8 @@ def run_ours(args, rank, world, local_rank):
         "metric": "fusionnet depth frames/sec @256x256x64planes", "value": fps, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": workload_config(B, weights_desc),
+        "config": (workload_config(B, weights_desc) if args.mode == "pipeline" else
+                   dict(workload_config(B, weights_desc), gpu_l2="flushed (256 MiB write) between timed steps")),
         "engine": {"mode": args.mode + ((" (LookaheadFusionnet: trunk, pyramid, plane sweep and encoder batched over groups of %d consecutive keyframes, "
                                           "recurrent stage per keyframe; 5 streams)" % args.lookahead) if (args.mode == "pipeline" and args.lookahead > 0)
                                          else (" (%d stages)" % args.stages if args.mode == "pipeline" else "")),
