@@ -105,6 +105,7 @@ def lib():
                                "`python deep-video-mvs_b200/build_native.py --force`" % (LIB_PATH, L.dvmvs_abi_version(), ABI_VERSION))
         i, f, p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
         L.dvmvs_last_error_string.restype = ctypes.c_char_p
+        L.dvmvs_set_programmatic_launch.argtypes = [i]
         L.dvmvs_plane_sweep_fused.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
         L.dvmvs_plane_sweep_generic.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, i, p]
         L.dvmvs_plane_sweep_fused_h16.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, f, f, p]

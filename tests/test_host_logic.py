@@ -27,6 +27,48 @@ def test_library_exports_every_declared_symbol():
     assert lib.dvmvs_abi_version() == N.ABI_VERSION == 6
 
 
+def test_binding_argtypes_match_header_prototypes():
+    """Every prototype of include/dvmvs_b200.h against the ctypes binding: same number of parameters, and each parameter's C
+    class (pointer / int / long long / float / double) maps to the ctypes type the binding declares.  A drifted argtypes list
+    passes garbage in registers without any error."""
+    import ctypes
+    from dvmvs import _native as N
+    header = open(os.path.join(REPO, "include", "dvmvs_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    lib = N.lib()
+    protos = re.findall(r"\b(?:int|const char\*)\s+(dvmvs_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header)
+    assert len(protos) >= 30
+
+    def c_class(param):
+        param = param.strip()
+        if param in ("void", ""):
+            return None
+        if "*" in param or "dvmvs_stream_t" in param:
+            return "ptr"
+        base = re.sub(r"\b(const|unsigned|signed)\b", "", param).split()
+        kinds = {"int": "int", "float": "float", "double": "double"}
+        if "long" in base:
+            return "longlong"
+        return kinds[base[0]]
+
+    ok = {"ptr": (ctypes.c_void_p, ctypes.c_char_p), "int": (ctypes.c_int, ctypes.c_uint), "longlong": (ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_size_t),
+          "float": (ctypes.c_float,), "double": (ctypes.c_double,)}
+    checked = 0
+    for name, params in protos:
+        want = [c for c in (c_class(q) for q in params.split(",")) if c is not None]
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            assert not want or name in ("dvmvs_abi_version", "dvmvs_kernel_launch_count", "dvmvs_last_error_string"), \
+                "%s takes %d arguments but the binding declares no argtypes" % (name, len(want))
+            continue
+        assert len(fn.argtypes) == len(want), "%s: header has %d parameters, binding declares %d" % (name, len(want), len(fn.argtypes))
+        for i, (kind, at) in enumerate(zip(want, fn.argtypes)):
+            is_ptr = isinstance(at, type) and (issubclass(at, ctypes._Pointer) or at in ok["ptr"])
+            assert (kind == "ptr" and is_ptr) or (kind != "ptr" and at in ok[kind]), "%s parameter %d: header %s, binding %s" % (name, i, kind, at)
+        checked += 1
+    assert checked >= 25, checked
+
+
 def test_desc_structs_match_header_field_order():
     """The ctypes mirrors must list exactly the fields of the C structs, in order (a mismatch corrupts memory)."""
     from dvmvs import _native as N
